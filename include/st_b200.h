@@ -1,0 +1,194 @@
+/* st_b200.h -- C ABI of libst_b200.so: the sm_100a kernels behind smart-tree's hot path.
+ *
+ * smart-tree itself holds no native code: its arithmetic lives in three un-vendored
+ * third-party packages (spconv, FRNN, cugraph/cudf/cupy).  Each group of
+ * entry points below replaces the native calls the reference reaches through one Python
+ * call site; the call site is cited as file:line under /root/reference/.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host
+ *   - the CALLER allocates every output and workspace (sizes via *_workspace_bytes or the
+ *     stated worst-case bounds); the library never allocates, never frees, holds no state
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it; functions that
+ *     return a count through an *_host pointer synchronise that stream before returning
+ *   - return value: 0 = ok, negative = error; st_last_error() gives the thread-local text
+ *   - features are fp32 row-major; coordinates int32 (batch, z, y, x) with
+ *     0 <= z,y,x < 65534 and 0 <= batch < 32768; graph indices int32
+ */
+#ifndef ST_B200_H
+#define ST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ST_OK 0
+#define ST_ERR_ARG (-1)
+#define ST_ERR_CUDA (-2)
+#define ST_ERR_WORKSPACE (-3)
+#define ST_ERR_UNSUPPORTED (-4)
+
+#define ST_ACT_RELU 1
+
+int st_version(void);
+const char *st_last_error(void);
+/* 0 if `device` is sm_100 or newer, ST_ERR_UNSUPPORTED otherwise. */
+int st_device_check(int device);
+int st_sm_count(int device);
+
+/* ------------------------------------------------------------------ K1 voxelise
+ * replaces spconv.pytorch.utils.PointToVoxel(...).generate_voxel_with_id with
+ * max_num_points_per_voxel=1          smart_tree/dataset/dataset.py:199-216
+ * Batched over blocks: point i belongs to block point_block[i] (or block 0 if NULL); block b
+ * has range lo = block_lo[b*3..], grid = block_grid[b*3..] (xyz order; grid =
+ * round((hi-lo)/vsize) computed by the caller).  coordinate c = floor((p-lo)/vsize) (fp32);
+ * points with c<0 or c>=grid are dropped (pc_voxel_id -1).  The first point (lowest index)
+ * of a voxel is its representative; voxels are numbered in first-appearance order.
+ *   points[n, ld] (xyz first) ; pc_voxel_id[n] ; rep_point[n] ; coords[n,4]=(b,z,y,x)
+ *   *n_voxels_host receives M.                                                        */
+size_t st_voxelize_workspace_bytes(int64_t n);
+int st_voxelize(const float *points, int64_t n, int ld, const int32_t *point_block,
+                const float *block_lo, const int32_t *block_grid, int32_t n_blocks, float vsize,
+                int32_t *pc_voxel_id, int32_t *rep_point, int32_t *coords,
+                int64_t *n_voxels_host, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ K2 coordinate table + sub-manifold map
+ * replaces spconv ops.get_indice_pairs(subm=True) reached from every SubMConv3d.forward
+ *                                      smart_tree/model/model_blocks.py:24-32,123-144,258-282
+ * Hash table: `capacity` slots (power of two >= 2n, see st_hash_capacity), keys u64, vals i32.
+ * nbr[27, n]: row of the active voxel at coords[i] + (kz-1,ky-1,kx-1), k=(kz*3+ky)*3+kx, or -1.
+ * Coordinates are unbounded: no spatial_shape clipping.           */
+int64_t st_hash_capacity(int64_t n);
+int st_hash_build(const int32_t *coords, int64_t n, uint64_t *keys, int32_t *vals,
+                  int64_t capacity, void *stream);
+int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *keys, const int32_t *vals,
+                int64_t capacity, int32_t *nbr, void *stream);
+
+/* ------------------------------------------------------------------ K3 strided / inverse conv maps
+ * replaces spconv generate_conv_inds for SparseConv3d(k=3,s=2,p=1,indice_key) and the reuse of
+ * that rulebook by SparseInverseConv3d   smart_tree/model/model_blocks.py:57-70,90-100
+ * Step 1: out_coords = sorted unique { (b, (p+1-k)/2) } ; *n_out_host receives M (M <= 8n;
+ *         out_coords must hold 8n rows).  Step 2 (after the caller built the hash of
+ *         out_coords): down[27,M] = input row feeding output o through tap k (p = 2o-1+k),
+ *         up[27,n] = output row fed by input p through tap k; -1 where absent.           */
+size_t st_strided_coords_workspace_bytes(int64_t n);
+int st_strided_coords(const int32_t *coords, int64_t n, int32_t *out_coords,
+                      int64_t *n_out_host, void *workspace, size_t workspace_bytes, void *stream);
+int st_strided_maps(const int32_t *coords, int64_t n, int64_t n_out, const uint64_t *out_keys,
+                    const int32_t *out_vals, int64_t out_capacity, int32_t *down, int32_t *up,
+                    void *stream);
+
+/* ------------------------------------------------------------------ K4/K5/K6 gather convolution, fused epilogue
+ * replaces spconv Fsp.indice_subm_conv / indice_conv / indice_inverse_conv (ConvAlgo.Native)
+ * followed by nn.BatchNorm1d(eval), the residual add, nn.ReLU and torch.cat
+ *                                      smart_tree/model/model_blocks.py:33-34,68-69,99-100,148-156,238-240
+ *   out[i, :] = act( scale * sum_k W[k] . in[map[k, i], :] + shift + residual[i, :] )
+ * map[ntaps, n_out] (NULL with ntaps==1 means the identity map: a 1x1 conv / nn.Linear),
+ * w[ntaps, cin, cout] (the spconv weight [cout,kz,ky,kx,cin] transposed by the caller),
+ * scale/shift/residual may be NULL; in_ld/out_ld/res_ld are row strides in floats so that
+ * a conv can read from / write into a column slice of a wider buffer (the skip concat).
+ * Optional second input (fused ResBlock identity 1x1 conv): adds w2[cin2,cout] . in2[i,:]
+ * after the affine, before the activation.                                             */
+int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps,
+                   const float *w, int cin, int cout, const float *scale, const float *shift,
+                   const float *residual, int res_ld, const float *in2, int in2_ld,
+                   const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
+
+/* Fused heads: the three SparseFC stacks (8->8,BN,ReLU, 8->4,BN,ReLU, 4->{1,3,2}), F.normalize,
+ * exp(radius)*direction and argmax     smart_tree/model/model.py:83-85 ; model_blocks.py:258-282 ;
+ *                                      smart_tree/model/model_inference.py:87-88
+ * params: packed fp32 block described in smart-tree_b200/engine.py (pack_heads).
+ * Outputs (any may be NULL): radius[n] (log radius), direction[n,3] (unit), class_logits[n,2],
+ * medial_vector[n,3], class_l[n] (int32 argmax, first maximum).                         */
+int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params, float *radius,
+                   float *direction, float *class_logits, float *medial_vector,
+                   int32_t *class_l, void *stream);
+
+/* ------------------------------------------------------------------ K7 fixed-radius kNN
+ * replaces frnn.frnn_grid_points(p1, p2, len1, len2, K, r, return_sorted=True)
+ *                                      smart_tree/skeleton/graph.py:15-24
+ * K nearest of dst[m,3] within radius r of each src[n,3]: d2 = (dx*dx+dy*dy)+dz*dz < r*r,
+ * ascending (d2, index); idx[n,K] (-1 padded), d2[n,K] (-1 padded).  K <= 32.
+ * query_radius (optional, [n]): additionally restrict query i to d <= query_radius[i]
+ * (exactly the reference's later `idxs[dists > radii] = -1`).                           */
+size_t st_knn_workspace_bytes(int64_t m);
+int st_knn(const float *src, int64_t n, const float *dst, int64_t m, int K, float r,
+           const float *query_radius, int32_t *idx, float *d2, void *workspace,
+           size_t workspace_bytes, void *stream);
+
+/* outlier_removal                      smart_tree/skeleton/filter.py:6-11
+ * keep[i] = 1 iff the nb nearest neighbours (self included) within r=max radius all exist and
+ * have sqrt(d2) < radii[i].                                                             */
+int st_outlier_mask(const float *points, int64_t n, const float *radii, float r_max, int nb,
+                    uint8_t *keep, void *workspace, size_t workspace_bytes, void *stream);
+
+/* nn_graph + make_edges                smart_tree/skeleton/graph.py:36-40,52-60
+ * From a kNN result: drop neighbour if sqrt(d2) > radii[i]; emit (i, j, sqrt(d2)) for j > 0
+ * (sic), row-major order.  edges[n*K,2], weights[n*K]; *n_edges_host receives E.         */
+size_t st_edges_workspace_bytes(int64_t n, int K);
+int st_edges_from_knn(const int32_t *idx, const float *d2, int64_t n, int K, const float *radii,
+                      int32_t *edges, float *weights, int64_t *n_edges_host, void *workspace,
+                      size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ K8 connected components
+ * replaces cugraph.connected_components on Graph(directed=False, renumber=False)
+ *                                      smart_tree/data_types/graph.py:32-51
+ * label[v] = smallest vertex id of v's component; size[v] = component size (at every v).   */
+int st_connected_components(const int32_t *edges, int64_t n_edges, int64_t n, int32_t *label,
+                            int32_t *size, void *stream);
+
+/* ------------------------------------------------------------------ K9 shortest paths
+ * replaces cugraph.sssp (twice)        smart_tree/skeleton/shortest_path.py:12-21 ;
+ *                                      smart_tree/skeleton/skeletonize.py:73-85
+ * Undirected weighted graph given as CSR over arcs (both directions, self loops removed):
+ * row_ptr[n+1], col[A], w[A].  sources[s]: dist 0 there.  dist = least fixed point of
+ * d[v] = min_u fl32(d[u]+w); pred[v] = lowest u with fl32(d[u]+w)==d[v] (-1 at sources and
+ * unreachable, dist FLT_MAX there).  st_csr_build makes the CSR from an edge list.        */
+size_t st_csr_workspace_bytes(int64_t n, int64_t n_edges);
+int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, int64_t n,
+                 int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host,
+                 void *workspace, size_t workspace_bytes, void *stream);
+int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n,
+            const int32_t *sources, int32_t n_sources, float *dist, int32_t *pred,
+            int32_t *sweeps_host, void *ctl_workspace /* 256 B, device */, void *stream);
+/* pred_graph + second sssp             smart_tree/skeleton/shortest_path.py:46-55
+ * tree_dist[v] = tree_dist[pred[v]] + ||p_v - p_pred(v)||, 0 at roots (pred<0 & reachable
+ * flag), FLT_MAX where unreachable[v] != 0.                                              */
+int st_tree_distances(const float *points, const int32_t *pred, const uint8_t *is_root,
+                      int64_t n, float *tree_dist, void *ctl_workspace /* 256 B, device */,
+                      void *stream);
+
+/* ------------------------------------------------------------------ K10 greedy branch extraction
+ * replaces sample_tree / trace_route / select_path_points (torch + one FRNN call per branch)
+ *                                      smart_tree/skeleton/path.py:9-140
+ * Batched over components: component c owns vertices [comp_off[c], comp_off[c+1]); pred is
+ * component-local (-1 at the root); all quirks of SURVEY Appendix E are reproduced.
+ * The uniform grid used to claim points near a path has cell size `cell_size` (enlarged if it
+ * would exceed the cell budget); any positive value gives identical results.
+ * Outputs are SEGMENT-LOCAL: component c writes into [comp_off[c], comp_off[c+1]) of
+ * path_vertices[n] (component-local vertex ids, branch after branch, root side first),
+ * branch_len[n] and branch_parent[n] (one entry per emitted branch, in emission order = branch
+ * id); comp_n_branches[c] / comp_n_path[c] give how many entries of the segment are valid.   */
+size_t st_sample_tree_workspace_bytes(int64_t n, int32_t n_comp);
+int st_sample_tree(const float *medial_pts, const float *radii, const int32_t *pred,
+                   const float *tree_dist, const int32_t *comp_off, int32_t n_comp, int64_t n,
+                   float cell_size, int32_t *path_vertices, int32_t *branch_len,
+                   int32_t *branch_parent, int32_t *comp_n_branches, int32_t *comp_n_path,
+                   void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------ K11 point -> tapered tube projection (repair)
+ * replaces pts_to_nearest_tube_gpu     smart_tree/util/queries.py:89-133
+ * For query q (one per branch): tubes [tube_off[q], tube_off[q+1]) of a[.,3], b[.,3], r1, r2;
+ * t = clip((p-a).(b-a)/(b-a).(b-a), 0, 1); picks argmin |dist - r(t)| (first minimum);
+ * out_vec[q,3] = projection - p ; out_idx[q] (tube index local to the query); out_r[q].   */
+int st_points_to_tubes(const float *pts, int64_t n_q, const float *a, const float *b,
+                       const float *r1, const float *r2, const int32_t *tube_off,
+                       float *out_vec, int32_t *out_idx, float *out_r, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ST_B200_H */

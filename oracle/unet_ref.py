@@ -45,9 +45,10 @@ def point_to_voxel(points: np.ndarray, vsize: float, lo: np.ndarray, hi: np.ndar
     vs = np.float32(vsize)
     lo = np.asarray(lo, np.float32)
     hi = np.asarray(hi, np.float32)
-    # std::round on float: half away from zero
+    # std::round on float: half away from zero (q >= 0 here); evaluated exactly via trunc + fraction
     q = (hi - lo) / vs
-    grid = np.where(q >= 0, np.floor(q + np.float32(0.5)), np.ceil(q - np.float32(0.5))).astype(np.int64)
+    t = np.trunc(q)
+    grid = (t + ((q - t) >= np.float32(0.5))).astype(np.int64)
     c = np.floor((points[:, :3] - lo) / vs).astype(np.int64)          # fp32 sub, fp32 div, floor
     ok = np.all((c >= 0) & (c < grid), axis=1)
     lin = (c[:, 2] * (grid[1] + 1) + c[:, 1]) * (grid[0] + 1) + c[:, 0]

@@ -1,0 +1,317 @@
+// Gather convolution (sub-manifold / strided / inverse / 1x1) with fused BN-affine, residual,
+// fused ResBlock-identity 1x1 conv, ReLU and concat-slice store; fused prediction heads.
+//
+// fp32 FMA path: out[i,:] = act(scale * sum_k W[k] . in[map[k,i],:] + shift + res[i,:] + W2 . in2[i,:])
+//   - one thread owns RT output rows x CT output channels (accumulators in registers)
+//   - the [CIN x COUT] weight tile of each tap is staged in shared memory with cp.async,
+//     double buffered, and read as warp-broadcast LDS.128
+//   - neighbour rows are read with 128-bit loads straight from L2/L1 (every feature array of
+//     the network is L2 resident on B200: <= 16 MB per tensor at 250k voxels)
+//   - taps for which no lane of the warp has a neighbour are skipped (decoder: <= 8 of 27)
+#include "common.cuh"
+
+using namespace st;
+
+struct ConvArgs {
+    const float *in;
+    int in_ld;
+    const int32_t *map;
+    int n_out;
+    int ntaps;
+    const float *w;
+    int cin, cout;
+    const float *scale, *shift;
+    const float *res;
+    int res_ld;
+    const float *in2;
+    int in2_ld;
+    const float *w2;
+    int cin2;
+    float *out;
+    int out_ld;
+    int act;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int CIN, int COUT>
+struct ConvCfg {
+    static constexpr int THREADS = 256;
+    static constexpr int CT = COUT >= 16 ? 16 : COUT;   // output channels per thread
+    static constexpr int TPR = COUT / CT;               // threads per output row
+    static constexpr int RT = 2;                        // rows per thread
+    static constexpr int ROW_SLOTS = THREADS / TPR;
+    static constexpr int ROWS = ROW_SLOTS * RT;         // rows per CTA
+    static constexpr int TAP_FLOATS = CIN * COUT;
+    static constexpr int TPS_RAW = 4096 / TAP_FLOATS;   // taps per 16 KB stage
+    static constexpr int TPS = TPS_RAW < 1 ? 1 : (TPS_RAW > 27 ? 27 : TPS_RAW);
+    static constexpr int STAGE_FLOATS = TPS * TAP_FLOATS;
+    static constexpr int SMEM_BYTES = 2 * STAGE_FLOATS * 4;
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(256) k_conv_fma(ConvArgs a) {
+    using C = ConvCfg<CIN, COUT>;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int cg = tid % C::TPR;
+    const int slot = tid / C::TPR;
+    const int row0 = blockIdx.x * C::ROWS + slot;
+    int rows[C::RT];
+#pragma unroll
+    for (int r = 0; r < C::RT; ++r) rows[r] = row0 + r * C::ROW_SLOTS;
+
+    float acc[C::RT][C::CT];
+#pragma unroll
+    for (int r = 0; r < C::RT; ++r)
+#pragma unroll
+        for (int c = 0; c < C::CT; ++c) acc[r][c] = 0.f;
+
+    const int nstages = (a.ntaps + C::TPS - 1) / C::TPS;
+    auto issue = [&](int s) {
+        int t0 = s * C::TPS;
+        int nt = min(C::TPS, a.ntaps - t0);
+        const float *src = a.w + (size_t)t0 * C::TAP_FLOATS;
+        float *dst = smem + (s & 1) * C::STAGE_FLOATS;
+        for (int i = tid * 4; i < nt * C::TAP_FLOATS; i += C::THREADS * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue(0);
+    for (int s = 0; s < nstages; ++s) {
+        if (s + 1 < nstages) { issue(s + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const float *ws = smem + (s & 1) * C::STAGE_FLOATS;
+        const int t0 = s * C::TPS;
+        const int nt = min(C::TPS, a.ntaps - t0);
+        for (int t = 0; t < nt; ++t) {
+            const int k = t0 + t;
+            int j[C::RT];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) {
+                j[r] = -1;
+                if (rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+                any |= j[r] >= 0;
+            }
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float *wt = ws + t * C::TAP_FLOATS + cg * C::CT;
+#pragma unroll
+            for (int ci4 = 0; ci4 < CIN / 4; ++ci4) {
+                float4 x[C::RT];
+#pragma unroll
+                for (int r = 0; r < C::RT; ++r)
+                    x[r] = j[r] >= 0 ? __ldg((const float4 *)(a.in + (size_t)j[r] * a.in_ld) + ci4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int co4 = 0; co4 < C::CT / 4; ++co4) {
+                        float4 w4 = *(const float4 *)(wt + (ci4 * 4 + c) * COUT + co4 * 4);
+#pragma unroll
+                        for (int r = 0; r < C::RT; ++r) {
+                            float xv = c == 0 ? x[r].x : c == 1 ? x[r].y : c == 2 ? x[r].z : x[r].w;
+                            acc[r][co4 * 4 + 0] = fmaf(xv, w4.x, acc[r][co4 * 4 + 0]);
+                            acc[r][co4 * 4 + 1] = fmaf(xv, w4.y, acc[r][co4 * 4 + 1]);
+                            acc[r][co4 * 4 + 2] = fmaf(xv, w4.z, acc[r][co4 * 4 + 2]);
+                            acc[r][co4 * 4 + 3] = fmaf(xv, w4.w, acc[r][co4 * 4 + 3]);
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- epilogue: affine, residual, fused identity 1x1 conv, activation, slice store
+    const int co0 = cg * C::CT;
+#pragma unroll
+    for (int r = 0; r < C::RT; ++r) {
+        const int row = rows[r];
+        if (row >= a.n_out) continue;
+        float v[C::CT];
+#pragma unroll
+        for (int c = 0; c < C::CT; ++c) {
+            float sc = a.scale ? __ldg(a.scale + co0 + c) : 1.f;
+            float sh = a.shift ? __ldg(a.shift + co0 + c) : 0.f;
+            v[c] = fmaf(acc[r][c], sc, sh);
+        }
+        if (a.res) {
+#pragma unroll
+            for (int c4 = 0; c4 < C::CT / 4; ++c4) {
+                float4 rr = __ldg((const float4 *)(a.res + (size_t)row * a.res_ld + co0) + c4);
+                v[c4 * 4 + 0] += rr.x; v[c4 * 4 + 1] += rr.y; v[c4 * 4 + 2] += rr.z; v[c4 * 4 + 3] += rr.w;
+            }
+        }
+        if (a.in2) {
+            float e[C::CT];
+#pragma unroll
+            for (int c = 0; c < C::CT; ++c) e[c] = 0.f;
+            const float *xr = a.in2 + (size_t)row * a.in2_ld;
+            for (int ci = 0; ci < a.cin2; ++ci) {
+                float xv = __ldg(xr + ci);
+#pragma unroll
+                for (int c4 = 0; c4 < C::CT / 4; ++c4) {
+                    float4 w4 = __ldg((const float4 *)(a.w2 + (size_t)ci * COUT + co0) + c4);
+                    e[c4 * 4 + 0] = fmaf(xv, w4.x, e[c4 * 4 + 0]);
+                    e[c4 * 4 + 1] = fmaf(xv, w4.y, e[c4 * 4 + 1]);
+                    e[c4 * 4 + 2] = fmaf(xv, w4.z, e[c4 * 4 + 2]);
+                    e[c4 * 4 + 3] = fmaf(xv, w4.w, e[c4 * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < C::CT; ++c) v[c] += e[c];
+        }
+        if (a.act & ST_ACT_RELU) {
+#pragma unroll
+            for (int c = 0; c < C::CT; ++c) v[c] = fmaxf(v[c], 0.f);
+        }
+        float4 *o = (float4 *)(a.out + (size_t)row * a.out_ld + co0);
+#pragma unroll
+        for (int c4 = 0; c4 < C::CT / 4; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+    }
+}
+
+// Generic fallback for channel counts outside the tuned set (e.g. the 3->8 stem):
+// one thread per (row, output channel).
+__global__ void k_conv_generic(ConvArgs a) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)a.n_out * a.cout) return;
+    int row = (int)(idx / a.cout), co = (int)(idx % a.cout);
+    float acc = 0.f;
+    for (int k = 0; k < a.ntaps; ++k) {
+        int j = a.map ? __ldg(a.map + (size_t)k * a.n_out + row) : row;
+        if (j < 0) continue;
+        const float *x = a.in + (size_t)j * a.in_ld;
+        const float *w = a.w + (size_t)k * a.cin * a.cout + co;
+        for (int ci = 0; ci < a.cin; ++ci) acc = fmaf(__ldg(x + ci), __ldg(w + (size_t)ci * a.cout), acc);
+    }
+    float v = fmaf(acc, a.scale ? a.scale[co] : 1.f, a.shift ? a.shift[co] : 0.f);
+    if (a.res) v += a.res[(size_t)row * a.res_ld + co];
+    if (a.in2) {
+        float e = 0.f;
+        for (int ci = 0; ci < a.cin2; ++ci) e = fmaf(a.in2[(size_t)row * a.in2_ld + ci], a.w2[(size_t)ci * a.cout + co], e);
+        v += e;
+    }
+    if (a.act & ST_ACT_RELU) v = fmaxf(v, 0.f);
+    a.out[(size_t)row * a.out_ld + co] = v;
+}
+
+template <int CIN, int COUT>
+static int launch_fma(const ConvArgs &a, cudaStream_t s) {
+    using C = ConvCfg<CIN, COUT>;
+    static bool attr_set = false;
+    if (!attr_set && C::SMEM_BYTES > 48 * 1024) {
+        ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_fma<CIN, COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    unsigned grid = (unsigned)cdiv(a.n_out, C::ROWS);
+    k_conv_fma<CIN, COUT><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *w,
+                              int cin, int cout, const float *scale, const float *shift, const float *residual,
+                              int res_ld, const float *in2, int in2_ld, const float *w2, int cin2, float *out,
+                              int out_ld, int act, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_out == 0) return ST_OK;
+    ST_REQUIRE(n_out < (1ll << 31), "n_out");
+    ST_REQUIRE(ntaps >= 1 && (map != nullptr || ntaps == 1), "identity map requires ntaps == 1");
+    ST_REQUIRE(!in2 || w2, "in2 needs w2");
+    ConvArgs a{in, in_ld, map, (int)n_out, ntaps, w, cin, cout, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
+    bool fast = aligned16(in) && aligned16(out) && aligned16(w) && (in_ld % 4 == 0) && (out_ld % 4 == 0) &&
+                (!residual || (aligned16(residual) && res_ld % 4 == 0)) && (!w2 || aligned16(w2));
+    if (fast) {
+#define ST_CASE(CI, CO) if (cin == CI && cout == CO) return launch_fma<CI, CO>(a, s);
+        ST_CASE(8, 8) ST_CASE(8, 16) ST_CASE(16, 8) ST_CASE(16, 16) ST_CASE(16, 32) ST_CASE(32, 16)
+        ST_CASE(32, 32) ST_CASE(32, 64) ST_CASE(64, 32) ST_CASE(64, 64) ST_CASE(8, 4) ST_CASE(4, 4)
+#undef ST_CASE
+    }
+    int64_t total = n_out * cout;
+    k_conv_generic<<<(unsigned)cdiv(total, 256), 256, 0, s>>>(a);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ fused heads
+// params (floats): for head h in {radius(k=1), direction(k=3), class(k=2)}:
+//   W1[8][8] (ci-major), s1[8], b1[8], W2[8][4], s2[4], b2[4], W3[4][k], b3[k]
+constexpr int HEAD_FIXED = 64 + 8 + 8 + 32 + 4 + 4;
+__host__ __device__ constexpr int head_size(int k) { return HEAD_FIXED + 5 * k; }
+constexpr int HEADS_TOTAL = head_size(1) + head_size(3) + head_size(2);
+
+template <int K>
+__device__ __forceinline__ void run_head(const float *__restrict__ p, const float x[8], float out[K]) {
+    float h1[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(x[i], p[i * 8 + o], acc);
+        h1[o] = fmaxf(fmaf(acc, p[64 + o], p[72 + o]), 0.f);
+    }
+    const float *q = p + 80;
+    float h2[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc = fmaf(h1[i], q[i * 4 + o], acc);
+        h2[o] = fmaxf(fmaf(acc, q[32 + o], q[36 + o]), 0.f);
+    }
+    const float *t = q + 40;
+#pragma unroll
+    for (int o = 0; o < K; ++o) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc = fmaf(h2[i], t[i * K + o], acc);
+        out[o] = acc + t[4 * K + o];
+    }
+}
+
+__global__ void __launch_bounds__(256) k_heads(const float *__restrict__ in, int in_ld, int n, const float *__restrict__ params,
+                                               float *__restrict__ radius, float *__restrict__ direction,
+                                               float *__restrict__ logits, float *__restrict__ medial, int32_t *__restrict__ cls) {
+    __shared__ float sp[HEADS_TOTAL];
+    for (int i = threadIdx.x; i < HEADS_TOTAL; i += blockDim.x) sp[i] = params[i];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float x[8];
+    const float4 *xr = (const float4 *)(in + (size_t)i * in_ld);
+    float4 a = __ldg(xr), b = __ldg(xr + 1);
+    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    float r[1], d[3], c[2];
+    run_head<1>(sp, x, r);
+    run_head<3>(sp + head_size(1), x, d);
+    run_head<2>(sp + head_size(1) + head_size(3), x, c);
+    // F.normalize(p=2, dim=1, eps=1e-12)
+    float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
+    float den = fmaxf(nrm, 1e-12f);
+    d[0] = __fdiv_rn(d[0], den); d[1] = __fdiv_rn(d[1], den); d[2] = __fdiv_rn(d[2], den);
+    if (radius) radius[i] = r[0];
+    if (direction) { direction[3 * (size_t)i] = d[0]; direction[3 * (size_t)i + 1] = d[1]; direction[3 * (size_t)i + 2] = d[2]; }
+    if (logits) { logits[2 * (size_t)i] = c[0]; logits[2 * (size_t)i + 1] = c[1]; }
+    if (medial) {
+        float e = expf(r[0]);
+        medial[3 * (size_t)i] = e * d[0]; medial[3 * (size_t)i + 1] = e * d[1]; medial[3 * (size_t)i + 2] = e * d[2];
+    }
+    if (cls) cls[i] = c[1] > c[0] ? 1 : 0;
+}
+
+extern "C" int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params, float *radius, float *direction,
+                              float *class_logits, float *medial_vector, int32_t *class_l, void *stream) {
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(aligned16(in) && in_ld % 4 == 0, "heads input must be 16-byte aligned rows");
+    k_heads<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, (int)n, params, radius, direction,
+                                                                        class_logits, medial_vector, class_l);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

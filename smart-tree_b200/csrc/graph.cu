@@ -1,0 +1,393 @@
+// Connected components (lock-free union-find, root = smallest vertex id), CSR build,
+// single/multi-source shortest paths (pull-based fp32 relaxation to the least fixed point in a
+// resident persistent grid), deterministic predecessors, tree path lengths, tube projection.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+using namespace st;
+
+// ------------------------------------------------------------------------------------ connected components
+__device__ __forceinline__ int uf_find(int32_t *parent, int v) {
+    int p = parent[v];
+    while (p != v) {
+        int gp = parent[p];
+        if (gp != p) parent[v] = gp;  // path halving (benign race: only ever moves towards the root)
+        v = p;
+        p = gp;
+    }
+    return v;
+}
+
+__global__ void k_cc_init(int32_t *parent, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) parent[i] = i;
+}
+
+__global__ void k_cc_hook(const int32_t *__restrict__ edges, int64_t ne, int32_t *parent) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int u = edges[2 * e], v = edges[2 * e + 1];
+    if (u == v) return;
+    int ru = uf_find(parent, u), rv = uf_find(parent, v);
+    while (ru != rv) {
+        if (ru < rv) { int t = ru; ru = rv; rv = t; }          // ru = larger root, rv = smaller
+        int old = atomicCAS(parent + ru, ru, rv);               // hang the larger root under the smaller
+        if (old == ru) break;
+        ru = uf_find(parent, old);
+        rv = uf_find(parent, rv);
+    }
+}
+
+__global__ void k_cc_flatten(int32_t *parent, int n, int32_t *size) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = i;
+    while (true) { int p = parent[r]; if (p == r) break; r = p; }
+    parent[i] = r;      // racing writers all write a value on the path to the same root
+    atomicAdd(size + r, 1);
+}
+
+__global__ void k_cc_sizes(const int32_t *__restrict__ label, int n, int32_t *size) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = label[i];
+    if (r != i) size[i] = size[r];
+}
+
+__global__ void k_cc_relabel(int32_t *label, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = label[i];
+    while (true) { int p = label[r]; if (p == r) break; r = p; }
+    label[i] = r;
+}
+
+extern "C" int st_connected_components(const int32_t *edges, int64_t n_edges, int64_t n, int32_t *label, int32_t *size, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    unsigned g = (unsigned)cdiv(n, 256);
+    k_cc_init<<<g, 256, 0, s>>>(label, (int)n);
+    ST_CHECK_LAUNCH();
+    if (n_edges) {
+        k_cc_hook<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, label);
+        ST_CHECK_LAUNCH();
+    }
+    k_cc_relabel<<<g, 256, 0, s>>>(label, (int)n);   // two passes: after the first every entry points at a root
+    ST_CHECK_LAUNCH();
+    ST_CHECK_CUDA(cudaMemsetAsync(size, 0, n * 4, s));
+    k_cc_flatten<<<g, 256, 0, s>>>(label, (int)n, size);
+    ST_CHECK_LAUNCH();
+    k_cc_sizes<<<g, 256, 0, s>>>(label, (int)n, size);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ CSR
+__global__ void k_csr_degree(const int32_t *__restrict__ edges, int64_t ne, int32_t *deg) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int u = edges[2 * e], v = edges[2 * e + 1];
+    if (u == v) return;
+    atomicAdd(deg + u, 1);
+    atomicAdd(deg + v, 1);
+}
+
+__global__ void k_csr_fill(const int32_t *__restrict__ edges, const float *__restrict__ weights, int64_t ne,
+                           const int32_t *__restrict__ row_ptr, int32_t *cursor, int32_t *__restrict__ col, float *__restrict__ w) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    int u = edges[2 * e], v = edges[2 * e + 1];
+    if (u == v) return;
+    float ww = weights[e];
+    int pu = row_ptr[u] + atomicAdd(cursor + u, 1);
+    col[pu] = v; w[pu] = ww;
+    int pv = row_ptr[v] + atomicAdd(cursor + v, 1);
+    col[pv] = u; w[pv] = ww;
+}
+
+extern "C" size_t st_csr_workspace_bytes(int64_t n, int64_t n_edges) {
+    size_t scan = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan, (int *)nullptr, (int *)nullptr, (int)(n + 1));
+    return align_up(scan) + 2 * align_up((n + 1) * 4) + 1024;
+}
+
+extern "C" int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, int64_t n, int32_t *row_ptr,
+                            int32_t *col, float *w, int64_t *n_arcs_host, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    *n_arcs_host = 0;
+    if (n == 0) return ST_OK;
+    Carver cv(workspace, workspace_bytes);
+    int32_t *deg = cv.take<int32_t>(n + 1);
+    int32_t *cursor = cv.take<int32_t>(n + 1);
+    size_t scan_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, deg, row_ptr, (int)(n + 1));
+    void *scan_ws = cv.take<char>(scan_bytes);
+    if (!cv.ok()) { set_error("st_csr_build: workspace too small"); return ST_ERR_WORKSPACE; }
+    ST_CHECK_CUDA(cudaMemsetAsync(deg, 0, (n + 1) * 4, s));
+    ST_CHECK_CUDA(cudaMemsetAsync(cursor, 0, (n + 1) * 4, s));
+    if (n_edges) {
+        k_csr_degree<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, deg);
+        ST_CHECK_LAUNCH();
+    }
+    ST_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, deg, row_ptr, (int)(n + 1), s));
+    if (n_edges) {
+        k_csr_fill<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, weights, n_edges, row_ptr, cursor, col, w);
+        ST_CHECK_LAUNCH();
+    }
+    int32_t arcs = 0;
+    ST_CHECK_CUDA(cudaMemcpyAsync(&arcs, row_ptr + n, 4, cudaMemcpyDeviceToHost, s));
+    ST_CHECK_CUDA(cudaStreamSynchronize(s));
+    *n_arcs_host = arcs;
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ resident-grid barrier
+// All CTAs are co-resident (cooperative launch).  `ctr` counts arrivals monotonically.
+__device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        ++phase;
+        unsigned target = phase * gridDim.x;
+        atomicAdd(ctr, 1u);
+        while (*(volatile unsigned *)ctr < target) { __nanosleep(32); }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------ SSSP
+// Pull-based chaotic relaxation: every thread owns a few vertices and keeps re-evaluating
+// d[v] = min(d[v], min_u fl32(d[u] + w(u,v))) with L2-coherent loads.  fl32(+) is monotone, so any
+// schedule converges to the same least fixed point (== fp32 Dijkstra).  Grid barriers only every
+// `PASSES` local passes; stop after a whole chunk in which nothing changed.
+constexpr int SSSP_PASSES = 16;
+constexpr float ST_INF = __builtin_huge_valf();
+
+struct SsspCtl {
+    unsigned barrier;
+    unsigned changed[3];
+    unsigned chunks;
+};
+
+__global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                              const float *__restrict__ w, int n, float *dist, SsspCtl *ctl) {
+    unsigned phase = 0;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned chunk = 0;; ++chunk) {
+        bool changed = false;
+        for (int pass = 0; pass < SSSP_PASSES; ++pass) {
+            for (int v = t0; v < n; v += stride) {
+                float cur = __ldcg(dist + v);
+                float best = cur;
+                int b = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
+                for (int a = b; a < e; ++a) {
+                    float c = __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a));
+                    best = fminf(best, c);
+                }
+                if (best < cur) { __stcg(dist + v, best); changed = true; }
+            }
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->changed[(chunk + 1) % 3] = 0;
+        grid_barrier(&ctl->barrier, phase);
+        unsigned any = *(volatile unsigned *)&ctl->changed[chunk % 3];
+        if (!any) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->chunks = chunk + 1;
+            break;
+        }
+    }
+}
+
+__global__ void k_sssp_init(float *dist, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dist[i] = ST_INF;
+}
+
+__global__ void k_sssp_sources(float *dist, const int32_t *__restrict__ sources, int ns) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns) dist[sources[i]] = 0.f;
+}
+
+__global__ void k_sssp_pred(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float *__restrict__ w,
+                            int n, const float *__restrict__ dist, int32_t *__restrict__ pred) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    float dv = dist[v];
+    int best = INT_MAX;
+    if (dv != ST_INF) {
+        for (int a = row_ptr[v]; a < row_ptr[v + 1]; ++a) {
+            int u = col[a];
+            if (__fadd_rn(dist[u], w[a]) == dv) best = min(best, u);
+        }
+    }
+    pred[v] = best == INT_MAX ? -1 : best;
+}
+
+__global__ void k_sssp_finish(float *dist, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && dist[i] == ST_INF) dist[i] = FLT_MAX;
+}
+
+__global__ void k_set_pred_sources(int32_t *pred, const int32_t *__restrict__ sources, int ns) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns) pred[sources[i]] = -1;
+}
+
+static int coop_grid(const void *kernel, int threads, int device, int &blocks) {
+    int per_sm = 0, sms = 0;
+    ST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+    ST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    blocks = per_sm * sms;
+    return ST_OK;
+}
+
+extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n, const int32_t *sources,
+                       int32_t n_sources, float *dist, int32_t *pred, int32_t *sweeps_host, void *ctl_workspace, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sweeps_host) *sweeps_host = 0;
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 bytes) required");
+    int device = 0;
+    ST_CHECK_CUDA(cudaGetDevice(&device));
+    SsspCtl *ctl = (SsspCtl *)ctl_workspace;
+    ST_CHECK_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SsspCtl), s));
+    unsigned g = (unsigned)cdiv(n, 256);
+    k_sssp_init<<<g, 256, 0, s>>>(dist, (int)n);
+    ST_CHECK_LAUNCH();
+    if (n_sources) {
+        k_sssp_sources<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(dist, sources, n_sources);
+        ST_CHECK_LAUNCH();
+    }
+    int blocks = 0;
+    int rc = coop_grid((const void *)k_sssp, 256, device, blocks);
+    if (rc) return rc;
+    if (blocks > (int)g) blocks = (int)g;
+    int nn = (int)n;
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&ctl};
+    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
+    k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
+    ST_CHECK_LAUNCH();
+    k_sssp_finish<<<g, 256, 0, s>>>(dist, (int)n);
+    ST_CHECK_LAUNCH();
+    if (n_sources) {
+        k_set_pred_sources<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(pred, sources, n_sources);
+        ST_CHECK_LAUNCH();
+    }
+    if (sweeps_host) {
+        unsigned chunks = 0;
+        ST_CHECK_CUDA(cudaMemcpyAsync(&chunks, &ctl->chunks, 4, cudaMemcpyDeviceToHost, s));
+        ST_CHECK_CUDA(cudaStreamSynchronize(s));
+        *sweeps_host = (int32_t)chunks * SSSP_PASSES;
+    }
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ tree path lengths
+// td[v] = td[pred[v]] + ||p_v - p_pred||, accumulated root -> leaf in fp32 (same order as an SSSP over
+// the predecessor tree).  -1 marks "not ready"; resident threads poll their parent with L2-coherent loads.
+__global__ void __launch_bounds__(256) k_tree_dist(const float *__restrict__ pts, const int32_t *__restrict__ pred, int n,
+                                                   float *td, SsspCtl *ctl) {
+    unsigned phase = 0;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (unsigned chunk = 0;; ++chunk) {
+        bool changed = false;
+        for (int pass = 0; pass < SSSP_PASSES; ++pass) {
+            for (int v = t0; v < n; v += stride) {
+                if (__ldcg(td + v) >= 0.f) continue;
+                int p = __ldg(pred + v);
+                if (p < 0) continue;
+                float tp = __ldcg(td + p);
+                if (tp < 0.f) continue;
+                float d = sqrtf(dist2_exact(pts[3 * (size_t)v], pts[3 * (size_t)v + 1], pts[3 * (size_t)v + 2],
+                                            pts[3 * (size_t)p], pts[3 * (size_t)p + 1], pts[3 * (size_t)p + 2]));
+                __stcg(td + v, __fadd_rn(tp, d));
+                changed = true;
+            }
+        }
+        if (__syncthreads_or(changed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->changed[(chunk + 1) % 3] = 0;
+        grid_barrier(&ctl->barrier, phase);
+        unsigned any = *(volatile unsigned *)&ctl->changed[chunk % 3];
+        if (!any) break;
+    }
+}
+
+__global__ void k_tree_dist_init(const int32_t *__restrict__ pred, const uint8_t *__restrict__ is_root, int n, float *td) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    td[i] = is_root[i] ? 0.f : -1.f;
+}
+
+__global__ void k_tree_dist_finish(int n, float *td) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && td[i] < 0.f) td[i] = FLT_MAX;   // unreachable from any root
+}
+
+extern "C" int st_tree_distances(const float *points, const int32_t *pred, const uint8_t *is_root, int64_t n, float *tree_dist,
+                                 void *ctl_workspace, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 bytes) required");
+    int device = 0;
+    ST_CHECK_CUDA(cudaGetDevice(&device));
+    SsspCtl *ctl = (SsspCtl *)ctl_workspace;
+    ST_CHECK_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SsspCtl), s));
+    unsigned g = (unsigned)cdiv(n, 256);
+    k_tree_dist_init<<<g, 256, 0, s>>>(pred, is_root, (int)n, tree_dist);
+    ST_CHECK_LAUNCH();
+    int blocks = 0;
+    int rc = coop_grid((const void *)k_tree_dist, 256, device, blocks);
+    if (rc) return rc;
+    if (blocks > (int)g) blocks = (int)g;
+    int nn = (int)n;
+    void *args[] = {(void *)&points, (void *)&pred, (void *)&nn, (void *)&tree_dist, (void *)&ctl};
+    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_tree_dist, dim3(blocks), dim3(256), args, 0, s));
+    k_tree_dist_finish<<<g, 256, 0, s>>>((int)n, tree_dist);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ point -> tube (repair)
+// queries.py:89-133: t = clip(ap.ab / ab.ab, 0, 1) ; proj = a + t ab ; dist = ||proj - p|| ;
+// r = (1-t) r1 + t r2 ; argmin |dist - r| (first minimum)
+__global__ void k_points_to_tubes(const float *__restrict__ pts, int nq, const float *__restrict__ a, const float *__restrict__ b,
+                                  const float *__restrict__ r1, const float *__restrict__ r2, const int32_t *__restrict__ off,
+                                  float *__restrict__ out_vec, int32_t *__restrict__ out_idx, float *__restrict__ out_r) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    float px = pts[3 * q], py = pts[3 * q + 1], pz = pts[3 * q + 2];
+    float best = ST_INF, bvx = 0, bvy = 0, bvz = 0, br = 0;
+    int bidx = -1;
+    bool nan_first = false;
+    for (int m = off[q]; m < off[q + 1]; ++m) {
+        float ax = a[3 * m], ay = a[3 * m + 1], az = a[3 * m + 2];
+        float abx = b[3 * m] - ax, aby = b[3 * m + 1] - ay, abz = b[3 * m + 2] - az;
+        float apx = px - ax, apy = py - ay, apz = pz - az;
+        float num = apx * abx + apy * aby + apz * abz;
+        float den = abx * abx + aby * aby + abz * abz;
+        float t = fminf(fmaxf(num / den, 0.f), 1.f);
+        float qx = ax + t * abx, qy = ay + t * aby, qz = az + t * abz;
+        float dx = qx - px, dy = qy - py, dz = qz - pz;
+        float dist = sqrtf(dx * dx + dy * dy + dz * dz);
+        float r = (1.f - t) * r1[m] + t * r2[m];
+        float score = fabsf(dist - r);
+        if (score != score && bidx < 0) { nan_first = true; }
+        if (score < best) { best = score; bidx = m - off[q]; bvx = dx; bvy = dy; bvz = dz; br = r; }
+    }
+    (void)nan_first;
+    out_vec[3 * q] = bvx; out_vec[3 * q + 1] = bvy; out_vec[3 * q + 2] = bvz;
+    out_idx[q] = bidx;
+    out_r[q] = br;
+}
+
+extern "C" int st_points_to_tubes(const float *pts, int64_t n_q, const float *a, const float *b, const float *r1, const float *r2,
+                                  const int32_t *tube_off, float *out_vec, int32_t *out_idx, float *out_r, void *stream) {
+    if (n_q == 0) return ST_OK;
+    k_points_to_tubes<<<(unsigned)cdiv(n_q, 128), 128, 0, (cudaStream_t)stream>>>(pts, (int)n_q, a, b, r1, r2, tube_off, out_vec, out_idx, out_r);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

@@ -1,0 +1,223 @@
+"""Fused Smart_Tree inference engine: compiles a reference state_dict into a layer plan
+(BN folded into a per-channel affine epilogue, weights transposed to [tap, cin, cout], heads
+packed) and runs the whole network on libst_b200 kernels.
+
+Architecture follows /root/reference/smart_tree/model/model.py:77-87 and
+model_blocks.py:107-243 as found in the shipped checkpoints:
+stem 1x1 -> recursive UBlock(Head ResBlock, strided Encode, U, inverse Decode, concat, Tail
+ResBlock) -> three heads.  Index structures are built ONCE per level and shared by every conv
+of that level (the reference rebuilds the sub-manifold rulebook 14 times per forward)."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+
+
+def _fold_bn(sd, prefix, eps, extra_bias=None):
+    """BatchNorm1d(eval) as y = x*scale + shift (model_blocks.py:33; eps=1e-4 in the checkpoints)."""
+    w, b = sd[prefix + ".weight"].double(), sd[prefix + ".bias"].double()
+    m, v = sd[prefix + ".running_mean"].double(), sd[prefix + ".running_var"].double()
+    scale = w / torch.sqrt(v + eps)
+    shift = b - m * scale
+    if extra_bias is not None:
+        shift = shift + extra_bias.double() * scale
+    return scale.float(), shift.float()
+
+
+def _conv_w(w):
+    """spconv layout [cout, kz, ky, kx, cin] -> [taps, cin, cout]."""
+    cout, cin = w.shape[0], w.shape[-1]
+    return w.reshape(cout, -1, cin).permute(1, 2, 0).contiguous().float()
+
+
+@dataclass
+class ConvLayer:
+    w: torch.Tensor                       # [taps, cin, cout]
+    scale: Optional[torch.Tensor] = None
+    shift: Optional[torch.Tensor] = None
+
+    def to(self, dev):
+        return ConvLayer(self.w.to(dev), None if self.scale is None else self.scale.to(dev),
+                         None if self.shift is None else self.shift.to(dev))
+
+
+@dataclass
+class ResBlockPlan:
+    c1: ConvLayer
+    c2: ConvLayer
+    ident_w: Optional[torch.Tensor]       # [cin, cout] or None (Identity)
+
+
+@dataclass
+class LevelPlan:
+    head: ResBlockPlan
+    encode: Optional[ConvLayer] = None
+    decode: Optional[ConvLayer] = None
+    tail: Optional[ResBlockPlan] = None
+
+
+class LevelIndex:
+    """Coordinate table and gather maps of one resolution level."""
+
+    def __init__(self, coords):
+        self.coords = coords
+        self.n = coords.shape[0]
+        self.table = ops.CoordTable(coords)
+        self.nbr = ops.subm_map(coords, self.table)
+        self.down = None
+        self.up = None
+
+
+def build_levels(coords: torch.Tensor, depth: int) -> List[LevelIndex]:
+    levels = [LevelIndex(coords)]
+    for _ in range(depth - 1):
+        cur = levels[-1]
+        oc = ops.strided_coords(cur.coords)
+        nxt = LevelIndex(oc)
+        cur.down, cur.up = ops.strided_maps(cur.coords, oc, nxt.table)
+        levels.append(nxt)
+    return levels
+
+
+class SmartTreeEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = "fma"):
+        sd = {k: v.detach().cpu() for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
+        self.device = torch.device(device)
+        self.eps = eps
+        self.conv_impl = conv_impl
+        dev = self.device
+        self.stem = ConvLayer(_conv_w(sd["input_conv.sequence.0.weight"]),
+                              *_fold_bn(sd, "input_conv.sequence.1", eps)).to(dev)
+        self.levels: List[LevelPlan] = []
+        pre = "UNet."
+        while pre + "Head.sequence.0.weight" in sd:
+            lp = LevelPlan(head=self._resblock(sd, pre + "Head."))
+            if pre + "Encode.sequence.0.weight" in sd:
+                lp.encode = ConvLayer(_conv_w(sd[pre + "Encode.sequence.0.weight"]), *_fold_bn(sd, pre + "Encode.sequence.1", eps)).to(dev)
+                lp.decode = ConvLayer(_conv_w(sd[pre + "Decode.sequence.0.weight"]), *_fold_bn(sd, pre + "Decode.sequence.1", eps)).to(dev)
+                lp.tail = self._resblock(sd, pre + "Tail.")
+            self.levels.append(lp)
+            pre += "U."
+        self.depth = len(self.levels)
+        self.planes = [lp.head.c1.w.shape[2] for lp in self.levels]
+        self.in_channels = self.stem.w.shape[1]
+        self.heads_packed = self._pack_heads(sd)
+        self.head_layers = None if self.heads_packed is not None else {h: self._head_layers(sd, h + "_head.") for h in ("radius", "direction", "class")}
+        if self.heads_packed is not None:
+            self.heads_packed = self.heads_packed.to(dev)
+
+    # ---- plan construction
+    def _resblock(self, sd, pre):
+        dev = self.device
+        c1 = ConvLayer(_conv_w(sd[pre + "sequence.0.weight"]), *_fold_bn(sd, pre + "sequence.1", self.eps)).to(dev)
+        c2 = ConvLayer(_conv_w(sd[pre + "sequence.3.weight"]), *_fold_bn(sd, pre + "sequence.4", self.eps)).to(dev)
+        idk = pre + "identity.0.weight"
+        ident = _conv_w(sd[idk])[0].contiguous().to(dev) if idk in sd else None
+        return ResBlockPlan(c1, c2, ident)
+
+    def _head_layers(self, sd, pre):
+        layers, i = [], 0
+        while f"{pre}sequence.{i}.weight" in sd:
+            w = sd[f"{pre}sequence.{i}.weight"]
+            lin_bias = sd.get(f"{pre}sequence.{i}.bias") if w.dim() == 2 else None
+            wt = (w.t().contiguous().float()[None] if w.dim() == 2 else _conv_w(w))
+            if f"{pre}sequence.{i + 1}.weight" in sd:
+                scale, shift = _fold_bn(sd, f"{pre}sequence.{i + 1}", self.eps, extra_bias=lin_bias)
+                layers.append((ConvLayer(wt, scale, shift).to(self.device), True))
+                i += 3
+            else:
+                shift = lin_bias.float() if lin_bias is not None else None
+                layers.append((ConvLayer(wt, None, shift).to(self.device), False))
+                break
+        return layers
+
+    def _pack_heads(self, sd):
+        """Packed block for st_heads_fused: per head W1[8][8], s1[8], b1[8], W2[8][4], s2[4], b2[4], W3[4][k], b3[k]."""
+        chunks = []
+        for name, k in (("radius", 1), ("direction", 3), ("class", 2)):
+            ls = self._head_layers(sd, name + "_head.")
+            if len(ls) != 3:
+                return None
+            (l1, _), (l2, _), (l3, _) = ls
+            if tuple(l1.w.shape) != (1, 8, 8) or tuple(l2.w.shape) != (1, 8, 4) or tuple(l3.w.shape) != (1, 4, k):
+                return None
+            b3 = l3.shift if l3.shift is not None else torch.zeros(k, device=self.device)
+            chunks += [l1.w.reshape(-1), l1.scale, l1.shift, l2.w.reshape(-1), l2.scale, l2.shift, l3.w.reshape(-1), b3]
+        return torch.cat([c.float().reshape(-1).to(self.device) for c in chunks]).contiguous()
+
+    # ---- execution
+    def _conv(self, x, layer: ConvLayer, nbr, n_out, relu, out=None, residual=None, in2=None, w2=None):
+        return ops.conv_gather(x, nbr, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2,
+                               out=out, relu=relu, impl=self.conv_impl if layer.w.shape[0] > 1 else "fma")
+
+    def _resblock_run(self, x, rb: ResBlockPlan, nbr, out):
+        n = x.shape[0]
+        t = self._conv(x, rb.c1, nbr, n, relu=True)
+        if rb.ident_w is None:
+            return self._conv(t, rb.c2, nbr, n, relu=True, out=out, residual=x)
+        return self._conv(t, rb.c2, nbr, n, relu=True, out=out, in2=x, w2=rb.ident_w)
+
+    def _ublock(self, x, li, levels, trace, pre="UNet."):
+        lp, lv = self.levels[li], levels[li]
+        n, c = lv.n, self.planes[li]
+        if lp.encode is None:
+            y = self._resblock_run(x, lp.head, lv.nbr, None)
+            if trace is not None:
+                trace[pre + "Head"] = y
+            return y
+        cat = torch.empty((n, 2 * c), dtype=F32, device=x.device)
+        skip = cat[:, :c]
+        self._resblock_run(x, lp.head, lv.nbr, skip)
+        nxt = levels[li + 1]
+        y = self._conv(skip, lp.encode, lv.down, nxt.n, relu=True)
+        if trace is not None:
+            trace[pre + "Head"] = skip.clone(); trace[pre + "Encode"] = y
+        y = self._ublock(y, li + 1, levels, trace, pre + "U.")
+        self._conv(y, lp.decode, lv.up, n, relu=True, out=cat[:, c:])
+        out = self._resblock_run(cat, lp.tail, lv.nbr, None)
+        if trace is not None:
+            trace[pre + "Decode"] = cat[:, c:].clone(); trace[pre + "Tail"] = out
+        return out
+
+    def build_levels(self, coords):
+        return build_levels(coords.contiguous(), self.depth)
+
+    @torch.no_grad()
+    def forward(self, features: torch.Tensor, coords: torch.Tensor, levels=None, trace=None, fused_outputs=False):
+        """features [N, Cin] f32, coords [N,4] i32 (b,z,y,x), both CUDA.  Returns the reference's
+        prediction dict (model.py:77-87); with fused_outputs also medial_vector / class index."""
+        if not features.is_cuda:
+            raise RuntimeError("SmartTreeEngine.forward needs CUDA tensors: there is no CPU path")
+        features = features.contiguous().float()
+        coords = coords.contiguous().int()
+        n = features.shape[0]
+        if levels is None:
+            levels = self.build_levels(coords)
+        x = self._conv(features, self.stem, None, n, relu=True)
+        if trace is not None:
+            trace["input_conv"] = x
+        x = self._ublock(x, 0, levels, trace)
+        if self.heads_packed is not None and x.shape[1] == 8:
+            radius, direction, logits, medial, cls = ops.heads_fused(x, self.heads_packed)
+        else:
+            outs = {}
+            for name, ls in self.head_layers.items():
+                h = x
+                for layer, relu in ls:
+                    h = self._conv(h, layer, None, n, relu=relu)
+                outs[name] = h
+            radius, logits = outs["radius"], outs["class"]
+            direction = torch.nn.functional.normalize(outs["direction"])
+            medial = torch.exp(radius) * direction
+            cls = torch.argmax(logits, dim=1).int()
+        preds = {"radius": radius, "direction": direction, "class_l": logits}
+        if fused_outputs:
+            preds["medial_vector"] = medial
+            preds["class_idx"] = cls
+        return preds

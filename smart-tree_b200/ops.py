@@ -1,0 +1,275 @@
+"""Torch-tensor wrappers over the C ABI (include/st_b200.h).  PyTorch supplies device memory
+and streams only; all arithmetic happens in libst_b200.so.  CUDA tensors only -- no fallback."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+I32, I64, F32, U8 = torch.int32, torch.int64, torch.float32, torch.uint8
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def _req(t: torch.Tensor, dtype, name):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.StB200Error(f"{name}: expected a CUDA tensor (libst_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.StB200Error(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise _lib.StB200Error(f"{name}: expected a contiguous tensor")
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=U8, device=device)
+
+
+# ------------------------------------------------------------------ voxelise
+def voxelize(points, point_block, block_lo, block_grid, vsize):
+    """points [n,F] f32, point_block [n] i32 or None, block_lo [B,3] f32, block_grid [B,3] i32.
+    Returns pc_voxel_id[n] i32, rep_point[M] i32, coords[M,4] i32 (b,z,y,x)."""
+    lib = _lib.load()
+    _req(points, F32, "points"); _req(block_lo, F32, "block_lo"); _req(block_grid, I32, "block_grid")
+    if point_block is not None:
+        _req(point_block, I32, "point_block")
+    n, ld = points.shape
+    dev = points.device
+    pc = torch.empty(n, dtype=I32, device=dev)
+    rep = torch.empty(n, dtype=I32, device=dev)
+    coords = torch.empty((n, 4), dtype=I32, device=dev)
+    wsb = lib.st_voxelize_workspace_bytes(n)
+    ws = _ws(wsb, dev)
+    m = C.c_int64(0)
+    _lib.check(lib.st_voxelize(_ptr(points), n, ld, _ptr(point_block), _ptr(block_lo), _ptr(block_grid),
+                               block_lo.shape[0], float(vsize), _ptr(pc), _ptr(rep), _ptr(coords), C.byref(m),
+                               _ptr(ws), ws.numel(), _stream()), "st_voxelize")
+    return pc, rep[:m.value], coords[:m.value]
+
+
+# ------------------------------------------------------------------ coordinate table / maps
+class CoordTable:
+    """Open-addressing hash of (b,z,y,x) -> row."""
+
+    def __init__(self, coords):
+        lib = _lib.load()
+        _req(coords, I32, "coords")
+        self.n = coords.shape[0]
+        self.capacity = lib.st_hash_capacity(self.n)
+        self.keys = torch.empty(self.capacity, dtype=I64, device=coords.device)
+        self.vals = torch.empty(self.capacity, dtype=I32, device=coords.device)
+        _lib.check(lib.st_hash_build(_ptr(coords), self.n, _ptr(self.keys), _ptr(self.vals), self.capacity, _stream()),
+                   "st_hash_build")
+
+
+def subm_map(coords, table: CoordTable):
+    lib = _lib.load()
+    n = coords.shape[0]
+    nbr = torch.empty((27, n), dtype=I32, device=coords.device)
+    _lib.check(lib.st_subm_map(_ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.capacity, _ptr(nbr), _stream()),
+               "st_subm_map")
+    return nbr
+
+
+def strided_coords(coords):
+    lib = _lib.load()
+    _req(coords, I32, "coords")
+    n = coords.shape[0]
+    out = torch.empty((max(8 * n, 1), 4), dtype=I32, device=coords.device)
+    ws = _ws(lib.st_strided_coords_workspace_bytes(n), coords.device)
+    m = C.c_int64(0)
+    _lib.check(lib.st_strided_coords(_ptr(coords), n, _ptr(out), C.byref(m), _ptr(ws), ws.numel(), _stream()),
+               "st_strided_coords")
+    return out[:m.value].clone() if m.value * 4 < out.shape[0] else out[:m.value]
+
+
+def strided_maps(coords, out_coords, out_table: CoordTable):
+    lib = _lib.load()
+    n, m = coords.shape[0], out_coords.shape[0]
+    down = torch.empty((27, m), dtype=I32, device=coords.device)
+    up = torch.empty((27, n), dtype=I32, device=coords.device)
+    _lib.check(lib.st_strided_maps(_ptr(coords), n, m, _ptr(out_table.keys), _ptr(out_table.vals), out_table.capacity,
+                                   _ptr(down), _ptr(up), _stream()), "st_strided_maps")
+    return down, up
+
+
+# ------------------------------------------------------------------ convolution
+def _ld(t):
+    return t.stride(0) if t is not None else 0
+
+
+def _req_rows(t, name):
+    """2-D fp32 CUDA tensor whose rows are contiguous (a column slice of a wider buffer is fine)."""
+    if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != F32 or t.dim() != 2 or (t.shape[1] > 1 and t.stride(1) != 1):
+        raise _lib.StB200Error(f"{name}: expected a 2-D fp32 CUDA tensor with unit column stride")
+    return t
+
+
+def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=None, in2=None, w2=None,
+                out=None, relu=False, impl="fma"):
+    """out[i] = act(scale * sum_k W[k] . in[map[k,i]] + shift + residual[i] + w2 . in2[i]).
+    weight [ntaps, cin, cout]; nbr_map [ntaps, n_out] i32 or None (identity, ntaps == 1)."""
+    lib = _lib.load()
+    _req_rows(inp, "inp"); _req(weight, F32, "weight")
+    ntaps, cin, cout = weight.shape
+    if nbr_map is not None:
+        _req(nbr_map, I32, "map")
+        assert nbr_map.shape == (ntaps, n_out), (nbr_map.shape, ntaps, n_out)
+    if out is None:
+        out = torch.empty((n_out, cout), dtype=F32, device=inp.device)
+    _req_rows(out, "out")
+    assert out.shape == (n_out, cout) and inp.shape[1] == cin
+    if residual is not None:
+        _req_rows(residual, "residual")
+    if in2 is not None:
+        _req_rows(in2, "in2"); _req(w2, F32, "w2")
+    fn = lib.st_conv_gather_tc if impl == "tc" else lib.st_conv_gather
+    _lib.check(fn(_ptr(inp), _ld(inp), _ptr(nbr_map), n_out, ntaps, _ptr(weight), cin, cout, _ptr(scale), _ptr(shift),
+                  _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (w2.shape[0] if w2 is not None else 0),
+                  _ptr(out), _ld(out), 1 if relu else 0, _stream()), "st_conv_gather")
+    return out
+
+
+def heads_fused(feat, params, want_logits=True):
+    lib = _lib.load()
+    _req_rows(feat, "feat"); _req(params, F32, "params")
+    n, dev = feat.shape[0], feat.device
+    radius = torch.empty((n, 1), dtype=F32, device=dev)
+    direction = torch.empty((n, 3), dtype=F32, device=dev)
+    logits = torch.empty((n, 2), dtype=F32, device=dev) if want_logits else None
+    medial = torch.empty((n, 3), dtype=F32, device=dev)
+    cls = torch.empty(n, dtype=I32, device=dev)
+    _lib.check(lib.st_heads_fused(_ptr(feat), _ld(feat), n, _ptr(params), _ptr(radius), _ptr(direction), _ptr(logits),
+                                  _ptr(medial), _ptr(cls), _stream()), "st_heads_fused")
+    return radius, direction, logits, medial, cls
+
+
+# ------------------------------------------------------------------ kNN / graph
+def knn(src, dst, K, r, query_radius=None):
+    """idx[n,K] i32 (-1 padded), d2[n,K] f32 squared distances (-1 padded)."""
+    lib = _lib.load()
+    _req(src, F32, "src"); _req(dst, F32, "dst")
+    n, m = src.shape[0], dst.shape[0]
+    idx = torch.empty((n, K), dtype=I32, device=src.device)
+    d2 = torch.empty((n, K), dtype=F32, device=src.device)
+    ws = _ws(lib.st_knn_workspace_bytes(m), src.device)
+    if query_radius is not None:
+        _req(query_radius, F32, "query_radius")
+    _lib.check(lib.st_knn(_ptr(src), n, _ptr(dst), m, K, float(r), _ptr(query_radius), _ptr(idx), _ptr(d2), _ptr(ws),
+                          ws.numel(), _stream()), "st_knn")
+    return idx, d2
+
+
+def outlier_mask(points, radii, r_max, nb=8):
+    lib = _lib.load()
+    _req(points, F32, "points"); _req(radii, F32, "radii")
+    n = points.shape[0]
+    keep = torch.empty(n, dtype=U8, device=points.device)
+    ws = _ws(lib.st_knn_workspace_bytes(n), points.device)
+    _lib.check(lib.st_outlier_mask(_ptr(points), n, _ptr(radii), float(r_max), nb, _ptr(keep), _ptr(ws), ws.numel(), _stream()),
+               "st_outlier_mask")
+    return keep.bool()
+
+
+def edges_from_knn(idx, d2, radii=None):
+    lib = _lib.load()
+    _req(idx, I32, "idx"); _req(d2, F32, "d2")
+    n, K = idx.shape
+    edges = torch.empty((max(n * K, 1), 2), dtype=I32, device=idx.device)
+    weights = torch.empty(max(n * K, 1), dtype=F32, device=idx.device)
+    ws = _ws(lib.st_edges_workspace_bytes(n, K), idx.device)
+    ne = C.c_int64(0)
+    _lib.check(lib.st_edges_from_knn(_ptr(idx), _ptr(d2), n, K, _ptr(radii), _ptr(edges), _ptr(weights), C.byref(ne), _ptr(ws),
+                                     ws.numel(), _stream()), "st_edges_from_knn")
+    return edges[:ne.value], weights[:ne.value]
+
+
+def connected_components(edges, n):
+    lib = _lib.load()
+    _req(edges, I32, "edges")
+    label = torch.empty(n, dtype=I32, device=edges.device)
+    size = torch.empty(n, dtype=I32, device=edges.device)
+    _lib.check(lib.st_connected_components(_ptr(edges), edges.shape[0], n, _ptr(label), _ptr(size), _stream()),
+               "st_connected_components")
+    return label, size
+
+
+def csr_build(edges, weights, n):
+    lib = _lib.load()
+    _req(edges, I32, "edges"); _req(weights, F32, "weights")
+    ne, dev = edges.shape[0], edges.device
+    row_ptr = torch.empty(n + 1, dtype=I32, device=dev)
+    col = torch.empty(max(2 * ne, 1), dtype=I32, device=dev)
+    w = torch.empty(max(2 * ne, 1), dtype=F32, device=dev)
+    ws = _ws(lib.st_csr_workspace_bytes(n, ne), dev)
+    na = C.c_int64(0)
+    _lib.check(lib.st_csr_build(_ptr(edges), _ptr(weights), ne, n, _ptr(row_ptr), _ptr(col), _ptr(w), C.byref(na), _ptr(ws),
+                                ws.numel(), _stream()), "st_csr_build")
+    return row_ptr, col[:na.value], w[:na.value]
+
+
+def sssp(row_ptr, col, w, n, sources, want_sweeps=False):
+    lib = _lib.load()
+    _req(sources, I32, "sources")
+    dev = row_ptr.device
+    dist = torch.empty(n, dtype=F32, device=dev)
+    pred = torch.empty(n, dtype=I32, device=dev)
+    ctl = torch.zeros(64, dtype=I32, device=dev)
+    sweeps = C.c_int32(0)
+    _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], _ptr(dist), _ptr(pred),
+                           C.byref(sweeps) if want_sweeps else None, _ptr(ctl), _stream()), "st_sssp")
+    return (dist, pred, sweeps.value) if want_sweeps else (dist, pred)
+
+
+def tree_distances(points, pred, is_root):
+    lib = _lib.load()
+    _req(points, F32, "points"); _req(pred, I32, "pred"); _req(is_root, U8, "is_root")
+    n = pred.shape[0]
+    td = torch.empty(n, dtype=F32, device=pred.device)
+    ctl = torch.zeros(64, dtype=I32, device=pred.device)
+    _lib.check(lib.st_tree_distances(_ptr(points), _ptr(pred), _ptr(is_root), n, _ptr(td), _ptr(ctl), _stream()),
+               "st_tree_distances")
+    return td
+
+
+def sample_tree(medial_pts, radii, pred, tree_dist, comp_off, cell_size):
+    """Returns segment-local path_vertices[n], branch_len[n], branch_parent[n], comp_nb[C], comp_np[C]."""
+    lib = _lib.load()
+    _req(medial_pts, F32, "medial_pts"); _req(radii, F32, "radii"); _req(pred, I32, "pred")
+    _req(tree_dist, F32, "tree_dist"); _req(comp_off, I32, "comp_off")
+    n, dev = pred.shape[0], pred.device
+    nc = comp_off.shape[0] - 1
+    path = torch.empty(max(n, 1), dtype=I32, device=dev)
+    blen = torch.empty(max(n, 1), dtype=I32, device=dev)
+    bpar = torch.empty(max(n, 1), dtype=I32, device=dev)
+    cnb = torch.zeros(max(nc, 1), dtype=I32, device=dev)
+    cnp = torch.zeros(max(nc, 1), dtype=I32, device=dev)
+    ws = _ws(lib.st_sample_tree_workspace_bytes(n, nc), dev)
+    _lib.check(lib.st_sample_tree(_ptr(medial_pts), _ptr(radii), _ptr(pred), _ptr(tree_dist), _ptr(comp_off), nc, n,
+                                  float(cell_size), _ptr(path), _ptr(blen), _ptr(bpar), _ptr(cnb), _ptr(cnp), _ptr(ws),
+                                  ws.numel(), _stream()), "st_sample_tree")
+    return path, blen, bpar, cnb, cnp
+
+
+def points_to_tubes(pts, a, b, r1, r2, tube_off):
+    lib = _lib.load()
+    for t, nme in ((pts, "pts"), (a, "a"), (b, "b"), (r1, "r1"), (r2, "r2")):
+        _req(t, F32, nme)
+    _req(tube_off, I32, "tube_off")
+    nq, dev = pts.shape[0], pts.device
+    vec = torch.empty((nq, 3), dtype=F32, device=dev)
+    idx = torch.empty(nq, dtype=I32, device=dev)
+    rr = torch.empty(nq, dtype=F32, device=dev)
+    _lib.check(lib.st_points_to_tubes(_ptr(pts), nq, _ptr(a), _ptr(b), _ptr(r1), _ptr(r2), _ptr(tube_off), _ptr(vec),
+                                      _ptr(idx), _ptr(rr), _stream()), "st_points_to_tubes")
+    return vec, idx, rr

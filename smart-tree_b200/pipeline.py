@@ -1,0 +1,72 @@
+"""Pipeline with the reference's constructor and process_cloud
+(/root/reference/smart_tree/pipeline.py:13-106): load -> preprocess -> infer -> class filter ->
+skeletonise -> prune / repair / smooth.  Viewing and open3d export are out of scope (GUI);
+`save_outputs` writes the reference's npz skeleton schema instead."""
+from __future__ import annotations
+
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from .data_types.cloud import Cloud
+from .data_types.tree import DisjointTreeSkeleton
+from .util.file import load_cloud, save_skeleton
+
+
+class Pipeline:
+    def __init__(self, preprocessing, model_inference, skeletonizer, repair_skeletons=False, smooth_skeletons=False,
+                 smooth_kernel_size=0, prune_skeletons=False, min_skeleton_radius=0.0, min_skeleton_length=1000,
+                 view_model_output=False, view_skeletons=False, save_outputs=False, save_path="/", branch_classes=[0],
+                 cmap=[[1, 0, 0], [0, 1, 0]], device=torch.device("cuda:0")):
+        self.preprocessing = preprocessing
+        self.model_inference = model_inference
+        self.skeletonizer = skeletonizer
+        self.repair_skeletons = repair_skeletons
+        self.smooth_skeletons = smooth_skeletons
+        self.smooth_kernel_size = smooth_kernel_size
+        self.prune_skeletons = prune_skeletons
+        self.min_skeleton_radius = min_skeleton_radius
+        self.min_skeleton_length = min_skeleton_length
+        self.view_model_output = view_model_output
+        self.view_skeletons = view_skeletons
+        self.save_outputs = save_outputs
+        self.save_path = save_path
+        self.branch_classes = list(branch_classes)
+        self.cmap = np.asarray(cmap)
+        self.device = torch.device(device)
+        self.timings = {}
+        self.labelled_cloud = None
+
+    def process_cloud(self, path: Path = None, cloud: Cloud = None) -> DisjointTreeSkeleton:
+        cloud = load_cloud(Path(path)) if path is not None else cloud
+        t = {}
+        sync = (lambda: torch.cuda.synchronize(self.device)) if self.device.type == "cuda" else (lambda: None)
+        t0 = time.perf_counter()
+        cloud = cloud.to_device(self.device)
+        cloud = self.preprocessing(cloud)
+        sync(); t["preprocess"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        lc: Cloud = self.model_inference.forward(cloud).to_device(self.device)      # pipeline.py:63
+        sync(); t["inference"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.labelled_cloud = lc
+        branch_cloud = lc.filter_by_class(self.branch_classes)                      # pipeline.py:68
+        skeleton = self.skeletonizer.forward(branch_cloud)                          # pipeline.py:71
+        sync(); t["skeleton"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.post_process(skeleton)
+        sync(); t["post_process"] = time.perf_counter() - t0
+        self.timings = t
+        if self.view_model_output or self.view_skeletons:
+            print("smart_tree_b200: viewers are out of scope (open3d GUI); ignoring view_* flags")
+        if self.save_outputs:
+            for s in skeleton.skeletons:
+                save_skeleton(s, f"{self.save_path}/skeleton_{s._id}.npz")
+        return skeleton
+
+    def post_process(self, skeleton: DisjointTreeSkeleton):
+        if self.prune_skeletons:
+            skeleton.prune(min_length=self.min_skeleton_length, min_radius=self.min_skeleton_radius)
+        if self.repair_skeletons:
+            skeleton.repair(device=self.device)
+        if self.smooth_skeletons:
+            skeleton.smooth(self.smooth_kernel_size)
