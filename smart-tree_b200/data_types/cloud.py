@@ -106,7 +106,10 @@ class Cloud:
 
     @property
     def radius(self):
-        return self.medial_vector.pow(2).sum(1).sqrt()
+        # cloud.py:255-256 (`pow(2).sum(1).sqrt()`); the summation order is spelled out so that the
+        # value is bit-identical on every device: sqrt((x*x + y*y) + z*z), one rounding per operation
+        v = self.medial_vector
+        return ((v[:, 0] * v[:, 0] + v[:, 1] * v[:, 1]) + v[:, 2] * v[:, 2]).sqrt()
 
     @property
     def direction(self):

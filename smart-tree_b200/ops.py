@@ -10,6 +10,26 @@ from . import _lib
 
 I32, I64, F32, U8 = torch.int32, torch.int64, torch.float32, torch.uint8
 
+# ---- instrumentation (bench.py): number of libst_b200 kernels launched, optional per-conv CUDA events
+LAUNCHES = 0
+_conv_profile = None
+_KERNELS_PER_CALL = {"voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
+                     "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
+                     "sample_tree": 5, "tubes": 1}
+
+
+def _count(op):
+    global LAUNCHES
+    LAUNCHES += _KERNELS_PER_CALL[op]
+
+
+def conv_profile(enable: bool):
+    """Start/stop recording (cin, cout, taps, n_out, extra_bytes, start_event, end_event) per conv launch."""
+    global _conv_profile
+    prev = _conv_profile
+    _conv_profile = [] if enable else None
+    return prev
+
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -51,6 +71,7 @@ def voxelize(points, point_block, block_lo, block_grid, vsize):
     wsb = lib.st_voxelize_workspace_bytes(n)
     ws = _ws(wsb, dev)
     m = C.c_int64(0)
+    _count("voxelize")
     _lib.check(lib.st_voxelize(_ptr(points), n, ld, _ptr(point_block), _ptr(block_lo), _ptr(block_grid),
                                block_lo.shape[0], float(vsize), _ptr(pc), _ptr(rep), _ptr(coords), C.byref(m),
                                _ptr(ws), ws.numel(), _stream()), "st_voxelize")
@@ -68,6 +89,7 @@ class CoordTable:
         self.capacity = lib.st_hash_capacity(self.n)
         self.keys = torch.empty(self.capacity, dtype=I64, device=coords.device)
         self.vals = torch.empty(self.capacity, dtype=I32, device=coords.device)
+        _count("hash_build")
         _lib.check(lib.st_hash_build(_ptr(coords), self.n, _ptr(self.keys), _ptr(self.vals), self.capacity, _stream()),
                    "st_hash_build")
 
@@ -76,6 +98,7 @@ def subm_map(coords, table: CoordTable):
     lib = _lib.load()
     n = coords.shape[0]
     nbr = torch.empty((27, n), dtype=I32, device=coords.device)
+    _count("subm_map")
     _lib.check(lib.st_subm_map(_ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.capacity, _ptr(nbr), _stream()),
                "st_subm_map")
     return nbr
@@ -88,6 +111,7 @@ def strided_coords(coords):
     out = torch.empty((max(8 * n, 1), 4), dtype=I32, device=coords.device)
     ws = _ws(lib.st_strided_coords_workspace_bytes(n), coords.device)
     m = C.c_int64(0)
+    _count("strided_coords")
     _lib.check(lib.st_strided_coords(_ptr(coords), n, _ptr(out), C.byref(m), _ptr(ws), ws.numel(), _stream()),
                "st_strided_coords")
     return out[:m.value].clone() if m.value * 4 < out.shape[0] else out[:m.value]
@@ -98,6 +122,7 @@ def strided_maps(coords, out_coords, out_table: CoordTable):
     n, m = coords.shape[0], out_coords.shape[0]
     down = torch.empty((27, m), dtype=I32, device=coords.device)
     up = torch.empty((27, n), dtype=I32, device=coords.device)
+    _count("strided_maps")
     _lib.check(lib.st_strided_maps(_ptr(coords), n, m, _ptr(out_table.keys), _ptr(out_table.vals), out_table.capacity,
                                    _ptr(down), _ptr(up), _stream()), "st_strided_maps")
     return down, up
@@ -134,9 +159,18 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
     if in2 is not None:
         _req_rows(in2, "in2"); _req(w2, F32, "w2")
     fn = lib.st_conv_gather_tc if impl == "tc" else lib.st_conv_gather
+    _count("conv")
+    prof = _conv_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     _lib.check(fn(_ptr(inp), _ld(inp), _ptr(nbr_map), n_out, ntaps, _ptr(weight), cin, cout, _ptr(scale), _ptr(shift),
                   _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (w2.shape[0] if w2 is not None else 0),
                   _ptr(out), _ld(out), 1 if relu else 0, _stream()), "st_conv_gather")
+    if prof is not None:
+        ev1.record()
+        extra = (cout if residual is not None else 0) + (w2.shape[0] if w2 is not None else 0)
+        prof.append((cin, cout, ntaps, n_out, extra, ev0, ev1, impl))
     return out
 
 
@@ -149,6 +183,7 @@ def heads_fused(feat, params, want_logits=True):
     logits = torch.empty((n, 2), dtype=F32, device=dev) if want_logits else None
     medial = torch.empty((n, 3), dtype=F32, device=dev)
     cls = torch.empty(n, dtype=I32, device=dev)
+    _count("heads")
     _lib.check(lib.st_heads_fused(_ptr(feat), _ld(feat), n, _ptr(params), _ptr(radius), _ptr(direction), _ptr(logits),
                                   _ptr(medial), _ptr(cls), _stream()), "st_heads_fused")
     return radius, direction, logits, medial, cls
@@ -165,6 +200,7 @@ def knn(src, dst, K, r, query_radius=None):
     ws = _ws(lib.st_knn_workspace_bytes(m), src.device)
     if query_radius is not None:
         _req(query_radius, F32, "query_radius")
+    _count("knn")
     _lib.check(lib.st_knn(_ptr(src), n, _ptr(dst), m, K, float(r), _ptr(query_radius), _ptr(idx), _ptr(d2), _ptr(ws),
                           ws.numel(), _stream()), "st_knn")
     return idx, d2
@@ -176,6 +212,7 @@ def outlier_mask(points, radii, r_max, nb=8):
     n = points.shape[0]
     keep = torch.empty(n, dtype=U8, device=points.device)
     ws = _ws(lib.st_knn_workspace_bytes(n), points.device)
+    _count("outlier")
     _lib.check(lib.st_outlier_mask(_ptr(points), n, _ptr(radii), float(r_max), nb, _ptr(keep), _ptr(ws), ws.numel(), _stream()),
                "st_outlier_mask")
     return keep.bool()
@@ -189,6 +226,7 @@ def edges_from_knn(idx, d2, radii=None):
     weights = torch.empty(max(n * K, 1), dtype=F32, device=idx.device)
     ws = _ws(lib.st_edges_workspace_bytes(n, K), idx.device)
     ne = C.c_int64(0)
+    _count("edges")
     _lib.check(lib.st_edges_from_knn(_ptr(idx), _ptr(d2), n, K, _ptr(radii), _ptr(edges), _ptr(weights), C.byref(ne), _ptr(ws),
                                      ws.numel(), _stream()), "st_edges_from_knn")
     return edges[:ne.value], weights[:ne.value]
@@ -199,6 +237,7 @@ def connected_components(edges, n):
     _req(edges, I32, "edges")
     label = torch.empty(n, dtype=I32, device=edges.device)
     size = torch.empty(n, dtype=I32, device=edges.device)
+    _count("cc")
     _lib.check(lib.st_connected_components(_ptr(edges), edges.shape[0], n, _ptr(label), _ptr(size), _stream()),
                "st_connected_components")
     return label, size
@@ -213,6 +252,7 @@ def csr_build(edges, weights, n):
     w = torch.empty(max(2 * ne, 1), dtype=F32, device=dev)
     ws = _ws(lib.st_csr_workspace_bytes(n, ne), dev)
     na = C.c_int64(0)
+    _count("csr")
     _lib.check(lib.st_csr_build(_ptr(edges), _ptr(weights), ne, n, _ptr(row_ptr), _ptr(col), _ptr(w), C.byref(na), _ptr(ws),
                                 ws.numel(), _stream()), "st_csr_build")
     return row_ptr, col[:na.value], w[:na.value]
@@ -226,6 +266,7 @@ def sssp(row_ptr, col, w, n, sources, want_sweeps=False):
     pred = torch.empty(n, dtype=I32, device=dev)
     ctl = torch.zeros(64, dtype=I32, device=dev)
     sweeps = C.c_int32(0)
+    _count("sssp")
     _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], _ptr(dist), _ptr(pred),
                            C.byref(sweeps) if want_sweeps else None, _ptr(ctl), _stream()), "st_sssp")
     return (dist, pred, sweeps.value) if want_sweeps else (dist, pred)
@@ -237,6 +278,7 @@ def tree_distances(points, pred, is_root):
     n = pred.shape[0]
     td = torch.empty(n, dtype=F32, device=pred.device)
     ctl = torch.zeros(64, dtype=I32, device=pred.device)
+    _count("tree_dist")
     _lib.check(lib.st_tree_distances(_ptr(points), _ptr(pred), _ptr(is_root), n, _ptr(td), _ptr(ctl), _stream()),
                "st_tree_distances")
     return td
@@ -255,6 +297,7 @@ def sample_tree(medial_pts, radii, pred, tree_dist, comp_off, cell_size):
     cnb = torch.zeros(max(nc, 1), dtype=I32, device=dev)
     cnp = torch.zeros(max(nc, 1), dtype=I32, device=dev)
     ws = _ws(lib.st_sample_tree_workspace_bytes(n, nc), dev)
+    _count("sample_tree")
     _lib.check(lib.st_sample_tree(_ptr(medial_pts), _ptr(radii), _ptr(pred), _ptr(tree_dist), _ptr(comp_off), nc, n,
                                   float(cell_size), _ptr(path), _ptr(blen), _ptr(bpar), _ptr(cnb), _ptr(cnp), _ptr(ws),
                                   ws.numel(), _stream()), "st_sample_tree")
@@ -270,6 +313,7 @@ def points_to_tubes(pts, a, b, r1, r2, tube_off):
     vec = torch.empty((nq, 3), dtype=F32, device=dev)
     idx = torch.empty(nq, dtype=I32, device=dev)
     rr = torch.empty(nq, dtype=F32, device=dev)
+    _count("tubes")
     _lib.check(lib.st_points_to_tubes(_ptr(pts), nq, _ptr(a), _ptr(b), _ptr(r1), _ptr(r2), _ptr(tube_off), _ptr(vec),
                                       _ptr(idx), _ptr(rr), _stream()), "st_points_to_tubes")
     return vec, idx, rr
