@@ -1,0 +1,28 @@
+"""Opt-in stage timers (ST_TIMING=1 or timing.enable()): synchronising wall-clock sections used by
+tools/stage_stats.py and bench.py's stage table.  Disabled = zero overhead, no synchronisation."""
+import os
+import time
+from contextlib import contextmanager
+
+import torch
+
+ENABLED = bool(int(os.environ.get("ST_TIMING", "0")))
+RECORDS = {}
+
+
+def enable(on=True):
+    global ENABLED
+    ENABLED = on
+    RECORDS.clear()
+
+
+@contextmanager
+def section(name):
+    if not ENABLED:
+        yield
+        return
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    yield
+    torch.cuda.synchronize()
+    RECORDS[name] = RECORDS.get(name, 0.0) + (time.perf_counter() - t0) * 1e3

@@ -158,11 +158,15 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 }
 
 // ------------------------------------------------------------------------------------ SSSP
-// Pull-based chaotic relaxation: every thread owns a few vertices and keeps re-evaluating
-// d[v] = min(d[v], min_u fl32(d[u] + w(u,v))) with L2-coherent loads.  fl32(+) is monotone, so any
-// schedule converges to the same least fixed point (== fp32 Dijkstra).  Grid barriers only every
-// `PASSES` local passes; stop after a whole chunk in which nothing changed.
-constexpr int SSSP_PASSES = 16;
+// Pull-based asynchronous relaxation in a resident grid.  Every thread owns a few vertices and
+// polls a per-vertex "dirty" word; when it is set the vertex re-evaluates
+//     d[v] = min(d[v], min_u fl32(d[u] + w(u,v)))
+// with L2-coherent loads, and if d[v] dropped it publishes the value (store, fence) and marks its
+// neighbours dirty.  fl32(+) is monotone, so ANY schedule converges to the same least fixed point
+// (== fp32 Dijkstra); a shortest-path chain advances one hop per poll period (~1 us) instead of
+// one hop per grid-wide sweep.  Grid barriers only every SSSP_PASSES polls; the kernel stops after
+// a whole chunk in which no dirty word was consumed.
+constexpr int SSSP_PASSES = 64;
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -172,25 +176,37 @@ struct SsspCtl {
 };
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                              const float *__restrict__ w, int n, float *dist, SsspCtl *ctl) {
+                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl) {
     unsigned phase = 0;
     const int stride = gridDim.x * blockDim.x;
     const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
     for (unsigned chunk = 0;; ++chunk) {
-        bool changed = false;
+        bool consumed = false;
         for (int pass = 0; pass < SSSP_PASSES; ++pass) {
             for (int v = t0; v < n; v += stride) {
+                if (__ldcg(dirty + v) == 0) continue;
+                if (atomicExch(dirty + v, 0) == 0) continue;
+                __threadfence();
+                consumed = true;
                 float cur = __ldcg(dist + v);
                 float best = cur;
-                int b = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
+                const int b = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
                 for (int a = b; a < e; ++a) {
                     float c = __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a));
                     best = fminf(best, c);
                 }
-                if (best < cur) { __stcg(dist + v, best); changed = true; }
+                if (best < cur) {
+                    __stcg(dist + v, best);
+                    __threadfence();
+                    for (int a = b; a < e; ++a) {
+                        int u = __ldg(col + a);
+                        // u can only improve through v if d[v] + w < d[u]
+                        if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicExch(dirty + u, 1);
+                    }
+                }
             }
         }
-        if (__syncthreads_or(changed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (__syncthreads_or(consumed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl->changed[(chunk + 1) % 3] = 0;
         grid_barrier(&ctl->barrier, phase);
         unsigned any = *(volatile unsigned *)&ctl->changed[chunk % 3];
@@ -199,6 +215,14 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
             break;
         }
     }
+}
+
+__global__ void k_sssp_seed(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int *dirty,
+                            const int32_t *__restrict__ sources, int ns) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns) return;
+    int s = sources[i];
+    for (int a = row_ptr[s]; a < row_ptr[s + 1]; ++a) dirty[col[a]] = 1;
 }
 
 __global__ void k_sssp_init(float *dist, int n) {
@@ -249,7 +273,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     cudaStream_t s = (cudaStream_t)stream;
     if (sweeps_host) *sweeps_host = 0;
     if (n == 0) return ST_OK;
-    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 bytes) required");
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 4n bytes) required");
     int device = 0;
     ST_CHECK_CUDA(cudaGetDevice(&device));
     SsspCtl *ctl = (SsspCtl *)ctl_workspace;
@@ -261,12 +285,18 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
         k_sssp_sources<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(dist, sources, n_sources);
         ST_CHECK_LAUNCH();
     }
+    int *dirty = (int *)((char *)ctl_workspace + 256);
+    ST_CHECK_CUDA(cudaMemsetAsync(dirty, 0, n * sizeof(int), s));
+    if (n_sources) {
+        k_sssp_seed<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(row_ptr, col, dirty, sources, n_sources);
+        ST_CHECK_LAUNCH();
+    }
     int blocks = 0;
     int rc = coop_grid((const void *)k_sssp, 256, device, blocks);
     if (rc) return rc;
     if (blocks > (int)g) blocks = (int)g;
     int nn = (int)n;
-    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&ctl};
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl};
     ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
     k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
     ST_CHECK_LAUNCH();
@@ -354,16 +384,20 @@ extern "C" int st_tree_distances(const float *points, const int32_t *pred, const
 // ------------------------------------------------------------------------------------ point -> tube (repair)
 // queries.py:89-133: t = clip(ap.ab / ab.ab, 0, 1) ; proj = a + t ab ; dist = ||proj - p|| ;
 // r = (1-t) r1 + t r2 ; argmin |dist - r| (first minimum)
-__global__ void k_points_to_tubes(const float *__restrict__ pts, int nq, const float *__restrict__ a, const float *__restrict__ b,
-                                  const float *__restrict__ r1, const float *__restrict__ r2, const int32_t *__restrict__ off,
-                                  float *__restrict__ out_vec, int32_t *__restrict__ out_idx, float *__restrict__ out_r) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_points_to_tubes(const float *__restrict__ pts, int nq, const float *__restrict__ a,
+                                                         const float *__restrict__ b, const float *__restrict__ r1,
+                                                         const float *__restrict__ r2, const int32_t *__restrict__ off,
+                                                         float *__restrict__ out_vec, int32_t *__restrict__ out_idx,
+                                                         float *__restrict__ out_r) {
+    // one warp per query; lanes stride over the query's tubes, then an argmin reduction (first minimum)
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (q >= nq) return;
-    float px = pts[3 * q], py = pts[3 * q + 1], pz = pts[3 * q + 2];
+    const float px = pts[3 * q], py = pts[3 * q + 1], pz = pts[3 * q + 2];
     float best = ST_INF, bvx = 0, bvy = 0, bvz = 0, br = 0;
-    int bidx = -1;
-    bool nan_first = false;
-    for (int m = off[q]; m < off[q + 1]; ++m) {
+    int bidx = INT_MAX;
+    const int m0 = off[q], m1 = off[q + 1];
+    for (int m = m0 + lane; m < m1; m += 32) {
         float ax = a[3 * m], ay = a[3 * m + 1], az = a[3 * m + 2];
         float abx = b[3 * m] - ax, aby = b[3 * m + 1] - ay, abz = b[3 * m + 2] - az;
         float apx = px - ax, apy = py - ay, apz = pz - az;
@@ -375,19 +409,26 @@ __global__ void k_points_to_tubes(const float *__restrict__ pts, int nq, const f
         float dist = sqrtf(dx * dx + dy * dy + dz * dz);
         float r = (1.f - t) * r1[m] + t * r2[m];
         float score = fabsf(dist - r);
-        if (score != score && bidx < 0) { nan_first = true; }
-        if (score < best) { best = score; bidx = m - off[q]; bvx = dx; bvy = dy; bvz = dz; br = r; }
+        if (score < best) { best = score; bidx = m - m0; bvx = dx; bvy = dy; bvz = dz; br = r; }
     }
-    (void)nan_first;
-    out_vec[3 * q] = bvx; out_vec[3 * q + 1] = bvy; out_vec[3 * q + 2] = bvz;
-    out_idx[q] = bidx;
-    out_r[q] = br;
+    for (int o = 16; o; o >>= 1) {
+        float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        float ox = __shfl_xor_sync(0xffffffffu, bvx, o), oy = __shfl_xor_sync(0xffffffffu, bvy, o);
+        float oz = __shfl_xor_sync(0xffffffffu, bvz, o), orr = __shfl_xor_sync(0xffffffffu, br, o);
+        if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bvx = ox; bvy = oy; bvz = oz; br = orr; }
+    }
+    if (lane == 0) {
+        out_vec[3 * q] = bvx; out_vec[3 * q + 1] = bvy; out_vec[3 * q + 2] = bvz;
+        out_idx[q] = bidx == INT_MAX ? -1 : bidx;
+        out_r[q] = br;
+    }
 }
 
 extern "C" int st_points_to_tubes(const float *pts, int64_t n_q, const float *a, const float *b, const float *r1, const float *r2,
                                   const int32_t *tube_off, float *out_vec, int32_t *out_idx, float *out_r, void *stream) {
     if (n_q == 0) return ST_OK;
-    k_points_to_tubes<<<(unsigned)cdiv(n_q, 128), 128, 0, (cudaStream_t)stream>>>(pts, (int)n_q, a, b, r1, r2, tube_off, out_vec, out_idx, out_r);
+    k_points_to_tubes<<<(unsigned)cdiv(n_q * 32, 128), 128, 0, (cudaStream_t)stream>>>(pts, (int)n_q, a, b, r1, r2, tube_off, out_vec, out_idx, out_r);
     ST_CHECK_LAUNCH();
     return ST_OK;
 }

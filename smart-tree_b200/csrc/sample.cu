@@ -12,6 +12,9 @@ using namespace st;
 
 constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 
+// debug counters of the last launch's block 0 (cycles per phase, iterations, path vertices)
+__device__ unsigned long long g_st_stats[8];
+
 __global__ void k_st_init(const int32_t *__restrict__ pred, const float *__restrict__ tree_dist, int n, float *distw,
                           uint8_t *alloc, int32_t *branch_id, unsigned long long *best, const int32_t *__restrict__ comp_off,
                           int n_comp, unsigned long long *keys, int32_t *vals) {
@@ -89,6 +92,9 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __shared__ int s_minpos, s_len, s_term, s_parent, s_rbits;
     int cursor = 0, bid = 0, pcur = 0;
+    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define ST_PHASE(i) do { if (tid == 0) { long long _t = clock64(); st[i] += (unsigned long long)(_t - tc); tc = _t; } } while (0)
     while (true) {
         // ---- 1. farthest live vertex
         int f = -1;
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
             cursor += blockDim.x;
         }
         if (f < 0) break;
+        ST_PHASE(0);
         // ---- 2. trace the route to the first allocated ancestor (path.py:9-16)
         if (tid == 0) {
             int len = 0, i = f;
@@ -121,7 +128,9 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
             s_rbits = 0;
         }
         __syncthreads();
+        ST_PHASE(1);
         const int len = s_len;
+        if (tid == 0) { st[5] += 1; st[6] += len; }
         const int *path = a.path_out + base + pcur;   // farthest first; position pos = len-1-jj is root side first
         // ---- 3. search radius = max radius over the path
         float rl = 0.f;
@@ -137,9 +146,12 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
             for (int jj = warp; jj < len; jj += (blockDim.x >> 5))
                 scan_path_vertex<true>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
             __syncthreads();
+            ST_PHASE(2);
             for (int jj = warp; jj < len; jj += (blockDim.x >> 5))
                 scan_path_vertex<false>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
         }
+        __syncthreads();
+        ST_PHASE(3);
         // ---- 6. the path itself
         for (int jj = tid; jj < len; jj += blockDim.x) {
             int v = base + path[jj];
@@ -164,8 +176,10 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
             pcur += len;
         }
         __syncthreads();
+        ST_PHASE(4);
     }
     if (tid == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
+    if (tid == 0 && c == 0) for (int i = 0; i < 8; ++i) g_st_stats[i] = st[i];
 }
 
 static size_t sort_bytes(int64_t n) {
@@ -209,5 +223,12 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
                  path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path};
     k_sample_tree<<<n_comp, 1024, 0, s>>>(a);
     ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// debug only (not part of include/st_b200.h): cycles spent by component 0 in
+// [find, trace, claim, resolve, finish], iterations, traced path vertices
+extern "C" int st_debug_sample_stats(unsigned long long *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_stats, sizeof(unsigned long long) * 8));
     return ST_OK;
 }

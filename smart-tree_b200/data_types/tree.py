@@ -28,64 +28,65 @@ class TreeSkeleton:
         return [t for b in self.branches.values() for t in b.to_tubes()]
 
     def repair(self, device=None):
-        """Prepend to each branch the point of its parent branch's tube surface model nearest to
-        the branch start (tree.py:73-92, queries.py:107-133).  All queries are evaluated against the
-        parents as they are BEFORE this call's edits only when the parent comes later in iteration
-        order -- the reference mutates branches in dict order, so a parent visited earlier is
-        already extended; that order dependence is reproduced by processing in waves."""
+        """Prepend to each branch the point of its parent branch's tube model nearest to the branch
+        start (tree.py:73-92, queries.py:107-133).  The reference visits branches in dict order and a
+        parent always precedes its children (parent ids are ids of earlier-emitted branches), so a
+        child sees its parent already repaired.  The same result is obtained level by level: all
+        branches of one tree depth are resolved with ONE st_points_to_tubes launch."""
         from .. import ops
         dev = torch.device(device) if device is not None else torch.device("cuda")
-        ids = set(self.branches.keys())
-        todo = [b for b in self.branches.values() if b.parent_id in ids]
-        if not todo:
-            return
-        # A child must see its parent's *current* geometry.  Parents with smaller dict position are
-        # already repaired when the child is visited.  Process branches in dict order, batching
-        # maximal runs whose parents are not part of the same run.
-        order = list(self.branches.values())
-        pos = {b._id: i for i, b in enumerate(order)}
-        i = 0
-        run: List[BranchSkeleton] = []
-        run_ids = set()
-
-        def flush():
-            if not run:
-                return
-            pts, a, b_, r1, r2, off = [], [], [], [], [], [0]
-            for br in run:
-                par = self.branches[br.parent_id]
-                pts.append(br.xyz[0].reshape(1, 3))
-                a.append(par.xyz[:-1]); b_.append(par.xyz[1:])
-                r1.append(par.radii[:-1].reshape(-1)); r2.append(par.radii[1:].reshape(-1))
-                off.append(off[-1] + len(par) - 1)
-            f = lambda ts: torch.cat(ts).float().contiguous().to(dev)
-            vec, _, _ = ops.points_to_tubes(f(pts), f(a), f(b_), f(r1), f(r2), torch.tensor(off, dtype=torch.int32, device=dev))
-            vec = vec.cpu()
-            for k, br in enumerate(run):
-                conn = br.xyz[0].reshape(1, 3).cpu() + vec[k].reshape(1, 3)
-                br.xyz = torch.cat((conn, br.xyz))
-                br.radii = torch.cat((br.radii[[0]], br.radii))
-            run.clear(); run_ids.clear()
-
-        for br in order:
-            if br.parent_id not in ids:
+        ids = self.branches
+        depth, waves = {}, {}
+        for bid, br in ids.items():
+            if br.parent_id not in ids or br.parent_id == bid:
                 continue
-            # parent edited in this very run (earlier in order) -> its new geometry is needed first
-            if br.parent_id in run_ids or br._id == br.parent_id:
-                flush()
-            run.append(br); run_ids.add(br._id)
-        flush()
+            if br.parent_id > bid:      # would see an un-repaired parent in dict order: handle serially
+                depth[bid] = None
+                continue
+            d = (depth.get(br.parent_id) or 0) + 1
+            depth[bid] = d
+            waves.setdefault(d, []).append(br)
+        late = [ids[b] for b, d in depth.items() if d is None]
+        for d in sorted(waves) + ([None] if late else []):
+            run = waves[d] if d is not None else late
+            pts = torch.stack([br.xyz[0] for br in run])
+            pa = [ids[br.parent_id] for br in run]
+            a = torch.cat([p.xyz[:-1] for p in pa]); b_ = torch.cat([p.xyz[1:] for p in pa])
+            r1 = torch.cat([p.radii[:-1].reshape(-1) for p in pa]); r2 = torch.cat([p.radii[1:].reshape(-1) for p in pa])
+            off = torch.tensor([0] + [len(p) - 1 for p in pa], dtype=torch.int64).cumsum(0).int()
+            f = lambda t: t.float().contiguous().to(dev, non_blocking=True)
+            vec, _, _ = ops.points_to_tubes(f(pts), f(a), f(b_), f(r1), f(r2), off.to(dev))
+            conn = pts + vec.cpu()
+            for k, br in enumerate(run):
+                br.xyz = torch.cat((conn[k:k + 1], br.xyz))
+                br.radii = torch.cat((br.radii[[0]], br.radii))
+
+    def branch_lengths(self):
+        """Polyline length of every branch in one vectorised pass (== BranchSkeleton.length)."""
+        bs = list(self.branches.values())
+        xyz = torch.cat([b.xyz for b in bs])
+        n = torch.tensor([len(b) for b in bs])
+        seg = (xyz[1:] - xyz[:-1]).norm(dim=1)
+        end = n.cumsum(0)
+        seg = torch.cat([seg, seg.new_zeros(1)])
+        seg[end - 1] = 0                                   # no segment across a branch boundary
+        cs = torch.cat([seg.new_zeros(1, dtype=torch.float64), seg.double().cumsum(0)])
+        return (cs[end] - cs[end - n]).float()
 
     def prune(self, min_radius: float, min_length: float, root_id=None):
+        """tree.py:94-121: drop branches that are too short / too thin, and everything below them."""
+        if not self.branches:
+            return TreeSkeleton(0, {})
         root_id = min(self.branches.keys()) if root_id is None else root_id
+        lengths = self.branch_lengths().tolist()
         keep = {root_id: self.branches[root_id]}
         remove = {}
-        for bid, b in self.branches.items():
+        for (bid, b), length in zip(self.branches.items(), lengths):
             if b.parent_id not in keep and b._id != root_id:
                 remove[bid] = b
-            elif b.length < min_length:
+            elif length < min_length:
                 remove[bid] = b
-            elif b.initial_radius < min_radius:
+            elif float(max(b.radii[0], b.radii[-1])) < min_radius:
                 remove[bid] = b
             else:
                 keep[bid] = b
@@ -93,11 +94,22 @@ class TreeSkeleton:
         return TreeSkeleton(0, remove)
 
     def smooth(self, kernel_size=5):
-        """Zero-padded box filter on the radii; turns radii [N,1] into [N] (quirk C-17)."""
+        """Zero-padded box filter on the radii; turns radii [N,1] into [N] (quirk C-17).  All branches
+        are filtered by one conv1d over their concatenation with kernel_size//2 zeros between them,
+        which is arithmetically the per-branch `padding="same"` convolution of the reference."""
+        todo = [b for b in self.branches.values() if b.radii.shape[0] > kernel_size]
+        if not todo:
+            return
+        pad = kernel_size // 2
+        z = torch.zeros(pad)
+        sig = torch.cat([t for b in todo for t in (b.radii.reshape(-1).float(), z)])
         kernel = torch.ones(1, 1, kernel_size) / kernel_size
-        for b in self.branches.values():
-            if b.radii.shape[0] > kernel_size:
-                b.radii = F.conv1d(b.radii.reshape(1, 1, -1), kernel, padding="same").reshape(-1)
+        out = F.conv1d(sig.reshape(1, 1, -1), kernel, padding="same").reshape(-1)
+        o = 0
+        for b in todo:
+            n = b.radii.shape[0]
+            b.radii = out[o:o + n].clone()
+            o += n + pad
 
     @property
     def length(self):

@@ -93,10 +93,17 @@ class SingleTreeInference:
             z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
             return BlockBatch(z(0, 6), z(0, 4, dt=torch.int32), z(0, dt=torch.bool), self.block_centres, z(0, dt=torch.int32),
                               self.point_index, self.point_block)
-        pb = self.point_block.long()
-        big = torch.full((nb, 3), float("inf"), device=dev)
-        lo = big.scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amin")
-        hi = (-big).scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amax")
+        if nb <= 64:          # points are block-major: per-block bounding box = min/max of a contiguous slice
+            cnt = torch.bincount(self.point_block.long(), minlength=nb).cumsum(0).tolist()
+            seg = [(0 if b == 0 else cnt[b - 1], cnt[b]) for b in range(nb)]
+            inf = torch.full((3,), float("inf"), device=dev)
+            lo = torch.stack([pts[a:b, :3].min(0)[0] if b > a else inf for a, b in seg])
+            hi = torch.stack([pts[a:b, :3].max(0)[0] if b > a else -inf for a, b in seg])
+        else:
+            pb = self.point_block.long()
+            big = torch.full((nb, 3), float("inf"), device=dev)
+            lo = big.scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amin")
+            hi = (-big).scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amax")
         vs = torch.tensor(self.voxel_size, dtype=torch.float32, device=dev)
         grid = _round_half_away((hi - lo) / vs).int().contiguous()                     # spconv calc_meta_data
         pc, rep, coords = ops.voxelize(pts, self.point_block.contiguous(), lo.contiguous(), grid, float(vs.item()))

@@ -7,6 +7,7 @@ import torch
 from ..data_types.cloud import Cloud
 from ..dataset.dataset import load_dataloader
 from ..engine import SmartTreeEngine
+from .._timing import section
 
 
 def load_model(model_path, weights_path, device=torch.device("cuda:0"), bn_eps=1e-4):
@@ -38,13 +39,18 @@ class ModelInference:
         moves it straight back, pipeline.py:63)."""
         if cloud.xyz.device.type != "cuda":
             cloud = cloud.to_device(self.device)
-        ds = load_dataloader(cloud, self.voxel_size, self.block_size, self.buffer_size, self.num_workers, self.batch_size)
-        bb = ds.voxelize_all()
+        with section("infer.blocks"):
+            ds = load_dataloader(cloud, self.voxel_size, self.block_size, self.buffer_size, self.num_workers, self.batch_size)
+        with section("infer.voxelize"):
+            bb = ds.voxelize_all()
         self.last_batch = bb
         if bb.feats.shape[0] == 0:
             z = torch.zeros(0, 3, device=cloud.xyz.device)
             return Cloud(xyz=z, rgb=z.clone(), medial_vector=z.clone(), class_l=torch.zeros(0, 1, dtype=torch.int64, device=z.device))
-        preds = self.model.forward(bb.feats[:, :3], bb.coords, fused_outputs=True)
+        with section("infer.levels"):
+            levels = self.model.build_levels(bb.coords)
+        with section("infer.unet"):
+            preds = self.model.forward(bb.feats[:, :3], bb.coords, levels=levels, fused_outputs=True)
         lc = Cloud(xyz=bb.feats[:, :3], rgb=bb.feats[:, 3:6], medial_vector=preds["medial_vector"],
                    class_l=preds["class_idx"].long().unsqueeze(1))
         self.last_preds = preds

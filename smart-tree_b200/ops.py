@@ -264,7 +264,7 @@ def sssp(row_ptr, col, w, n, sources, want_sweeps=False):
     dev = row_ptr.device
     dist = torch.empty(n, dtype=F32, device=dev)
     pred = torch.empty(n, dtype=I32, device=dev)
-    ctl = torch.zeros(64, dtype=I32, device=dev)
+    ctl = torch.empty(64 + n, dtype=I32, device=dev)
     sweeps = C.c_int32(0)
     _count("sssp")
     _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], _ptr(dist), _ptr(pred),

@@ -13,6 +13,7 @@ import torch
 from .data_types.cloud import Cloud
 from .data_types.tree import DisjointTreeSkeleton
 from .util.file import load_cloud, save_skeleton
+from ._timing import section
 
 
 class Pipeline:
@@ -65,8 +66,11 @@ class Pipeline:
 
     def post_process(self, skeleton: DisjointTreeSkeleton):
         if self.prune_skeletons:
-            skeleton.prune(min_length=self.min_skeleton_length, min_radius=self.min_skeleton_radius)
+            with section("post.prune"):
+                skeleton.prune(min_length=self.min_skeleton_length, min_radius=self.min_skeleton_radius)
         if self.repair_skeletons:
-            skeleton.repair(device=self.device)
+            with section("post.repair"):
+                skeleton.repair(device=self.device)
         if self.smooth_skeletons:
-            skeleton.smooth(self.smooth_kernel_size)
+            with section("post.smooth"):
+                skeleton.smooth(self.smooth_kernel_size)

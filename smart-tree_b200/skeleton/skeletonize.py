@@ -10,6 +10,7 @@ from typing import List
 import torch
 
 from .. import ops
+from .._timing import section
 from ..data_types.cloud import Cloud
 from ..data_types.graph import Graph
 from ..data_types.tree import DisjointTreeSkeleton, TreeSkeleton
@@ -27,70 +28,102 @@ class Skeletonizer:
         self.device = device
         self.last = None       # intermediate tensors of the last call (for tests / diagnostics)
 
+    @staticmethod
+    def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp) -> List[TreeSkeleton]:
+        """One gather + one device->host copy for the node coordinates / radii of every branch of
+        every component, then cheap CPU slicing into BranchSkeleton objects."""
+        from ..data_types.branch import BranchSkeleton
+        counts = torch.stack([cnb, cnp]).cpu()
+        cnb_h, cnp_h, off_h = counts[0].tolist(), counts[1].tolist(), comp_off.cpu().tolist()
+        dev = path.device
+        seg = torch.cat([torch.arange(off_h[c], off_h[c] + cnp_h[c], device=dev) for c in range(ncomp)]) if ncomp else path[:0].long()
+        bseg = torch.cat([torch.arange(off_h[c], off_h[c] + cnb_h[c], device=dev) for c in range(ncomp)]) if ncomp else path[:0].long()
+        base = torch.repeat_interleave(comp_off[:-1], torch.tensor(cnp_h, device=dev))
+        gidx = path[seg].long() + base
+        nodes = torch.cat([sub_medial[gidx], sub_radius[gidx].unsqueeze(1)], 1).cpu()
+        lens = blen[bseg].cpu().tolist()
+        pars = bpar[bseg].cpu().tolist()
+        skeletons, o, bi = [], 0, 0
+        for c in range(ncomp):
+            branches = {}
+            for bid in range(cnb_h[c]):
+                ln = lens[bi]
+                branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o:o + ln, :3], nodes[o:o + ln, 3:4])
+                o += ln
+                bi += 1
+            skeletons.append(TreeSkeleton(c, branches))
+        return skeletons
+
     def forward(self, cloud: Cloud) -> DisjointTreeSkeleton:
         cloud = cloud.to_device(self.device)
         if len(cloud) == 0:
             return DisjointTreeSkeleton([])
         # skeletonize.py:34-35
-        keep = outlier_removal(cloud.medial_pts, cloud.radius.unsqueeze(1), nb_points=8)
-        cloud = cloud.filter(keep)
+        with section("skel.outlier"):
+            keep = outlier_removal(cloud.medial_pts, cloud.radius.unsqueeze(1), nb_points=8)
+            cloud = cloud.filter(keep)
         n = len(cloud)
         if n == 0:
             return DisjointTreeSkeleton([])
         medial = cloud.medial_pts.contiguous()
         radius = cloud.radius.contiguous()
         # skeletonize.py:37-41 (the clamp applies to graph building only, quirk C-21)
-        graph: Graph = nn_graph(medial, radius.clamp(min=self.min_connection_length), K=self.K)
+        with section("skel.nn_graph"):
+            graph: Graph = nn_graph(medial, radius.clamp(min=self.min_connection_length), K=self.K)
         # skeletonize.py:43-45
-        label, roots, sizes = graph.ranked_components(self.minimum_graph_vertices)
+        with section("skel.components"):
+            label, roots, sizes = graph.ranked_components(self.minimum_graph_vertices)
         ncomp = int(roots.shape[0])
         if ncomp == 0:
             self.last = dict(keep=keep, n_components=0)
             return DisjointTreeSkeleton([])
-        dev = medial.device
-        # rank of each vertex's component (-1 = dropped), then vertices grouped by rank, ascending id inside
-        rank_of_root = torch.full((n,), -1, dtype=torch.int64, device=dev)
-        rank_of_root[roots] = torch.arange(ncomp, device=dev)
-        vrank = rank_of_root[label.long()]
-        sel = torch.nonzero(vrank >= 0).flatten()
-        order = sel[torch.argsort(vrank[sel], stable=True)]               # new id -> old vertex id
-        m = int(order.shape[0])
-        new_id = torch.full((n,), -1, dtype=torch.int32, device=dev)
-        new_id[order] = torch.arange(m, dtype=torch.int32, device=dev)
-        comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
-        comp_off[1:] = torch.cumsum(sizes, 0)
-        comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
-        # induced edges, renumbered (skeletonize.py:60-71)
-        e = graph.edges.long()
-        esel = new_id[e[:, 0]] >= 0
-        sub_edges = new_id[e[esel]].contiguous()
-        sub_w = graph.edge_weights[esel].contiguous()
-        row_ptr, col, w = ops.csr_build(sub_edges, sub_w, m)
-        sub_xyz = cloud.xyz[order]
-        sub_medial = medial[order].contiguous()
-        sub_radius = radius[order].contiguous()
-        # root of each component = first argmin of surface y (cloud.py:205-206)
-        y = sub_xyz[:, 1].contiguous()
-        miny = torch.full((ncomp,), float("inf"), device=dev).scatter_reduce(0, comp_of, y, "amin")
-        cand = torch.where(y == miny[comp_of], torch.arange(m, device=dev), torch.full((m,), m, device=dev))
-        src = torch.full((ncomp,), m, dtype=torch.int64, device=dev).scatter_reduce(0, comp_of, cand, "amin")
+        with section("skel.regroup_csr"):
+            dev = medial.device
+            # rank of each vertex's component (-1 = dropped), then vertices grouped by rank, ascending id inside
+            rank_of_root = torch.full((n,), -1, dtype=torch.int64, device=dev)
+            rank_of_root[roots] = torch.arange(ncomp, device=dev)
+            vrank = rank_of_root[label.long()]
+            sel = torch.nonzero(vrank >= 0).flatten()
+            order = sel[torch.argsort(vrank[sel], stable=True)]               # new id -> old vertex id
+            m = int(order.shape[0])
+            new_id = torch.full((n,), -1, dtype=torch.int32, device=dev)
+            new_id[order] = torch.arange(m, dtype=torch.int32, device=dev)
+            comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
+            comp_off[1:] = torch.cumsum(sizes, 0)
+            comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
+            # induced edges, renumbered (skeletonize.py:60-71)
+            e = graph.edges.long()
+            esel = new_id[e[:, 0]] >= 0
+            sub_edges = new_id[e[esel]].contiguous()
+            sub_w = graph.edge_weights[esel].contiguous()
+            row_ptr, col, w = ops.csr_build(sub_edges, sub_w, m)
+            sub_xyz = cloud.xyz[order]
+            sub_medial = medial[order].contiguous()
+            sub_radius = radius[order].contiguous()
+            # root of each component = first argmin of surface y (cloud.py:205-206)
+            y = sub_xyz[:, 1].contiguous()
+            if ncomp <= 64:       # components are contiguous segments: a plain argmin per segment
+                off_l = comp_off.tolist()
+                src = torch.stack([torch.argmin(y[off_l[c]:off_l[c + 1]]) + off_l[c] for c in range(ncomp)])
+            else:
+                miny = torch.full((ncomp,), float("inf"), device=dev).scatter_reduce(0, comp_of, y, "amin")
+                cand = torch.where(y == miny[comp_of], torch.arange(m, device=dev), torch.full((m,), m, device=dev))
+                src = torch.full((ncomp,), m, dtype=torch.int64, device=dev).scatter_reduce(0, comp_of, cand, "amin")
         # skeletonize.py:73-78
-        dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous())
-        is_root = torch.zeros(m, dtype=torch.uint8, device=dev)
-        is_root[src] = 1
-        # skeletonize.py:80-85
-        tdist = ops.tree_distances(sub_medial, pred, is_root)
-        off32 = comp_off.int().contiguous()
-        pred_local = torch.where(pred >= 0, pred - off32[comp_of], pred).contiguous()
+        with section("skel.sssp"):
+            dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous())
+        with section("skel.tree_dist"):
+            is_root = torch.zeros(m, dtype=torch.uint8, device=dev)
+            is_root[src] = 1
+            # skeletonize.py:80-85
+            tdist = ops.tree_distances(sub_medial, pred, is_root)
+            off32 = comp_off.int().contiguous()
+            pred_local = torch.where(pred >= 0, pred - off32[comp_of], pred).contiguous()
         # skeletonize.py:87-93
-        path, blen, bpar, cnb, cnp = ops.sample_tree(sub_medial, sub_radius, pred_local, tdist, off32, _cell_size(sub_radius))
-        cnb_h, cnp_h, off_h = cnb.cpu().tolist(), cnp.cpu().tolist(), comp_off.cpu().tolist()
-        skeletons: List[TreeSkeleton] = []
-        for c in range(ncomp):
-            o = off_h[c]
-            seg_pts, seg_rad = sub_medial[o:off_h[c + 1]], sub_radius[o:off_h[c + 1]]
-            branches = branches_from_segment(seg_pts, seg_rad, path[o:o + cnp_h[c]], blen[o:o + cnb_h[c]], bpar[o:o + cnb_h[c]])
-            skeletons.append(TreeSkeleton(c, branches))
+        with section("skel.sample_tree"):
+            path, blen, bpar, cnb, cnp = ops.sample_tree(sub_medial, sub_radius, pred_local, tdist, off32, _cell_size(sub_radius))
+        with section("skel.emit"):
+            skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp)
         self.last = dict(keep=keep, order=order, comp_off=comp_off, pred=pred_local, dist=dist, tree_dist=tdist, roots=src,
                          path=path, branch_len=blen, branch_parent=bpar, comp_n_branches=cnb, comp_n_path=cnp,
                          n_components=ncomp, edges=graph.edges, edge_weights=graph.edge_weights)
