@@ -177,31 +177,43 @@ struct SsspCtl {
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                               const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl) {
+    // Each warp owns groups of 32 consecutive vertices.  Lanes poll their own dirty word; every dirty
+    // vertex of the group is then relaxed by the WHOLE warp (lanes stride over its arcs), so one
+    // relaxation costs ~3 L2 round trips regardless of the degree.
     unsigned phase = 0;
-    const int stride = gridDim.x * blockDim.x;
-    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ngroups = (n + 31) >> 5;
     for (unsigned chunk = 0;; ++chunk) {
         bool consumed = false;
         for (int pass = 0; pass < SSSP_PASSES; ++pass) {
-            for (int v = t0; v < n; v += stride) {
-                if (__ldcg(dirty + v) == 0) continue;
-                if (atomicExch(dirty + v, 0) == 0) continue;
+            for (int g = w0; g < ngroups; g += nwarps) {
+                const int v = (g << 5) + lane;
+                int flag = v < n ? __ldcg(dirty + v) : 0;
+                unsigned mask = __ballot_sync(0xffffffffu, flag != 0);
+                if (!mask) continue;
+                if (flag) atomicExch(dirty + v, 0);
                 __threadfence();
                 consumed = true;
-                float cur = __ldcg(dist + v);
-                float best = cur;
-                const int b = __ldg(row_ptr + v), e = __ldg(row_ptr + v + 1);
-                for (int a = b; a < e; ++a) {
-                    float c = __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a));
-                    best = fminf(best, c);
-                }
-                if (best < cur) {
-                    __stcg(dist + v, best);
-                    __threadfence();
-                    for (int a = b; a < e; ++a) {
-                        int u = __ldg(col + a);
-                        // u can only improve through v if d[v] + w < d[u]
-                        if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicExch(dirty + u, 1);
+                while (mask) {
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int vv = (g << 5) + l;
+                    const int b = __ldg(row_ptr + vv), e = __ldg(row_ptr + vv + 1);
+                    const float cur = __ldcg(dist + vv);
+                    float best = cur;
+                    for (int a = b + lane; a < e; a += 32)
+                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (best < cur) {
+                        if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
+                        __syncwarp();
+                        for (int a = b + lane; a < e; a += 32) {
+                            const int u = __ldg(col + a);
+                            // u can only improve through vv if d[vv] + w < d[u]
+                            if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicExch(dirty + u, 1);
+                        }
                     }
                 }
             }

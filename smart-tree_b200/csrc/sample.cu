@@ -32,6 +32,14 @@ __global__ void k_st_init(const int32_t *__restrict__ pred, const float *__restr
     vals[v] = v;
 }
 
+__global__ void k_vertex_base(const int32_t *__restrict__ comp_off, int n_comp, int n, int32_t *__restrict__ vbase) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int lo = 0, hi = n_comp;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (comp_off[mid] <= v) lo = mid; else hi = mid; }
+    vbase[v] = comp_off[lo];
+}
+
 struct SampleArgs {
     const float *pts;
     const float *radii;
@@ -85,53 +93,99 @@ __device__ __forceinline__ void scan_path_vertex(const SampleArgs &a, int base, 
         }
 }
 
-__global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
-    const int c = blockIdx.x;
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_size() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+
+constexpr int JUMP_LEVELS = 11;   // ancestors 2^0 .. 2^10: a 1024-thread CTA resolves 1024 hops per round
+
+// jump[k][v] = 2^k-th ancestor of v in the predecessor tree (component-local ids, -1 past the root)
+__global__ void k_jump_level(const int32_t *__restrict__ prev, int32_t *__restrict__ next, const int32_t *__restrict__ comp_of_base,
+                             int n) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    int p = prev[v];
+    next[v] = p < 0 ? -1 : prev[comp_of_base[v] + p];
+}
+
+// One thread-block CLUSTER per connected component.  Every CTA of the cluster redundantly (and
+// deterministically) finds the next farthest vertex and traces its route by binary lifting -- thread j
+// resolves the j-th ancestor in <= 10 dependent loads, so 1024 hops cost one round instead of 1024
+// pointer-chase latencies -- then the CTAs split the path vertices between them for the claim /
+// resolve scans.  Two cluster barriers per branch.
+__global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int32_t *__restrict__ jump, int n_total) {
+    const unsigned CL = cluster_size(), cr = cluster_rank();
+    const int c = blockIdx.x / CL;
     const int base = a.comp_off[c];
     const int nc = a.comp_off[c + 1] - base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    __shared__ int s_minpos, s_len, s_term, s_parent, s_rbits;
+    const int gwarp = cr * 32 + warp, nwarp = CL * 32;
+    const int gtid = cr * 1024 + tid, nthr = CL * 1024;
+    __shared__ int s_minpos, s_first, s_term, s_rbits;
     int cursor = 0, bid = 0, pcur = 0;
-    unsigned long long st[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tc = clock64();
-#define ST_PHASE(i) do { if (tid == 0) { long long _t = clock64(); st[i] += (unsigned long long)(_t - tc); tc = _t; } } while (0)
+    __shared__ unsigned long long st[8];
+    __shared__ long long s_tc;
+    if (tid == 0) { for (int i = 0; i < 8; ++i) st[i] = 0; s_tc = clock64(); }
+#define ST_PHASE(i) do { if (tid == 0) { long long _t = clock64(); st[i] += (unsigned long long)(_t - s_tc); s_tc = _t; } } while (0)
     while (true) {
-        // ---- 1. farthest live vertex
+        // ---- 1. farthest live vertex: next entry of the (distance desc, index asc) list that is still unallocated
         int f = -1;
         while (cursor < nc) {
             if (tid == 0) s_minpos = INT_MAX;
             __syncthreads();
             int pos = cursor + tid;
             if (pos < nc) {
-                int v = a.order[base + pos];
-                if (a.distw[v] > 0.f) atomicMin(&s_minpos, pos);
+                int v = __ldg(a.order + base + pos);
+                if (__ldcg(a.distw + v) > 0.f) atomicMin(&s_minpos, pos);
             }
             __syncthreads();
             int m = s_minpos;
             __syncthreads();
-            if (m != INT_MAX) { f = a.order[base + m] - base; cursor = m + 1; break; }
+            if (m != INT_MAX) { f = __ldg(a.order + base + m) - base; cursor = m + 1; break; }
             cursor += blockDim.x;
         }
         if (f < 0) break;
         ST_PHASE(0);
-        // ---- 2. trace the route to the first allocated ancestor (path.py:9-16)
-        if (tid == 0) {
-            int len = 0, i = f;
-            int *out = a.path_out + base + pcur;
-            while (i >= 0 && !a.alloc[base + i] && pcur + len < nc) {
-                out[len++] = i;
-                i = a.pred[base + i];
-            }
-            s_len = len;
-            s_term = i;
-            s_parent = a.branch_id[base + (i >= 0 ? i : nc - 1)];   // -1 wraps to the last vertex (path.py:132)
-            s_rbits = 0;
+        // ---- 2. route to the first allocated ancestor (path.py:9-16), 1024 hops per round
+        int len = 0, cur = f, term = -1;
+        int *out = a.path_out + base + pcur;      // farthest first here; reversed when the branch is emitted
+        while (true) {
+            if (tid == 0) s_first = 1024;
+            __syncthreads();
+            int x = cur;
+#pragma unroll
+            for (int k = 0; k < 10; ++k)
+                if (((tid >> k) & 1) && x >= 0) x = __ldg(jump + (size_t)k * n_total + base + x);
+            bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
+            if (stop) atomicMin(&s_first, tid);
+            __syncthreads();
+            const int first = s_first;
+            if (tid == first) s_term = x;
+            const int cnt = min(first, max(nc - pcur - len, 0));
+            if (tid < cnt) out[len + tid] = x;
+            __syncthreads();
+            len += cnt;
+            if (first < 1024) { term = s_term; break; }
+            if (cnt < 1024) { term = -1; break; }           // defensive: path longer than the component
+            cur = __ldg(jump + (size_t)10 * n_total + base + cur);
+            __syncthreads();
         }
+        const int parent = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));   // -1 wraps to the last vertex (path.py:132)
+        if (tid == 0) s_rbits = 0;
         __syncthreads();
         ST_PHASE(1);
-        const int len = s_len;
         if (tid == 0) { st[5] += 1; st[6] += len; }
-        const int *path = a.path_out + base + pcur;   // farthest first; position pos = len-1-jj is root side first
+        const int *path = out;
         // ---- 3. search radius = max radius over the path
         float rl = 0.f;
         for (int jj = tid; jj < len; jj += blockDim.x) rl = fmaxf(rl, a.radii[base + path[jj]]);
@@ -141,45 +195,45 @@ __global__ void __launch_bounds__(1024) k_sample_tree(SampleArgs a) {
         const float r = __int_as_float(s_rbits);
         const float r2 = __fmul_rn(r, r);
         const bool emit = len >= 2;
-        // ---- 4./5. claim the nearest path vertex per point, then resolve the winners
-        if (r > 0.f) {
-            for (int jj = warp; jj < len; jj += (blockDim.x >> 5))
+        // ---- 4. claim: every point within r of the path records its nearest path vertex
+        if (r > 0.f)
+            for (int jj = gwarp; jj < len; jj += nwarp)
                 scan_path_vertex<true>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
-            __syncthreads();
-            ST_PHASE(2);
-            for (int jj = warp; jj < len; jj += (blockDim.x >> 5))
+        cluster_sync_all();
+        ST_PHASE(2);
+        // ---- 5. resolve the winners, 6. allocate the path itself
+        if (r > 0.f)
+            for (int jj = gwarp; jj < len; jj += nwarp)
                 scan_path_vertex<false>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
-        }
-        __syncthreads();
-        ST_PHASE(3);
-        // ---- 6. the path itself
-        for (int jj = tid; jj < len; jj += blockDim.x) {
+        for (int jj = gtid; jj < len; jj += nthr) {
             int v = base + path[jj];
             a.distw[v] = -1.f;
             a.alloc[v] = 1;
             if (emit) a.branch_id[v] = bid;
         }
-        __syncthreads();
-        // ---- 7. emit the branch (root side first)
+        cluster_sync_all();
+        ST_PHASE(3);
+        // ---- 7. emit the branch (root side first); only rank 0 touches the output
         if (emit) {
-            int *pp = a.path_out + base + pcur;
-            for (int jj = tid; jj < len / 2; jj += blockDim.x) {
-                int t = pp[jj];
-                pp[jj] = pp[len - 1 - jj];
-                pp[len - 1 - jj] = t;
-            }
-            if (tid == 0) {
-                a.branch_len[base + bid] = len;
-                a.branch_parent[base + bid] = s_parent;
+            if (cr == 0) {
+                for (int jj = tid; jj < len / 2; jj += blockDim.x) {
+                    int t = out[jj];
+                    out[jj] = out[len - 1 - jj];
+                    out[len - 1 - jj] = t;
+                }
+                if (tid == 0) {
+                    a.branch_len[base + bid] = len;
+                    a.branch_parent[base + bid] = parent;
+                }
             }
             ++bid;
             pcur += len;
         }
-        __syncthreads();
         ST_PHASE(4);
     }
-    if (tid == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
-    if (tid == 0 && c == 0) for (int i = 0; i < 8; ++i) g_st_stats[i] = st[i];
+    if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
+    if (tid == 0 && c == 0 && cr == 0) for (int i = 0; i < 8; ++i) g_st_stats[i] = st[i];
+    cluster_sync_all();   // no CTA of the cluster may exit while others still expect it at a barrier
 }
 
 static size_t sort_bytes(int64_t n) {
@@ -191,7 +245,7 @@ static size_t sort_bytes(int64_t n) {
 
 extern "C" size_t st_sample_tree_workspace_bytes(int64_t n, int32_t n_comp) {
     return grid_ws_bytes(n) + align_up(sort_bytes(n)) + 2 * align_up(n * 8) + 2 * align_up(n * 4) + align_up(n * 4) + align_up(n) +
-           align_up(n * 4) + align_up(n * 8) + 4096;
+           align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + align_up(n * 4) + 8192;
 }
 
 extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const int32_t *pred, const float *tree_dist,
@@ -210,6 +264,8 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     unsigned long long *keys2 = cv.take<unsigned long long>(n);
     int32_t *vals = cv.take<int32_t>(n);
     int32_t *order = cv.take<int32_t>(n);
+    int32_t *jump = cv.take<int32_t>((size_t)JUMP_LEVELS * n);
+    int32_t *vbase = cv.take<int32_t>(n);
     size_t sb = sort_bytes(n);
     void *sort_ws = cv.take<char>(sb);
     if (!cv.ok()) { set_error("st_sample_tree: workspace too small"); return ST_ERR_WORKSPACE; }
@@ -219,10 +275,48 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     GridBuild gb;
     int rc = build_grid(medial_pts, n, cell_size, cv, gb, s);
     if (rc) return rc;
+    // binary-lifting table over the (static) predecessor tree
+    k_vertex_base<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(comp_off, n_comp, (int)n, vbase);
+    ST_CHECK_LAUNCH();
+    ST_CHECK_CUDA(cudaMemcpyAsync(jump, pred, n * 4, cudaMemcpyDeviceToDevice, s));
+    for (int k = 1; k < JUMP_LEVELS; ++k) {
+        k_jump_level<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(jump + (size_t)(k - 1) * n, jump + (size_t)k * n, vbase, (int)n);
+        ST_CHECK_LAUNCH();
+    }
     SampleArgs a{medial_pts, radii, pred, comp_off, gb.g, gb.cell_start, gb.sorted, order, distw, alloc, branch_id, best,
                  path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path};
-    k_sample_tree<<<n_comp, 1024, 0, s>>>(a);
-    ST_CHECK_LAUNCH();
+    // largest cluster the device can co-schedule: more CTAs per component = more lanes on the scans
+    static int cluster_cached = 0;
+    int CL = cluster_cached;
+    if (CL == 0) {
+        cudaFuncSetAttribute((const void *)k_sample_tree, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        for (int cand : {16, 8, 4, 2, 1}) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cand);
+            cfg.blockDim = dim3(1024);
+            cudaLaunchAttribute at;
+            at.id = cudaLaunchAttributeClusterDimension;
+            at.val.clusterDim.x = cand; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+            cfg.attrs = &at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)k_sample_tree, &cfg) == cudaSuccess && nclusters >= 1) { CL = cand; break; }
+        }
+        cudaGetLastError();
+        if (CL == 0) CL = 1;
+        if (const char *e = getenv("ST_SAMPLE_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16) CL = v; }
+        cluster_cached = CL;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)n_comp * CL);
+    cfg.blockDim = dim3(1024);
+    cfg.stream = s;
+    cudaLaunchAttribute at;
+    at.id = cudaLaunchAttributeClusterDimension;
+    at.val.clusterDim.x = CL; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+    cfg.attrs = &at; cfg.numAttrs = 1;
+    int nt = (int)n;
+    const int32_t *jump_c = jump;
+    ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree, a, jump_c, nt));
     return ST_OK;
 }
 
