@@ -55,6 +55,31 @@ int st_voxelize(const float *points, int64_t n, int ld, const int32_t *point_blo
                 int32_t *pc_voxel_id, int32_t *rep_point, int32_t *coords,
                 int64_t *n_voxels_host, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ------------------------------------------------------------------ block tiling (inference)
+ * replaces SingleTreeInference.compute_blocks + cube_filter (pure torch in the reference: one O(N)
+ * mask, one device->host copy per block)   smart_tree/dataset/dataset.py:166-190 ; util/maths.py:145-155
+ * st_block_list : block id = torch.div(xyz, block_size, rounding_mode="floor"); blocks holding more
+ *                 than min_points points, sorted by (x,y,z) id as torch.unique(dim=0) does;
+ *                 block_ids[cap,3] (floats), kept_keys[cap] (opaque, for the next two calls).
+ * st_block_count / st_block_emit : every (block, point) pair with the point inside the block's
+ *                 enlarged cube  centre - half_cube <= p < centre + half_cube, centre = id*block_size
+ *                 + half_block (fp32, as the reference computes it); `reach` = how many neighbouring
+ *                 blocks a point can spill into per axis (ceil(buffer/block_size)).  Pairs come out
+ *                 block-major with ascending point index inside a block, together with each block's
+ *                 member bounding box block_lo / block_hi [n_blocks,3] (the voxeliser's range).      */
+size_t st_block_workspace_bytes(int64_t n, int64_t n_pairs);
+int st_block_list(const float *xyz, int64_t n, float block_size, int min_points, float *block_ids,
+                  uint64_t *kept_keys, int32_t cap, int64_t *n_blocks_host, void *workspace,
+                  size_t workspace_bytes, void *stream);
+int st_block_count(const float *xyz, int64_t n, const uint64_t *kept_keys, int32_t n_blocks,
+                   float block_size, float half_block, float half_cube, int reach, int32_t *offsets,
+                   int64_t *n_pairs_host, void *workspace, size_t workspace_bytes, void *stream);
+int st_block_emit(const float *xyz, int64_t n, const uint64_t *kept_keys, int32_t n_blocks,
+                  float block_size, float half_block, float half_cube, int reach,
+                  const int32_t *offsets, int64_t n_pairs, int64_t *point_index, int32_t *point_block,
+                  float *block_lo, float *block_hi, void *workspace, size_t workspace_bytes,
+                  void *stream);
+
 /* ------------------------------------------------------------------ K2 coordinate table + sub-manifold map
  * replaces spconv ops.get_indice_pairs(subm=True) reached from every SubMConv3d.forward
  *                                      smart_tree/model/model_blocks.py:24-32,123-144,258-282

@@ -28,6 +28,10 @@ SIGNATURES = {
     "st_sm_count": (C.c_int, [C.c_int]),
     "st_voxelize_workspace_bytes": (_sz, [_i64]),
     "st_voxelize": (C.c_int, [_p, _i64, C.c_int, _p, _p, _p, _i32, _f, _p, _p, _p, _pi64, _p, _sz, _p]),
+    "st_block_workspace_bytes": (_sz, [_i64, _i64]),
+    "st_block_list": (C.c_int, [_p, _i64, _f, C.c_int, _p, _p, _i32, _pi64, _p, _sz, _p]),
+    "st_block_count": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _f, C.c_int, _p, _pi64, _p, _sz, _p]),
+    "st_block_emit": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _f, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
     "st_hash_capacity": (_i64, [_i64]),
     "st_hash_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
     "st_subm_map": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),

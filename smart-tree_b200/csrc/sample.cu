@@ -56,41 +56,43 @@ struct SampleArgs {
     int32_t *path_out, *branch_len, *branch_parent, *comp_nb, *comp_np;
 };
 
+// One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered
+// 0 .. RW*RW-1 around the vertex's own cell, so a short path still spreads over every warp of the cluster.
 template <bool CLAIM>
-__device__ __forceinline__ void scan_path_vertex(const SampleArgs &a, int base, int nc, int v, unsigned pos, float r, float r2,
-                                                 int lane, bool emit, int bid) {
+__device__ __forceinline__ void scan_task(const SampleArgs &a, int base, int nc, int v, unsigned pos, int row, int R, float r,
+                                          float r2, int lane, bool emit, int bid) {
     const float px = a.pts[3 * (size_t)(base + v)], py = a.pts[3 * (size_t)(base + v) + 1], pz = a.pts[3 * (size_t)(base + v) + 2];
-    const float vr = a.radii[base + v];
     const Grid &g = a.g;
-    float rr = r * 1.0001f + 1e-7f;
-    int x0 = cell_coord(px - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(px + rr, g.ox, g.inv_h, g.nx);
-    int y0 = cell_coord(py - rr, g.oy, g.inv_h, g.ny), y1 = cell_coord(py + rr, g.oy, g.inv_h, g.ny);
-    int z0 = cell_coord(pz - rr, g.oz, g.inv_h, g.nz), z1 = cell_coord(pz + rr, g.oz, g.inv_h, g.nz);
-    for (int cz = z0; cz <= z1; ++cz)
-        for (int cy = y0; cy <= y1; ++cy) {
-            int rowc = (cz * g.ny + cy) * g.nx;
-            int beg = __ldg(a.cell_start + rowc + x0), end = __ldg(a.cell_start + rowc + x1 + 1);
-            for (int t = beg + lane; t < end; t += 32) {
-                float4 q = __ldg(a.sorted + t);
-                int gi = __float_as_int(q.w);
-                if (gi < base || gi >= base + nc) continue;
-                float d2 = dist2_exact(q.x, q.y, q.z, px, py, pz);
-                if (!(d2 < r2)) continue;
-                if (CLAIM) {
-                    unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
-                    atomicMin(a.best + gi, key);
-                } else {
-                    unsigned long long b = __ldcg(a.best + gi);
-                    if ((unsigned)(b & 0xFFFFFFFFull) != pos || (unsigned)(b >> 32) != __float_as_uint(d2)) continue;
-                    if (sqrtf(d2) < vr) {           // path.py:37-39: inside the radius of its nearest path vertex
-                        a.distw[gi] = -1.f;
-                        a.alloc[gi] = 1;
-                        if (emit) a.branch_id[gi] = bid;
-                    }
-                    __stcg(a.best + gi, BEST_NONE);
-                }
+    const float rr = r * 1.0001f + 1e-7f;
+    const int RW = 2 * R + 1;
+    const int cz = cell_coord(pz, g.oz, g.inv_h, g.nz) + row / RW - R;
+    const int cy = cell_coord(py, g.oy, g.inv_h, g.ny) + row % RW - R;
+    if (cz < cell_coord(pz - rr, g.oz, g.inv_h, g.nz) || cz > cell_coord(pz + rr, g.oz, g.inv_h, g.nz)) return;
+    if (cy < cell_coord(py - rr, g.oy, g.inv_h, g.ny) || cy > cell_coord(py + rr, g.oy, g.inv_h, g.ny)) return;
+    const int x0 = cell_coord(px - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(px + rr, g.ox, g.inv_h, g.nx);
+    const int rowc = (cz * g.ny + cy) * g.nx;
+    const int beg = __ldg(a.cell_start + rowc + x0), end = __ldg(a.cell_start + rowc + x1 + 1);
+    const float vr = CLAIM ? 0.f : a.radii[base + v];
+    for (int t = beg + lane; t < end; t += 32) {
+        float4 q = __ldg(a.sorted + t);
+        int gi = __float_as_int(q.w);
+        if (gi < base || gi >= base + nc) continue;
+        float d2 = dist2_exact(q.x, q.y, q.z, px, py, pz);
+        if (!(d2 < r2)) continue;
+        if (CLAIM) {
+            unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
+            atomicMin(a.best + gi, key);
+        } else {
+            unsigned long long b = __ldcg(a.best + gi);
+            if ((unsigned)(b & 0xFFFFFFFFull) != pos || (unsigned)(b >> 32) != __float_as_uint(d2)) continue;
+            if (sqrtf(d2) < vr) {           // path.py:37-39: inside the radius of its nearest path vertex
+                a.distw[gi] = -1.f;
+                a.alloc[gi] = 1;
+                if (emit) a.branch_id[gi] = bid;
             }
+            __stcg(a.best + gi, BEST_NONE);
         }
+    }
 }
 
 __device__ __forceinline__ void cluster_sync_all() {
@@ -196,15 +198,22 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         const float r2 = __fmul_rn(r, r);
         const bool emit = len >= 2;
         // ---- 4. claim: every point within r of the path records its nearest path vertex
+        const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;       // cells reached on either side of the vertex's cell
+        const int R2 = (2 * R + 1) * (2 * R + 1);
+        const long long ntask = (long long)len * R2;
         if (r > 0.f)
-            for (int jj = gwarp; jj < len; jj += nwarp)
-                scan_path_vertex<true>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
+            for (long long t = gwarp; t < ntask; t += nwarp) {
+                int jj = (int)(t / R2);
+                scan_task<true>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, emit, bid);
+            }
         cluster_sync_all();
         ST_PHASE(2);
         // ---- 5. resolve the winners, 6. allocate the path itself
         if (r > 0.f)
-            for (int jj = gwarp; jj < len; jj += nwarp)
-                scan_path_vertex<false>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), r, r2, lane, emit, bid);
+            for (long long t = gwarp; t < ntask; t += nwarp) {
+                int jj = (int)(t / R2);
+                scan_task<false>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, emit, bid);
+            }
         for (int jj = gtid; jj < len; jj += nthr) {
             int v = base + path[jj];
             a.distw[v] = -1.f;
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         ST_PHASE(4);
     }
     if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
-    if (tid == 0 && c == 0 && cr == 0) for (int i = 0; i < 8; ++i) g_st_stats[i] = st[i];
+    if (tid == 0 && c == 0 && cr == 0) { st[7] = CL; for (int i = 0; i < 8; ++i) g_st_stats[i] = st[i]; }
     cluster_sync_all();   // no CTA of the cluster may exit while others still expect it at a barrier
 }
 

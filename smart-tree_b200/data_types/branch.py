@@ -1,7 +1,7 @@
 """One skeleton branch (/root/reference/smart_tree/data_types/branch.py:19-75)."""
 from __future__ import annotations
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import List, Optional
 
 import torch
@@ -16,6 +16,9 @@ class BranchSkeleton:
     xyz: torch.Tensor     # [N,3]
     radii: torch.Tensor   # [N,1]
     child_id: Optional[int] = None
+    # (store, row, length): this branch's nodes are rows row+1 .. row+length of a shared [*,4] node array
+    # with one spare row in front (used by the batched post-processing fast paths); None = standalone
+    _flat: Optional[tuple] = field(default=None, repr=False, compare=False)
 
     def __post_init__(self):
         # the reference type-checks these shapes with torchtyping (tests/type_checks.py:9-13)

@@ -13,6 +13,13 @@ import torch.nn.functional as F
 from .branch import BranchSkeleton
 
 
+class NodeStore:
+    """Shared node array of a skeletoniser call: host [R,4] (xyz, radius) + its device twin."""
+
+    def __init__(self, host, dev):
+        self.host, self.dev = host, dev
+
+
 @dataclass
 class TreeSkeleton:
     _id: int
@@ -26,6 +33,18 @@ class TreeSkeleton:
 
     def to_tubes(self):
         return [t for b in self.branches.values() for t in b.to_tubes()]
+
+    def _flat_store(self):
+        """The shared NodeStore if every branch is still an untouched view into one (fast paths)."""
+        store = None
+        for b in self.branches.values():
+            f = b._flat
+            if f is None or (store is not None and f[0] is not store):
+                return None
+            if b.xyz.shape[0] != f[2] or b.xyz.data_ptr() != f[0].host[f[1] + 1].data_ptr():
+                return None
+            store = f[0]
+        return store
 
     def repair(self, device=None):
         """Prepend to each branch the point of its parent branch's tube model nearest to the branch
@@ -47,8 +66,13 @@ class TreeSkeleton:
             depth[bid] = d
             waves.setdefault(d, []).append(br)
         late = [ids[b] for b, d in depth.items() if d is None]
-        for d in sorted(waves) + ([None] if late else []):
-            run = waves[d] if d is not None else late
+        order = [waves[d] for d in sorted(waves)] + ([late] if late else [])
+        if not order:
+            return
+        store = self._flat_store()
+        if store is not None and store.dev.device == dev:
+            return self._repair_flat(order, store)
+        for run in order:
             pts = torch.stack([br.xyz[0] for br in run])
             pa = [ids[br.parent_id] for br in run]
             a = torch.cat([p.xyz[:-1] for p in pa]); b_ = torch.cat([p.xyz[1:] for p in pa])
@@ -61,9 +85,55 @@ class TreeSkeleton:
                 br.xyz = torch.cat((conn[k:k + 1], br.xyz))
                 br.radii = torch.cat((br.radii[[0]], br.radii))
 
+    def _repair_flat(self, order, store):
+        """repair() on the shared node array: the tubes of all parents of a wave are read straight from
+        the device twin, connection points are written into the spare rows on the device (so the next
+        wave sees repaired parents) and copied to the host once at the end."""
+        from .. import ops
+        nd = store.dev
+        dev = nd.device
+        ids = self.branches
+        repaired = set()
+        done_rows = []
+        for run in order:
+            q_row = torch.tensor([br._flat[1] for br in run], dtype=torch.int64)
+            ps, pc = [], []
+            for br in run:
+                _, o, ln = ids[br.parent_id]._flat
+                s0 = o if br.parent_id in repaired else o + 1
+                ps.append(s0); pc.append(o + ln - s0)                      # first tube row, tube count
+            meta = torch.tensor([ps, pc], dtype=torch.int64).to(dev, non_blocking=True)
+            q_row_d = q_row.to(dev, non_blocking=True)
+            cnt = meta[1]
+            off = torch.zeros(len(run) + 1, dtype=torch.int64, device=dev)
+            off[1:] = torch.cumsum(cnt, 0)
+            tube = torch.repeat_interleave(meta[0] - off[:-1], cnt) + torch.arange(int(sum(pc)), device=dev)
+            pts = nd[q_row_d + 1, :3].contiguous()
+            a, b_ = nd[tube], nd[tube + 1]
+            vec, _, _ = ops.points_to_tubes(pts, a[:, :3].contiguous(), b_[:, :3].contiguous(), a[:, 3].contiguous(),
+                                            b_[:, 3].contiguous(), off.int())
+            nd[q_row_d, :3] = pts + vec
+            repaired.update(br._id for br in run)
+            done_rows.append(q_row)
+        rows = torch.cat(done_rows)
+        store.host[rows, :3] = nd[rows.to(dev), :3].cpu()
+        for run in order:
+            for br in run:
+                _, o, ln = br._flat
+                br.xyz = store.host[o:o + ln + 1, :3]
+                br.radii = store.host[o:o + ln + 1, 3:4]
+                br._flat = None                                            # no longer the pristine view
+
     def branch_lengths(self):
         """Polyline length of every branch in one vectorised pass (== BranchSkeleton.length)."""
         bs = list(self.branches.values())
+        store = self._flat_store()
+        if store is not None:
+            # contiguous rows of the shared array: per-branch sums of consecutive-row distances
+            o = torch.tensor([b._flat[1] for b in bs]); n = torch.tensor([b._flat[2] for b in bs])
+            seg = (store.host[1:, :3] - store.host[:-1, :3]).norm(dim=1)
+            cs = torch.cat([seg.new_zeros(1, dtype=torch.float64), seg.double().cumsum(0)])
+            return (cs[o + n] - cs[o + 1]).float()
         xyz = torch.cat([b.xyz for b in bs])
         n = torch.tensor([len(b) for b in bs])
         seg = (xyz[1:] - xyz[:-1]).norm(dim=1)
@@ -79,14 +149,20 @@ class TreeSkeleton:
             return TreeSkeleton(0, {})
         root_id = min(self.branches.keys()) if root_id is None else root_id
         lengths = self.branch_lengths().tolist()
+        store = self._flat_store()
+        if store is not None:
+            o = torch.tensor([b._flat[1] for b in self.branches.values()]); n = torch.tensor([b._flat[2] for b in self.branches.values()])
+            init_r = torch.maximum(store.host[o + 1, 3], store.host[o + n, 3]).tolist()
+        else:
+            init_r = [float(max(b.radii[0], b.radii[-1])) for b in self.branches.values()]
         keep = {root_id: self.branches[root_id]}
         remove = {}
-        for (bid, b), length in zip(self.branches.items(), lengths):
+        for (bid, b), length, ir in zip(self.branches.items(), lengths, init_r):
             if b.parent_id not in keep and b._id != root_id:
                 remove[bid] = b
             elif length < min_length:
                 remove[bid] = b
-            elif float(max(b.radii[0], b.radii[-1])) < min_radius:
+            elif ir < min_radius:
                 remove[bid] = b
             else:
                 keep[bid] = b

@@ -42,44 +42,13 @@ class SingleTreeInference:
         self.compute_blocks()
 
     def compute_blocks(self):
-        xyz = self.cloud.xyz
-        dev = xyz.device
-        n = xyz.shape[0]
-        q = torch.div(xyz, self.block_size, rounding_mode="floor")                    # dataset.py:167-169
-        ids, counts = torch.unique(q, return_counts=True, dim=0)                      # sorted rows
-        ids = ids[counts > self.min_points]                                           # dataset.py:175 (quirk C-13)
+        """dataset.py:166-190 in three kernel launches (st_block_list / _count / _emit)."""
+        xyz = self.cloud.xyz.contiguous().float()
+        ids, pidx, pblk, lo, hi = ops.block_tiling(xyz, self.block_size, self.buffer_size, self.min_points)
         self.block_ids = ids
         self.block_centres = ids * self.block_size + (self.block_size / 2)
-        nb = ids.shape[0]
-        if nb == 0 or n == 0:
-            self.point_index = torch.zeros(0, dtype=torch.int64, device=dev)
-            self.point_block = torch.zeros(0, dtype=torch.int32, device=dev)
-            return
-        # dense lookup block-id triple -> block index
-        lo = ids.min(0)[0]
-        ext = (ids.max(0)[0] - lo + 1).long()
-        lin = lambda t: ((t[:, 0] - lo[0]).long() * ext[1] + (t[:, 1] - lo[1]).long()) * ext[2] + (t[:, 2] - lo[2]).long()
-        table = torch.full((int(ext.prod().item()),), -1, dtype=torch.int64, device=dev)
-        table[lin(ids)] = torch.arange(nb, device=dev)
-        cube = self.block_size + self.buffer_size * 2                                  # dataset.py:184
-        reach = int(-(-self.buffer_size // self.block_size)) if self.buffer_size > 0 else 0
-        pidx, pblk = [], []
-        rng = range(-reach, reach + 1)
-        ar = torch.arange(n, device=dev)
-        for dx in rng:
-            for dy in rng:
-                for dz in rng:
-                    cand = q + torch.tensor([dx, dy, dz], dtype=q.dtype, device=dev)
-                    inside = ((cand >= lo) & (cand < lo + ext.to(q.dtype))).all(1)
-                    b = torch.where(inside, table[lin(torch.where(inside[:, None], cand, lo.expand_as(cand)))], torch.full_like(ar, -1))
-                    ok = b >= 0
-                    bi = b.clamp(min=0)
-                    ok &= cube_filter(xyz, self.block_centres[bi], cube)
-                    pidx.append(ar[ok]); pblk.append(b[ok])
-        pidx, pblk = torch.cat(pidx), torch.cat(pblk)
-        order = torch.argsort(pblk * n + pidx)               # block-major, original point order inside a block
-        self.point_index = pidx[order]
-        self.point_block = pblk[order].int()
+        self.point_index, self.point_block = pidx, pblk
+        self.block_lo, self.block_hi = lo, hi
 
     def voxelize_all(self) -> BlockBatch:
         """Every block through the PointToVoxel restatement in one launch (dataset.py:192-226)."""
@@ -93,20 +62,10 @@ class SingleTreeInference:
             z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
             return BlockBatch(z(0, 6), z(0, 4, dt=torch.int32), z(0, dt=torch.bool), self.block_centres, z(0, dt=torch.int32),
                               self.point_index, self.point_block)
-        if nb <= 64:          # points are block-major: per-block bounding box = min/max of a contiguous slice
-            cnt = torch.bincount(self.point_block.long(), minlength=nb).cumsum(0).tolist()
-            seg = [(0 if b == 0 else cnt[b - 1], cnt[b]) for b in range(nb)]
-            inf = torch.full((3,), float("inf"), device=dev)
-            lo = torch.stack([pts[a:b, :3].min(0)[0] if b > a else inf for a, b in seg])
-            hi = torch.stack([pts[a:b, :3].max(0)[0] if b > a else -inf for a, b in seg])
-        else:
-            pb = self.point_block.long()
-            big = torch.full((nb, 3), float("inf"), device=dev)
-            lo = big.scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amin")
-            hi = (-big).scatter_reduce(0, pb[:, None].expand(-1, 3), pts[:, :3], "amax")
+        lo, hi = self.block_lo, self.block_hi                                         # each block cloud's own bounding box
         vs = torch.tensor(self.voxel_size, dtype=torch.float32, device=dev)
         grid = _round_half_away((hi - lo) / vs).int().contiguous()                     # spconv calc_meta_data
-        pc, rep, coords = ops.voxelize(pts, self.point_block.contiguous(), lo.contiguous(), grid, float(vs.item()))
+        pc, rep, coords = ops.voxelize(pts, self.point_block.contiguous(), lo.contiguous(), grid, float(self.voxel_size))
         feats = pts[rep.long()]
         mask = cube_filter(feats[:, :3], self.block_centres[coords[:, 0].long()], self.block_size)   # dataset.py:224
         return BlockBatch(feats, coords, mask, self.block_centres, pc, self.point_index, self.point_block)

@@ -13,7 +13,7 @@ I32, I64, F32, U8 = torch.int32, torch.int64, torch.float32, torch.uint8
 # ---- instrumentation (bench.py): number of libst_b200 kernels launched, optional per-conv CUDA events
 LAUNCHES = 0
 _conv_profile = None
-_KERNELS_PER_CALL = {"voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
+_KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
                      "sample_tree": 5, "tubes": 1}
 
@@ -53,6 +53,42 @@ def _req(t: torch.Tensor, dtype, name):
 
 def _ws(nbytes, device):
     return torch.empty(max(int(nbytes), 256), dtype=U8, device=device)
+
+
+# ------------------------------------------------------------------ block tiling
+def block_tiling(xyz, block_size, buffer_size, min_points=20, max_blocks=1 << 16):
+    """Returns block_ids [B,3] f32, point_index [T] i64, point_block [T] i32, block_lo / block_hi [B,3] f32."""
+    import numpy as np
+    lib = _lib.load()
+    _req(xyz, F32, "xyz")
+    n, dev = xyz.shape[0], xyz.device
+    ids = torch.empty((max_blocks, 3), dtype=F32, device=dev)
+    keys = torch.empty(max_blocks, dtype=I64, device=dev)
+    ws = _ws(lib.st_block_workspace_bytes(n, n), dev)
+    nb = C.c_int64(0)
+    _count("blocks")
+    _lib.check(lib.st_block_list(_ptr(xyz), n, float(block_size), int(min_points), _ptr(ids), _ptr(keys), max_blocks,
+                                 C.byref(nb), _ptr(ws), ws.numel(), _stream()), "st_block_list")
+    nb = nb.value
+    ids = ids[:nb]
+    # the reference evaluates these bounds in fp32 tensor arithmetic with Python-float scalars
+    half_block = float(np.float32(block_size / 2))
+    half_cube = float(np.float32((block_size + buffer_size * 2) / 2))
+    reach = int(-(-buffer_size // block_size)) if buffer_size > 0 else 0
+    offsets = torch.empty(max(n, 1), dtype=I32, device=dev)
+    npairs = C.c_int64(0)
+    _lib.check(lib.st_block_count(_ptr(xyz), n, _ptr(keys), nb, float(block_size), half_block, half_cube, reach, _ptr(offsets),
+                                  C.byref(npairs), _ptr(ws), ws.numel(), _stream()), "st_block_count")
+    t = npairs.value
+    pidx = torch.empty(t, dtype=I64, device=dev)
+    pblk = torch.empty(t, dtype=I32, device=dev)
+    lo = torch.empty((nb, 3), dtype=F32, device=dev)
+    hi = torch.empty((nb, 3), dtype=F32, device=dev)
+    if t > n:
+        ws = _ws(lib.st_block_workspace_bytes(n, t), dev)
+    _lib.check(lib.st_block_emit(_ptr(xyz), n, _ptr(keys), nb, float(block_size), half_block, half_cube, reach, _ptr(offsets), t,
+                                 _ptr(pidx), _ptr(pblk), _ptr(lo), _ptr(hi), _ptr(ws), ws.numel(), _stream()), "st_block_emit")
+    return ids, pidx, pblk, lo, hi
 
 
 # ------------------------------------------------------------------ voxelise

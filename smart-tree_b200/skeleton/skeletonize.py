@@ -31,25 +31,38 @@ class Skeletonizer:
     @staticmethod
     def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp) -> List[TreeSkeleton]:
         """One gather + one device->host copy for the node coordinates / radii of every branch of
-        every component, then cheap CPU slicing into BranchSkeleton objects."""
+        every component.  Nodes live in one shared [P+B,4] array (xyz, radius) with a spare row in
+        front of each branch, pre-filled with the branch's first node: `repair` later only has to
+        write the connection point there (its radius is the first node's radius by definition)."""
         from ..data_types.branch import BranchSkeleton
+        from ..data_types.tree import NodeStore
         counts = torch.stack([cnb, cnp]).cpu()
         cnb_h, cnp_h, off_h = counts[0].tolist(), counts[1].tolist(), comp_off.cpu().tolist()
         dev = path.device
-        seg = torch.cat([torch.arange(off_h[c], off_h[c] + cnp_h[c], device=dev) for c in range(ncomp)]) if ncomp else path[:0].long()
-        bseg = torch.cat([torch.arange(off_h[c], off_h[c] + cnb_h[c], device=dev) for c in range(ncomp)]) if ncomp else path[:0].long()
+        if sum(cnb_h) == 0:
+            return [TreeSkeleton(c, {}) for c in range(ncomp)]
+        seg = torch.cat([torch.arange(off_h[c], off_h[c] + cnp_h[c], device=dev) for c in range(ncomp)])
+        bseg = torch.cat([torch.arange(off_h[c], off_h[c] + cnb_h[c], device=dev) for c in range(ncomp)])
         base = torch.repeat_interleave(comp_off[:-1], torch.tensor(cnp_h, device=dev))
         gidx = path[seg].long() + base
-        nodes = torch.cat([sub_medial[gidx], sub_radius[gidx].unsqueeze(1)], 1).cpu()
-        lens = blen[bseg].cpu().tolist()
+        lens_d = blen[bseg].long()
+        starts = torch.cumsum(lens_d, 0) - lens_d
+        rep = torch.ones_like(gidx)
+        rep[starts] = 2                                          # first node of every branch twice
+        gidx = torch.repeat_interleave(gidx, rep)
+        nodes_dev = torch.cat([sub_medial[gidx], sub_radius[gidx].unsqueeze(1)], 1).contiguous()
+        nodes = nodes_dev.cpu()
+        lens = lens_d.cpu().tolist()
         pars = bpar[bseg].cpu().tolist()
+        store = NodeStore(nodes, nodes_dev)
         skeletons, o, bi = [], 0, 0
         for c in range(ncomp):
             branches = {}
             for bid in range(cnb_h[c]):
                 ln = lens[bi]
-                branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o:o + ln, :3], nodes[o:o + ln, 3:4])
-                o += ln
+                branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o + 1:o + 1 + ln, :3], nodes[o + 1:o + 1 + ln, 3:4],
+                                               _flat=(store, o, ln))
+                o += ln + 1
                 bi += 1
             skeletons.append(TreeSkeleton(c, branches))
         return skeletons

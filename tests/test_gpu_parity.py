@@ -99,6 +99,25 @@ def test_voxelize_exact():
     assert voff == rep.shape[0]
 
 
+@pytest.mark.parametrize("block,buffer", [(4, 0.4), (0.64, 0.4), (1.0, 0.0)])
+def test_block_tiling_exact(block, buffer):
+    """compute_blocks (dataset.py:166-190): kept blocks, their order, members and member order."""
+    ops = _ops()
+    tr = _synth(5, 60000)
+    xyz = P.centre_cloud(tr.xyz)
+    centres, members = P.compute_blocks(xyz, block, buffer)
+    ids, pidx, pblk, lo, hi = ops.block_tiling(_t(xyz), block, buffer)
+    got_centres = (ids * block + (block / 2)).cpu().numpy()
+    assert np.array_equal(got_centres, centres)
+    pidx, pblk = pidx.cpu().numpy(), pblk.cpu().numpy()
+    assert len(pidx) == sum(len(m) for m in members)
+    o = 0
+    for b, m in enumerate(members):
+        assert np.array_equal(pidx[o:o + len(m)], m) and np.all(pblk[o:o + len(m)] == b)
+        assert np.array_equal(lo[b].cpu().numpy(), xyz[m].min(0)) and np.array_equal(hi[b].cpu().numpy(), xyz[m].max(0))
+        o += len(m)
+
+
 # ------------------------------------------------------------------ convolution
 CONV_CASES = [(8, 8), (8, 16), (16, 8), (16, 16), (16, 32), (32, 16), (32, 32), (32, 64), (64, 32), (64, 64), (3, 8), (24, 40)]
 

@@ -54,6 +54,6 @@ cyc = {n: stats[i] for i, n in enumerate(names)}
 last = pipe.skeletonizer.last
 print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec,
                   "sample_tree_cycles": cyc, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
-                  "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
+                  "cluster_size": stats[7], "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
                   "skeleton_vertices": int(last["order"].shape[0]), "edges": int(last["edges"].shape[0]),
                   "voxels": int(pipe.model_inference.last_batch.feats.shape[0])}, indent=1))
