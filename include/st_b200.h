@@ -122,6 +122,17 @@ int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out
                    const float *residual, int res_ld, const float *in2, int in2_ld,
                    const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
 
+/* Tensor-core variant (tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM).  Same
+ * contract as st_conv_gather except that `wprep` is the weight tensor pre-arranged by
+ * st_conv_tc_prepare (st_conv_tc_weight_floats(ntaps,cin,cout) floats; -1 = unsupported channel
+ * counts: cin must divide 32 or be a multiple of 32, cout a multiple of 8) and `map` is mandatory.   */
+int64_t st_conv_tc_weight_floats(int ntaps, int cin, int cout);
+int st_conv_tc_prepare(const float *w, int ntaps, int cin, int cout, float *wprep, void *stream);
+int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps,
+                      const float *wprep, int cin, int cout, const float *scale, const float *shift,
+                      const float *residual, int res_ld, const float *in2, int in2_ld,
+                      const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
+
 /* Fused heads: the three SparseFC stacks (8->8,BN,ReLU, 8->4,BN,ReLU, 4->{1,3,2}), F.normalize,
  * exp(radius)*direction and argmax     smart_tree/model/model.py:83-85 ; model_blocks.py:258-282 ;
  *                                      smart_tree/model/model_inference.py:87-88

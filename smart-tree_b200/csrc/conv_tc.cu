@@ -1,0 +1,307 @@
+// Gather convolution on the 5th-generation tensor cores (tcgen05 / TMEM), fp32-grade accuracy.
+//
+//   out[i,:] = act(scale * sum_k W[k] . in[map[k,i],:] + shift + res[i,:] + W2 . in2[i,:])
+//
+// Implicit GEMM per CTA: M = 128 output rows, N = Cout (padded to a multiple of 16), K = 27*Cin
+// walked in stages of 32.  Per stage
+//   * 8 producer warps gather the neighbour rows (128-bit loads through L2; every feature array of
+//     the network is L2 resident), split each fp32 value into a TF32 head and an fp32 tail, and
+//     store both as K-major core-matrix tiles in shared memory (conflict-free 128-bit stores);
+//   * the weight tile (head + tail, pre-arranged by st_conv_tc_prepare) arrives by one 1-D bulk
+//     async copy (cp.async.bulk -> UBLKCP) that completes on the stage's mbarrier;
+//   * one elected thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x {hi*hi, lo*hi, hi*lo}: the
+//     3xTF32 split keeps ~21 mantissa bits, needed for the 1e-3 end-to-end tolerance) that
+//     accumulate in TMEM; tcgen05.commit releases the stage back to the producers.
+// Epilogue: the producer warps read their accumulator lanes with tcgen05.ld and apply the fused
+// BN affine / residual / identity 1x1 conv / ReLU, writing straight into the (possibly sliced) output.
+#include "common.cuh"
+
+using namespace st;
+
+namespace {
+
+constexpr int TC_M = 128;          // rows per CTA
+constexpr int TC_KS = 32;          // K elements per stage
+constexpr int TC_STAGES = 2;
+constexpr int TC_PRODUCERS = 256;  // 8 warps: 2 threads per row
+constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int A_TILE_FLOATS = TC_M * TC_KS;            // 4096 floats = 16 KB (one of hi / lo)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = 128 B between the two K chunks of one
+// MMA, SBO = 1024 B between 8-row groups (a stage row holds 8 chunks); descriptor version 1 (sm_100)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct TcArgs {
+    const float *in;
+    int in_ld;
+    const int32_t *map;
+    int n_out;
+    int ntaps;
+    const float *wprep;   // [nstages][2][npad*32] core-matrix tiles (hi, lo)
+    int cin, cout, npad, nstages;
+    const float *scale, *shift;
+    const float *res;
+    int res_ld;
+    const float *in2;
+    int in2_ld;
+    const float *w2;
+    int cin2;
+    float *out;
+    int out_ld;
+    int act;
+};
+
+__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // stage layout: A_hi (16 KB) | A_lo (16 KB) | B_hi (npad*128 B) | B_lo (npad*128 B)
+    const int b_tile_bytes = a.npad * TC_KS * 4;
+    const int stage_bytes = 2 * A_TILE_FLOATS * 4 + 2 * b_tile_bytes;
+    __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
+    __shared__ uint32_t tmem_base_sh;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
+
+    if (tid == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) tmem_alloc(&tmem_base_sh, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp < 8) {
+        // ================= producers (then epilogue) =================
+        const int rloc = 32 * (warp & 3) + lane;      // row within the tile == TMEM lane
+        const int half = warp >> 2;                   // which 4 of the 8 16-byte chunks of a stage row
+        const int row = blockIdx.x * TC_M + rloc;
+        const bool row_ok = row < a.n_out;
+        const uint32_t row_off = (uint32_t)((rloc >> 3) * 1024 + (rloc & 7) * 16);   // bytes inside a tile
+        int cached_tap = -1, cached_j = -1;
+        for (int s = 0; s < a.nstages; ++s) {
+            const int st = s % TC_STAGES;
+            if (s >= TC_STAGES) mbar_wait(&empty_bar[st], ((s / TC_STAGES) - 1) & 1);
+            uint8_t *stage = smem_raw + (size_t)st * stage_bytes;
+            if (tid == 0) {
+                // weight tile of this stage; its bytes complete on the same barrier
+                bulk_copy_g2s(stage + 2 * A_TILE_FLOATS * 4, a.wprep + (size_t)s * 2 * a.npad * TC_KS, 2 * b_tile_bytes, &full_bar[st]);
+            }
+            float4 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int kk = s * TC_KS + (half * 4 + q) * 4;          // first K index of this chunk
+                const int tap = kk / a.cin, c0 = kk - tap * a.cin;
+                if (tap != cached_tap) {
+                    cached_tap = tap;
+                    cached_j = (row_ok && tap < a.ntaps) ? __ldg(a.map + (size_t)tap * a.n_out + row) : -1;
+                }
+                x[q] = cached_j >= 0 ? __ldg((const float4 *)(a.in + (size_t)cached_j * a.in_ld + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float4 hi, lo;
+                hi.x = __uint_as_float(__float_as_uint(x[q].x) & 0xFFFFE000u); lo.x = x[q].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(x[q].y) & 0xFFFFE000u); lo.y = x[q].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(x[q].z) & 0xFFFFE000u); lo.z = x[q].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(x[q].w) & 0xFFFFE000u); lo.w = x[q].w - hi.w;
+                const uint32_t off = row_off + (uint32_t)(half * 4 + q) * 128;
+                *(float4 *)(stage + off) = hi;
+                *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
+            }
+            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            if (tid == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * b_tile_bytes);
+            else mbar_arrive(&full_bar[st]);
+        }
+        // ================= epilogue =================
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int ncols_half = a.npad / 2;                 // columns owned by this warp group
+        const int col0 = half * ncols_half;
+        for (int cb = 0; cb < ncols_half; cb += 8) {
+            const int c = col0 + cb;
+            float v[8];
+            tmem_ld8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c, v);
+            if (!row_ok || c >= a.cout) continue;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float sc = a.scale ? __ldg(a.scale + c + i) : 1.f;
+                float sh = a.shift ? __ldg(a.shift + c + i) : 0.f;
+                v[i] = fmaf(v[i], sc, sh);
+            }
+            if (a.res) {
+                const float4 *rp = (const float4 *)(a.res + (size_t)row * a.res_ld + c);
+                float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+            }
+            if (a.in2) {
+                float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                const float *xr = a.in2 + (size_t)row * a.in2_ld;
+                for (int ci = 0; ci < a.cin2; ++ci) {
+                    const float xv = __ldg(xr + ci);
+                    const float4 *wp = (const float4 *)(a.w2 + (size_t)ci * a.cout + c);
+                    float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                    e[0] = fmaf(xv, w0.x, e[0]); e[1] = fmaf(xv, w0.y, e[1]); e[2] = fmaf(xv, w0.z, e[2]); e[3] = fmaf(xv, w0.w, e[3]);
+                    e[4] = fmaf(xv, w1.x, e[4]); e[5] = fmaf(xv, w1.y, e[5]); e[6] = fmaf(xv, w1.z, e[6]); e[7] = fmaf(xv, w1.w, e[7]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += e[i];
+            }
+            if (a.act & ST_ACT_RELU) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            float4 *op = (float4 *)(a.out + (size_t)row * a.out_ld + c);
+            op[0] = make_float4(v[0], v[1], v[2], v[3]);
+            op[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+        tc_fence_before();
+    } else {
+        // ================= MMA issuer (one elected lane of warp 8) =================
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+        if (lane == 0) {
+            for (int s = 0; s < a.nstages; ++s) {
+                const int st = s % TC_STAGES;
+                mbar_wait(&full_bar[st], (s / TC_STAGES) & 1);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem_raw + (size_t)st * stage_bytes);
+                const uint32_t a_hi = sa, a_lo = sa + A_TILE_FLOATS * 4;
+                const uint32_t b_hi = sa + 2 * A_TILE_FLOATS * 4, b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                for (int j = 0; j < TC_KS / 8; ++j) {
+                    const uint32_t ko = (uint32_t)j * 256;       // two 128-byte K chunks per k-step
+                    umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_hi + ko), idesc, (s | j) ? 1u : 0u);
+                    umma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(b_hi + ko), idesc, 1u);
+                    umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_lo + ko), idesc, 1u);
+                }
+                umma_commit(&empty_bar[st]);      // stage reusable once these MMAs have read it
+            }
+            umma_commit(&accum_bar);              // accumulator complete
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+// w [ntaps, cin, cout] -> wprep [nstages][2][npad*32]: per stage the K-major core-matrix tile of the
+// TF32 heads followed by the tile of the tails; K index kk = tap*cin + c, zero padded.
+__global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, int cout, int npad, int nstages, float *__restrict__ wprep) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)nstages * npad * TC_KS;
+    if (idx >= total) return;
+    int s = (int)(idx / (npad * TC_KS));
+    int rem = (int)(idx % (npad * TC_KS));
+    int n = rem / TC_KS, kk = rem % TC_KS;
+    int K = s * TC_KS + kk;
+    int tap = K / cin, c = K % cin;
+    float v = (tap < ntaps && n < cout) ? w[((size_t)tap * cin + c) * cout + n] : 0.f;
+    float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    float lo = v - hi;
+    size_t pos = (size_t)(n >> 3) * 256 + (size_t)(kk >> 2) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
+    float *tile = wprep + (size_t)s * 2 * npad * TC_KS;
+    tile[pos] = hi;
+    tile[(size_t)npad * TC_KS + pos] = lo;
+}
+
+int tc_npad(int cout) { int n = (cout + 15) / 16 * 16; return n < 16 ? 16 : n; }
+int tc_nstages(int ntaps, int cin) { return (ntaps * cin + TC_KS - 1) / TC_KS; }
+bool tc_supported(int cin, int cout) { return cin >= 4 && cin % 4 == 0 && (TC_KS % cin == 0 || cin % TC_KS == 0) && cout % 8 == 0 && cout <= 256; }
+
+}  // namespace
+
+extern "C" int64_t st_conv_tc_weight_floats(int ntaps, int cin, int cout) {
+    if (!tc_supported(cin, cout)) return -1;
+    return (int64_t)tc_nstages(ntaps, cin) * 2 * tc_npad(cout) * TC_KS;
+}
+
+extern "C" int st_conv_tc_prepare(const float *w, int ntaps, int cin, int cout, float *wprep, void *stream) {
+    ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
+    int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
+    int64_t total = (int64_t)nst * npad * TC_KS;
+    k_tc_prepare<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, ntaps, cin, cout, npad, nst, wprep);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *wprep,
+                                 int cin, int cout, const float *scale, const float *shift, const float *residual, int res_ld,
+                                 const float *in2, int in2_ld, const float *w2, int cin2, float *out, int out_ld, int act,
+                                 void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_out == 0) return ST_OK;
+    ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
+    ST_REQUIRE(map != nullptr, "the tensor-core path needs an explicit gather map");
+    ST_REQUIRE(((uintptr_t)in & 15) == 0 && in_ld % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_ld % 4 == 0 && ((uintptr_t)wprep & 15) == 0,
+               "16-byte aligned rows required");
+    ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");
+    ST_REQUIRE(!in2 || (w2 && ((uintptr_t)w2 & 15) == 0), "in2 needs a 16-byte aligned w2");
+    const int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
+    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
+    const int smem = TC_STAGES * (2 * A_TILE_FLOATS * 4 + 2 * npad * TC_KS * 4) + 1024;
+    static int smem_set = 0;
+    if (smem > smem_set) {
+        ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        smem_set = smem;
+    }
+    k_conv_tc<<<(unsigned)cdiv(n_out, TC_M), TC_THREADS, smem, s>>>(a);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

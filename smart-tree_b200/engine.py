@@ -41,10 +41,16 @@ class ConvLayer:
     w: torch.Tensor                       # [taps, cin, cout]
     scale: Optional[torch.Tensor] = None
     shift: Optional[torch.Tensor] = None
+    w_tc: Optional[torch.Tensor] = None   # tensor-core layout (ops.conv_tc_prepare), built lazily on the device
 
     def to(self, dev):
         return ConvLayer(self.w.to(dev), None if self.scale is None else self.scale.to(dev),
                          None if self.shift is None else self.shift.to(dev))
+
+    def tc_weights(self):
+        if self.w_tc is None:
+            self.w_tc = ops.conv_tc_prepare(self.w)
+        return self.w_tc
 
 
 @dataclass
@@ -86,7 +92,9 @@ def build_levels(coords: torch.Tensor, depth: int) -> List[LevelIndex]:
 
 
 class SmartTreeEngine:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = "fma"):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = None):
+        import os
+        conv_impl = conv_impl or os.environ.get("ST_CONV_IMPL", "fma")
         sd = {k: v.detach().cpu() for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
         self.device = torch.device(device)
         self.eps = eps
@@ -153,8 +161,10 @@ class SmartTreeEngine:
 
     # ---- execution
     def _conv(self, x, layer: ConvLayer, nbr, n_out, relu, out=None, residual=None, in2=None, w2=None):
+        taps, cin, cout = layer.w.shape
+        use_tc = self.conv_impl == "tc" and taps > 1 and ops.conv_tc_supported(taps, cin, cout)
         return ops.conv_gather(x, nbr, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2,
-                               out=out, relu=relu, impl=self.conv_impl if layer.w.shape[0] > 1 else "fma")
+                               out=out, relu=relu, impl="tc" if use_tc else "fma", weight_tc=layer.tc_weights() if use_tc else None)
 
     def _resblock_run(self, x, rb: ResBlockPlan, nbr, out):
         n = x.shape[0]

@@ -176,8 +176,25 @@ def _req_rows(t, name):
     return t
 
 
+def conv_tc_supported(ntaps, cin, cout):
+    return _lib.load().st_conv_tc_weight_floats(ntaps, cin, cout) > 0
+
+
+def conv_tc_prepare(weight):
+    """weight [ntaps, cin, cout] -> the tensor-core path's pre-arranged (hi, lo) core-matrix tiles."""
+    lib = _lib.load()
+    _req(weight, F32, "weight")
+    ntaps, cin, cout = weight.shape
+    nfl = lib.st_conv_tc_weight_floats(ntaps, cin, cout)
+    if nfl < 0:
+        raise _lib.StB200Error(f"tensor-core conv does not support cin={cin}, cout={cout}")
+    wprep = torch.empty(nfl, dtype=F32, device=weight.device)
+    _lib.check(lib.st_conv_tc_prepare(_ptr(weight), ntaps, cin, cout, _ptr(wprep), _stream()), "st_conv_tc_prepare")
+    return wprep
+
+
 def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=None, in2=None, w2=None,
-                out=None, relu=False, impl="fma"):
+                out=None, relu=False, impl="fma", weight_tc=None):
     """out[i] = act(scale * sum_k W[k] . in[map[k,i]] + shift + residual[i] + w2 . in2[i]).
     weight [ntaps, cin, cout]; nbr_map [ntaps, n_out] i32 or None (identity, ntaps == 1)."""
     lib = _lib.load()
@@ -194,13 +211,17 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
         _req_rows(residual, "residual")
     if in2 is not None:
         _req_rows(in2, "in2"); _req(w2, F32, "w2")
-    fn = lib.st_conv_gather_tc if impl == "tc" else lib.st_conv_gather
+    fn, wptr = lib.st_conv_gather, weight
+    if impl == "tc":
+        if weight_tc is None:
+            weight_tc = conv_tc_prepare(weight)
+        fn, wptr = lib.st_conv_gather_tc, weight_tc
     _count("conv")
     prof = _conv_profile
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.check(fn(_ptr(inp), _ld(inp), _ptr(nbr_map), n_out, ntaps, _ptr(weight), cin, cout, _ptr(scale), _ptr(shift),
+    _lib.check(fn(_ptr(inp), _ld(inp), _ptr(nbr_map), n_out, ntaps, _ptr(wptr), cin, cout, _ptr(scale), _ptr(shift),
                   _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (w2.shape[0] if w2 is not None else 0),
                   _ptr(out), _ld(out), 1 if relu else 0, _stream()), "st_conv_gather")
     if prof is not None:

@@ -126,8 +126,8 @@ CONV_CASES = [(8, 8), (8, 16), (16, 8), (16, 16), (16, 32), (32, 16), (32, 32), 
 @pytest.mark.parametrize("impl", ["fma", "tc"])
 def test_conv_gather_matches_oracle(cin, cout, impl):
     ops = _ops()
-    if impl == "tc" and not hasattr(__import__("smart_tree_b200._lib", fromlist=["x"]).load(), "st_conv_gather_tc"):
-        pytest.skip("tensor-core path not built")
+    if impl == "tc" and not ops.conv_tc_supported(27, cin, cout):
+        pytest.skip("channel counts outside the tensor-core path")
     rng = np.random.default_rng(cin * 100 + cout)
     c = _random_coords(rng, 3000, 14)
     n = len(c)
@@ -201,8 +201,9 @@ def _rel_close(got, ref, tol=1e-3):
     return err
 
 
+@pytest.mark.parametrize("impl", ["fma", "tc"])
 @pytest.mark.parametrize("weights", ["noble-elevator-58", "peach-forest-65", "random"])
-def test_unet_forward_matches_oracle(weights):
+def test_unet_forward_matches_oracle(weights, impl):
     from smart_tree_b200.engine import SmartTreeEngine
     sd = _load("noble-elevator-58") if weights == "random" else _load(weights)
     if weights == "random":
@@ -210,7 +211,7 @@ def test_unet_forward_matches_oracle(weights):
     feats, coords = _cloud_inputs(0, 50000, 0.02)                        # BASELINE config C1
     if weights == "random":
         feats = np.random.default_rng(0).standard_normal(feats.shape).astype(np.float32)
-    eng = SmartTreeEngine(sd, device=DEV)
+    eng = SmartTreeEngine(sd, device=DEV, conv_impl=impl)
     tr_g = {}
     out = eng.forward(_t(feats), _t(coords), trace=tr_g)
     p = U.to_numpy_params(sd)
