@@ -8,12 +8,14 @@ import torch
 
 ENABLED = bool(int(os.environ.get("ST_TIMING", "0")))
 RECORDS = {}
+SAMPLES = {}
 
 
 def enable(on=True):
     global ENABLED
     ENABLED = on
     RECORDS.clear()
+    SAMPLES.clear()
 
 
 @contextmanager
@@ -25,4 +27,6 @@ def section(name):
     t0 = time.perf_counter()
     yield
     torch.cuda.synchronize()
-    RECORDS[name] = RECORDS.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+    dt = (time.perf_counter() - t0) * 1e3
+    RECORDS[name] = RECORDS.get(name, 0.0) + dt
+    SAMPLES.setdefault(name, []).append(dt)

@@ -23,6 +23,7 @@ namespace {
 constexpr int TC_M = 128;          // rows per CTA
 constexpr int TC_KS = 32;          // K elements per stage
 constexpr int TC_STAGES = 2;
+constexpr int TC_MAXTAPS = 28;        // gather-map entries of a row cached in shared memory
 constexpr int TC_PRODUCERS = 256;  // 8 warps: 2 threads per row
 constexpr int TC_THREADS = TC_PRODUCERS + 32;
 constexpr int A_TILE_FLOATS = TC_M * TC_KS;            // 4096 floats = 16 KB (one of hi / lo)
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     const int stage_bytes = 2 * A_TILE_FLOATS * 4 + 2 * b_tile_bytes;
     __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ int smap[TC_MAXTAPS * TC_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
@@ -132,33 +134,37 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
         const int row = blockIdx.x * TC_M + rloc;
         const bool row_ok = row < a.n_out;
         const uint32_t row_off = (uint32_t)((rloc >> 3) * 1024 + (rloc & 7) * 16);   // bytes inside a tile
-        int cached_tap = -1, cached_j = -1;
+        // this row's gather-map entries (one per tap), read once: removes a dependent L2 round trip per stage
+        for (int t = half; t < TC_MAXTAPS; t += 2)
+            smap[t * TC_M + rloc] = (row_ok && t < a.ntaps) ? __ldg(a.map + (size_t)t * a.n_out + row) : -1;
+        asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");      // producers only
+        auto load_stage = [&](int s, float4 (&x)[4]) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int kk = s * TC_KS + (half * 4 + q) * 4;          // first K index of this chunk
+                const int tap = kk / a.cin, c0 = kk - tap * a.cin;
+                const int j = tap < TC_MAXTAPS ? smap[tap * TC_M + rloc] : -1;
+                x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        float4 xc[4], xn[4];
+        load_stage(0, xc);
         for (int s = 0; s < a.nstages; ++s) {
             const int st = s % TC_STAGES;
+            if (s + 1 < a.nstages) load_stage(s + 1, xn);               // next stage's rows are in flight while this one is stored
             if (s >= TC_STAGES) mbar_wait(&empty_bar[st], ((s / TC_STAGES) - 1) & 1);
             uint8_t *stage = smem_raw + (size_t)st * stage_bytes;
             if (tid == 0) {
                 // weight tile of this stage; its bytes complete on the same barrier
                 bulk_copy_g2s(stage + 2 * A_TILE_FLOATS * 4, a.wprep + (size_t)s * 2 * a.npad * TC_KS, 2 * b_tile_bytes, &full_bar[st]);
             }
-            float4 x[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int kk = s * TC_KS + (half * 4 + q) * 4;          // first K index of this chunk
-                const int tap = kk / a.cin, c0 = kk - tap * a.cin;
-                if (tap != cached_tap) {
-                    cached_tap = tap;
-                    cached_j = (row_ok && tap < a.ntaps) ? __ldg(a.map + (size_t)tap * a.n_out + row) : -1;
-                }
-                x[q] = cached_j >= 0 ? __ldg((const float4 *)(a.in + (size_t)cached_j * a.in_ld + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(x[q].x) & 0xFFFFE000u); lo.x = x[q].x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(x[q].y) & 0xFFFFE000u); lo.y = x[q].y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(x[q].z) & 0xFFFFE000u); lo.z = x[q].z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(x[q].w) & 0xFFFFE000u); lo.w = x[q].w - hi.w;
+                hi.x = __uint_as_float(__float_as_uint(xc[q].x) & 0xFFFFE000u); lo.x = xc[q].x - hi.x;
+                hi.y = __uint_as_float(__float_as_uint(xc[q].y) & 0xFFFFE000u); lo.y = xc[q].y - hi.y;
+                hi.z = __uint_as_float(__float_as_uint(xc[q].z) & 0xFFFFE000u); lo.z = xc[q].z - hi.z;
+                hi.w = __uint_as_float(__float_as_uint(xc[q].w) & 0xFFFFE000u); lo.w = xc[q].w - hi.w;
                 const uint32_t off = row_off + (uint32_t)(half * 4 + q) * 128;
                 *(float4 *)(stage + off) = hi;
                 *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
@@ -166,6 +172,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
             if (tid == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * b_tile_bytes);
             else mbar_arrive(&full_bar[st]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) xc[q] = xn[q];
         }
         // ================= epilogue =================
         mbar_wait(&accum_bar, 0);
@@ -289,6 +297,7 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     if (n_out == 0) return ST_OK;
     ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
     ST_REQUIRE(map != nullptr, "the tensor-core path needs an explicit gather map");
+    ST_REQUIRE(ntaps <= TC_MAXTAPS, "at most 28 taps");
     ST_REQUIRE(((uintptr_t)in & 15) == 0 && in_ld % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_ld % 4 == 0 && ((uintptr_t)wprep & 15) == 0,
                "16-byte aligned rows required");
     ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");

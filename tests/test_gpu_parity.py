@@ -224,9 +224,11 @@ def test_unet_forward_matches_oracle(weights, impl):
         g = out[k].cpu().numpy()
         e32 = _rel_close(g, ref32[k])
         e64 = _rel_close(g, ref64[k].astype(np.float32))
-        # our fp32 result is as close to the fp64 truth as the fp32 oracle is (within a factor)
+        # distance to the fp64 truth: the FMA path is as accurate as the fp32 oracle itself; the 3xTF32
+        # tensor-core path keeps ~21 mantissa bits per product (a few 1e-5 after ~20 layers) -- both are
+        # far inside the 1e-3 tolerance of the north star
         eo = np.abs(ref32[k] - ref64[k]).max() / (np.abs(ref64[k]).max() + 1e-30)
-        assert e64 < max(20 * eo, 1e-5), (k, e32, e64, eo)
+        assert e64 < (max(20 * eo, 1e-5) if impl == "fma" else 2e-4), (k, e32, e64, eo)
 
 
 def test_layerwise_modules_match_fused_engine():

@@ -21,7 +21,7 @@ from smart_tree_b200.skeleton.skeletonize import Skeletonizer
 ap = argparse.ArgumentParser()
 ap.add_argument("--points", type=int, default=1_000_000)
 ap.add_argument("--voxel", type=float, default=0.01)
-ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--reps", type=int, default=10)
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 W = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "smart-tree_b200", "model", "weights", "noble-elevator-58_model_weights.pt")
@@ -39,6 +39,7 @@ for _ in range(args.reps):
 torch.cuda.synchronize()
 tot = (time.perf_counter() - t0) / args.reps * 1e3
 rec = {k: v / args.reps for k, v in _timing.RECORDS.items()}
+spread = {k: [round(min(v), 2), round(sorted(v)[len(v) // 2], 2), round(max(v), 2)] for k, v in _timing.SAMPLES.items() if max(v) > 1.0}
 _timing.enable(False)
 t0 = time.perf_counter()
 for _ in range(args.reps):
@@ -52,7 +53,7 @@ lib.st_debug_sample_stats(stats)
 names = ["find", "trace", "claim", "resolve", "finish"]
 cyc = {n: stats[i] for i, n in enumerate(names)}
 last = pipe.skeletonizer.last
-print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec,
+print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec, "min_med_max_ms": spread,
                   "sample_tree_cycles": cyc, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
                   "cluster_size": stats[7], "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
                   "skeleton_vertices": int(last["order"].shape[0]), "edges": int(last["edges"].shape[0]),
