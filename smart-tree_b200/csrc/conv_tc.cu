@@ -104,6 +104,7 @@ struct TcArgs {
     int act;
 };
 
+template <int CIN>
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // stage layout: A_hi (16 KB) | A_lo (16 KB) | B_hi (npad*128 B) | B_lo (npad*128 B)
@@ -111,13 +112,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     const int stage_bytes = 2 * A_TILE_FLOATS * 4 + 2 * b_tile_bytes;
     __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
-    __shared__ int smap[TC_MAXTAPS * TC_M];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -134,25 +134,46 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
         const int row = blockIdx.x * TC_M + rloc;
         const bool row_ok = row < a.n_out;
         const uint32_t row_off = (uint32_t)((rloc >> 3) * 1024 + (rloc & 7) * 16);   // bytes inside a tile
-        // this row's gather-map entries (one per tap), read once: removes a dependent L2 round trip per stage
-        for (int t = half; t < TC_MAXTAPS; t += 2)
-            smap[t * TC_M + rloc] = (row_ok && t < a.ntaps) ? __ldg(a.map + (size_t)t * a.n_out + row) : -1;
-        asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");      // producers only
-        auto load_stage = [&](int s, float4 (&x)[4]) {
+        // Per stage this thread owns 16 consecutive K elements = 4 chunks of 16 bytes:
+        //   CIN= 8: two taps (2 chunks each)   CIN=16: one tap   CIN>=32: 16 channels of one tap
+        constexpr int TAPS_PER_THREAD = CIN == 8 ? 2 : 1;
+        auto taps_of = [&](int s, int &t0, int &c0) {
+            if (CIN == 8)       { t0 = 4 * s + 2 * half; c0 = 0; }
+            else if (CIN == 16) { t0 = 2 * s + half;     c0 = 0; }
+            else                { constexpr int SPT = CIN / TC_KS; t0 = s / SPT; c0 = (s % SPT) * TC_KS + 16 * half; }
+        };
+        auto load_map = [&](int s, int (&m)[2]) {
+            int t0, c0;
+            taps_of(s, t0, c0);
+#pragma unroll
+            for (int i = 0; i < TAPS_PER_THREAD; ++i)
+                m[i] = (row_ok && s < a.nstages && t0 + i < a.ntaps) ? __ldg(a.map + (size_t)(t0 + i) * a.n_out + row) : -1;
+        };
+        auto load_rows = [&](int s, const int (&m)[2], float4 (&x)[4]) {
+            int t0, c0;
+            taps_of(s, t0, c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int kk = s * TC_KS + (half * 4 + q) * 4;          // first K index of this chunk
-                const int tap = kk / a.cin, c0 = kk - tap * a.cin;
-                const int j = tap < TC_MAXTAPS ? smap[tap * TC_M + rloc] : -1;
-                x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int j = CIN == 8 ? m[q >> 1] : m[0];
+                const int c = CIN == 8 ? (q & 1) * 4 : c0 + q * 4;
+                x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
+        // software pipeline: gather-map entries two stages ahead, feature rows one stage ahead
+        int m1[2], m2[2];
         float4 xc[4], xn[4];
-        load_stage(0, xc);
+        load_map(0, m1);
+        load_map(1, m2);
+        load_rows(0, m1, xc);
         for (int s = 0; s < a.nstages; ++s) {
             const int st = s % TC_STAGES;
-            if (s + 1 < a.nstages) load_stage(s + 1, xn);               // next stage's rows are in flight while this one is stored
-            if (s >= TC_STAGES) mbar_wait(&empty_bar[st], ((s / TC_STAGES) - 1) & 1);
+            m1[0] = m2[0]; m1[1] = m2[1];
+            load_map(s + 2, m2);
+            if (s + 1 < a.nstages) load_rows(s + 1, m1, xn);
+            if (s >= TC_STAGES) {
+                if (lane == 0) mbar_wait(&empty_bar[st], ((s / TC_STAGES) - 1) & 1);
+                __syncwarp();
+            }
             uint8_t *stage = smem_raw + (size_t)st * stage_bytes;
             if (tid == 0) {
                 // weight tile of this stage; its bytes complete on the same barrier
@@ -170,8 +191,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
             }
             fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            if (tid == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * b_tile_bytes);
-            else mbar_arrive(&full_bar[st]);
+            __syncwarp();
+            if (lane == 0) {              // one arrival per producer warp
+                if (tid == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * b_tile_bytes);
+                else mbar_arrive(&full_bar[st]);
+            }
 #pragma unroll
             for (int q = 0; q < 4; ++q) xc[q] = xn[q];
         }
@@ -271,7 +295,7 @@ __global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, in
 
 int tc_npad(int cout) { int n = (cout + 15) / 16 * 16; return n < 16 ? 16 : n; }
 int tc_nstages(int ntaps, int cin) { return (ntaps * cin + TC_KS - 1) / TC_KS; }
-bool tc_supported(int cin, int cout) { return cin >= 4 && cin % 4 == 0 && (TC_KS % cin == 0 || cin % TC_KS == 0) && cout % 8 == 0 && cout <= 256; }
+bool tc_supported(int cin, int cout) { return (cin == 8 || cin == 16 || cin == 32 || cin == 64 || cin == 128) && cout % 8 == 0 && cout <= 256; }
 
 }  // namespace
 
@@ -297,7 +321,6 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     if (n_out == 0) return ST_OK;
     ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
     ST_REQUIRE(map != nullptr, "the tensor-core path needs an explicit gather map");
-    ST_REQUIRE(ntaps <= TC_MAXTAPS, "at most 28 taps");
     ST_REQUIRE(((uintptr_t)in & 15) == 0 && in_ld % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_ld % 4 == 0 && ((uintptr_t)wprep & 15) == 0,
                "16-byte aligned rows required");
     ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");
@@ -305,12 +328,20 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     const int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
     TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
     const int smem = TC_STAGES * (2 * A_TILE_FLOATS * 4 + 2 * npad * TC_KS * 4) + 1024;
-    static int smem_set = 0;
-    if (smem > smem_set) {
-        ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        smem_set = smem;
+    const unsigned grid = (unsigned)cdiv(n_out, TC_M);
+#define ST_TC_CASE(CI)                                                                                              \
+    if (cin == CI) {                                                                                                \
+        static int smem_set = 0;                                                                                    \
+        if (smem > smem_set) {                                                                                      \
+            ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            smem_set = smem;                                                                                        \
+        }                                                                                                           \
+        k_conv_tc<CI><<<grid, TC_THREADS, smem, s>>>(a);                                                            \
+        ST_CHECK_LAUNCH();                                                                                          \
+        return ST_OK;                                                                                               \
     }
-    k_conv_tc<<<(unsigned)cdiv(n_out, TC_M), TC_THREADS, smem, s>>>(a);
-    ST_CHECK_LAUNCH();
-    return ST_OK;
+    ST_TC_CASE(8) ST_TC_CASE(16) ST_TC_CASE(32) ST_TC_CASE(64) ST_TC_CASE(128)
+#undef ST_TC_CASE
+    set_error("st_conv_gather_tc: cin=%d not instantiated", cin);
+    return ST_ERR_UNSUPPORTED;
 }
