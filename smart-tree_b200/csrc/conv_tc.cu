@@ -8,10 +8,13 @@
 //     the network is L2 resident), split each fp32 value into a TF32 head and an fp32 tail, and
 //     store both as K-major core-matrix tiles in shared memory (conflict-free 128-bit stores);
 //   * the weight tile (head + tail, pre-arranged by st_conv_tc_prepare) arrives by one 1-D bulk
-//     async copy (cp.async.bulk -> UBLKCP) that completes on the stage's mbarrier;
+//     async copy (cp.async.bulk -> UBLKCP) into its own deeper ring, issued several stages ahead by a
+//     dedicated loader lane so that its L2 latency never sits on the MMA critical path;
 //   * one elected thread issues 12 tcgen05.mma.kind::tf32 (4 k-steps x {hi*hi, lo*hi, hi*lo}: the
 //     3xTF32 split keeps ~21 mantissa bits, needed for the 1e-3 end-to-end tolerance) that
 //     accumulate in TMEM; tcgen05.commit releases the stage back to the producers.
+// CTAs are persistent (one or two per SM) and walk over 128-row tiles, so TMEM allocation, barrier
+// initialisation and pipeline fill are paid once.
 // Epilogue: the producer warps read their accumulator lanes with tcgen05.ld and apply the fused
 // BN affine / residual / identity 1x1 conv / ReLU, writing straight into the (possibly sliced) output.
 #include "common.cuh"
@@ -25,7 +28,8 @@ constexpr int TC_KS = 32;          // K elements per stage
 constexpr int TC_STAGES = 2;
 constexpr int TC_MAXTAPS = 28;        // gather-map entries of a row cached in shared memory
 constexpr int TC_PRODUCERS = 256;  // 8 warps: 2 threads per row
-constexpr int TC_THREADS = TC_PRODUCERS + 32;
+constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA issuer warp + weight-loader warp
+constexpr int TC_MAX_BSTAGES = 8;
 constexpr int A_TILE_FLOATS = TC_M * TC_KS;            // 4096 floats = 16 KB (one of hi / lo)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -91,7 +95,7 @@ struct TcArgs {
     int n_out;
     int ntaps;
     const float *wprep;   // [nstages][2][npad*32] core-matrix tiles (hi, lo)
-    int cin, cout, npad, nstages;
+    int cin, cout, npad, nstages, b_stages;
     const float *scale, *shift;
     const float *res;
     int res_ld;
@@ -107,17 +111,22 @@ struct TcArgs {
 template <int CIN>
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // stage layout: A_hi (16 KB) | A_lo (16 KB) | B_hi (npad*128 B) | B_lo (npad*128 B)
+    // smem: TC_STAGES x { A_hi (16 KB) | A_lo (16 KB) }  then  sb x { B_hi | B_lo } (npad*128 B each)
     const int b_tile_bytes = a.npad * TC_KS * 4;
-    const int stage_bytes = 2 * A_TILE_FLOATS * 4 + 2 * b_tile_bytes;
-    __shared__ uint64_t full_bar[TC_STAGES], empty_bar[TC_STAGES], accum_bar;
+    const int b_stage_bytes = 2 * b_tile_bytes;
+    constexpr int A_STAGE_BYTES = 2 * A_TILE_FLOATS * 4;
+    uint8_t *const b_ring = smem_raw + TC_STAGES * A_STAGE_BYTES;
+    const int SB = a.b_stages;
+    __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
+    const int ntiles = (a.n_out + TC_M - 1) / TC_M;
 
     if (tid == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full_bar[s], TC_PRODUCERS / 32); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&a_full[s], TC_PRODUCERS / 32); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < TC_MAX_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         mbar_init(&accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -128,11 +137,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     const uint32_t tmem_base = tmem_base_sh;
 
     if (warp < 8) {
-        // ================= producers (then epilogue) =================
+        // ================= producers (then epilogue), persistent over tiles =================
         const int rloc = 32 * (warp & 3) + lane;      // row within the tile == TMEM lane
         const int half = warp >> 2;                   // which 4 of the 8 16-byte chunks of a stage row
-        const int row = blockIdx.x * TC_M + rloc;
-        const bool row_ok = row < a.n_out;
         const uint32_t row_off = (uint32_t)((rloc >> 3) * 1024 + (rloc & 7) * 16);   // bytes inside a tile
         // Per stage this thread owns 16 consecutive K elements = 4 chunks of 16 bytes:
         //   CIN= 8: two taps (2 chunks each)   CIN=16: one tap   CIN>=32: 16 channels of one tap
@@ -142,12 +149,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             else if (CIN == 16) { t0 = 2 * s + half;     c0 = 0; }
             else                { constexpr int SPT = CIN / TC_KS; t0 = s / SPT; c0 = (s % SPT) * TC_KS + 16 * half; }
         };
-        auto load_map = [&](int s, int (&m)[2]) {
+        auto load_map = [&](int row, int s, int (&m)[2]) {
             int t0, c0;
             taps_of(s, t0, c0);
 #pragma unroll
             for (int i = 0; i < TAPS_PER_THREAD; ++i)
-                m[i] = (row_ok && s < a.nstages && t0 + i < a.ntaps) ? __ldg(a.map + (size_t)(t0 + i) * a.n_out + row) : -1;
+                m[i] = (row < a.n_out && s < a.nstages && t0 + i < a.ntaps) ? __ldg(a.map + (size_t)(t0 + i) * a.n_out + row) : -1;
         };
         auto load_rows = [&](int s, const int (&m)[2], float4 (&x)[4]) {
             int t0, c0;
@@ -159,110 +166,129 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        // software pipeline: gather-map entries two stages ahead, feature rows one stage ahead
-        int m1[2], m2[2];
-        float4 xc[4], xn[4];
-        load_map(0, m1);
-        load_map(1, m2);
-        load_rows(0, m1, xc);
-        for (int s = 0; s < a.nstages; ++s) {
-            const int st = s % TC_STAGES;
-            m1[0] = m2[0]; m1[1] = m2[1];
-            load_map(s + 2, m2);
-            if (s + 1 < a.nstages) load_rows(s + 1, m1, xn);
-            if (s >= TC_STAGES) {
-                if (lane == 0) mbar_wait(&empty_bar[st], ((s / TC_STAGES) - 1) & 1);
-                __syncwarp();
-            }
-            uint8_t *stage = smem_raw + (size_t)st * stage_bytes;
-            if (tid == 0) {
-                // weight tile of this stage; its bytes complete on the same barrier
-                bulk_copy_g2s(stage + 2 * A_TILE_FLOATS * 4, a.wprep + (size_t)s * 2 * a.npad * TC_KS, 2 * b_tile_bytes, &full_bar[st]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                float4 hi, lo;
-                hi.x = __uint_as_float(__float_as_uint(xc[q].x) & 0xFFFFE000u); lo.x = xc[q].x - hi.x;
-                hi.y = __uint_as_float(__float_as_uint(xc[q].y) & 0xFFFFE000u); lo.y = xc[q].y - hi.y;
-                hi.z = __uint_as_float(__float_as_uint(xc[q].z) & 0xFFFFE000u); lo.z = xc[q].z - hi.z;
-                hi.w = __uint_as_float(__float_as_uint(xc[q].w) & 0xFFFFE000u); lo.w = xc[q].w - hi.w;
-                const uint32_t off = row_off + (uint32_t)(half * 4 + q) * 128;
-                *(float4 *)(stage + off) = hi;
-                *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
-            }
-            fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-            __syncwarp();
-            if (lane == 0) {              // one arrival per producer warp
-                if (tid == 0) mbar_arrive_expect_tx(&full_bar[st], 2 * b_tile_bytes);
-                else mbar_arrive(&full_bar[st]);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) xc[q] = xn[q];
-        }
-        // ================= epilogue =================
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
-        const int ncols_half = a.npad / 2;                 // columns owned by this warp group
-        const int col0 = half * ncols_half;
-        for (int cb = 0; cb < ncols_half; cb += 8) {
-            const int c = col0 + cb;
-            float v[8];
-            tmem_ld8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c, v);
-            if (!row_ok || c >= a.cout) continue;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                float sc = a.scale ? __ldg(a.scale + c + i) : 1.f;
-                float sh = a.shift ? __ldg(a.shift + c + i) : 0.f;
-                v[i] = fmaf(v[i], sc, sh);
-            }
-            if (a.res) {
-                const float4 *rp = (const float4 *)(a.res + (size_t)row * a.res_ld + c);
-                float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-            }
-            if (a.in2) {
-                float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                const float *xr = a.in2 + (size_t)row * a.in2_ld;
-                for (int ci = 0; ci < a.cin2; ++ci) {
-                    const float xv = __ldg(xr + ci);
-                    const float4 *wp = (const float4 *)(a.w2 + (size_t)ci * a.cout + c);
-                    float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-                    e[0] = fmaf(xv, w0.x, e[0]); e[1] = fmaf(xv, w0.y, e[1]); e[2] = fmaf(xv, w0.z, e[2]); e[3] = fmaf(xv, w0.w, e[3]);
-                    e[4] = fmaf(xv, w1.x, e[4]); e[5] = fmaf(xv, w1.y, e[5]); e[6] = fmaf(xv, w1.z, e[6]); e[7] = fmaf(xv, w1.w, e[7]);
+        int g = 0;                                    // global stage counter (ring position / phase)
+        int tile_iter = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+            const int row = tile * TC_M + rloc;
+            const bool row_ok = row < a.n_out;
+            // software pipeline: gather-map entries two stages ahead, feature rows one stage ahead
+            int m1[2], m2[2];
+            float4 xc[4], xn[4];
+            load_map(row, 0, m1);
+            load_map(row, 1, m2);
+            load_rows(0, m1, xc);
+            for (int s = 0; s < a.nstages; ++s, ++g) {
+                const int st = g % TC_STAGES;
+                m1[0] = m2[0]; m1[1] = m2[1];
+                load_map(row, s + 2, m2);
+                if (s + 1 < a.nstages) load_rows(s + 1, m1, xn);
+                if (g >= TC_STAGES) {
+                    if (lane == 0) mbar_wait(&a_empty[st], ((g / TC_STAGES) - 1) & 1);
+                    __syncwarp();
                 }
+                uint8_t *stage = smem_raw + (size_t)st * A_STAGE_BYTES;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] += e[i];
-            }
-            if (a.act & ST_ACT_RELU) {
+                for (int q = 0; q < 4; ++q) {
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(xc[q].x) & 0xFFFFE000u); lo.x = xc[q].x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(xc[q].y) & 0xFFFFE000u); lo.y = xc[q].y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(xc[q].z) & 0xFFFFE000u); lo.z = xc[q].z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(xc[q].w) & 0xFFFFE000u); lo.w = xc[q].w - hi.w;
+                    const uint32_t off = row_off + (uint32_t)(half * 4 + q) * 128;
+                    *(float4 *)(stage + off) = hi;
+                    *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
+                }
+                fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                for (int q = 0; q < 4; ++q) xc[q] = xn[q];
             }
-            float4 *op = (float4 *)(a.out + (size_t)row * a.out_ld + c);
-            op[0] = make_float4(v[0], v[1], v[2], v[3]);
-            op[1] = make_float4(v[4], v[5], v[6], v[7]);
+            // ---------------- epilogue of this tile ----------------
+            mbar_wait(&accum_bar, tile_iter & 1);
+            tc_fence_after();
+            const int ncols_half = a.npad / 2;             // columns owned by this warp group
+            const int col0 = half * ncols_half;
+            for (int cb = 0; cb < ncols_half; cb += 8) {
+                const int c = col0 + cb;
+                float v[8];
+                tmem_ld8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c, v);
+                if (!row_ok || c >= a.cout) continue;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float sc = a.scale ? __ldg(a.scale + c + i) : 1.f;
+                    float sh = a.shift ? __ldg(a.shift + c + i) : 0.f;
+                    v[i] = fmaf(v[i], sc, sh);
+                }
+                if (a.res) {
+                    const float4 *rp = (const float4 *)(a.res + (size_t)row * a.res_ld + c);
+                    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                }
+                if (a.in2) {
+                    float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const float *xr = a.in2 + (size_t)row * a.in2_ld;
+                    for (int ci = 0; ci < a.cin2; ++ci) {
+                        const float xv = __ldg(xr + ci);
+                        const float4 *wp = (const float4 *)(a.w2 + (size_t)ci * a.cout + c);
+                        float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                        e[0] = fmaf(xv, w0.x, e[0]); e[1] = fmaf(xv, w0.y, e[1]); e[2] = fmaf(xv, w0.z, e[2]); e[3] = fmaf(xv, w0.w, e[3]);
+                        e[4] = fmaf(xv, w1.x, e[4]); e[5] = fmaf(xv, w1.y, e[5]); e[6] = fmaf(xv, w1.z, e[6]); e[7] = fmaf(xv, w1.w, e[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += e[i];
+                }
+                if (a.act & ST_ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                float4 *op = (float4 *)(a.out + (size_t)row * a.out_ld + c);
+                op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                op[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            // the accumulator has been read: order those TMEM loads before this thread's next arrivals,
+            // which in turn gate the next tile's first (overwriting) MMA
+            tc_fence_before();
         }
-        tc_fence_before();
-    } else {
-        // ================= MMA issuer (one elected lane of warp 8) =================
+    } else if (warp == 8) {
+        // ================= MMA issuer (one elected lane) =================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         if (lane == 0) {
-            for (int s = 0; s < a.nstages; ++s) {
-                const int st = s % TC_STAGES;
-                mbar_wait(&full_bar[st], (s / TC_STAGES) & 1);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem_raw + (size_t)st * stage_bytes);
-                const uint32_t a_hi = sa, a_lo = sa + A_TILE_FLOATS * 4;
-                const uint32_t b_hi = sa + 2 * A_TILE_FLOATS * 4, b_lo = b_hi + b_tile_bytes;
+            int g = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int s = 0; s < a.nstages; ++s, ++g) {
+                    const int st = g % TC_STAGES, sb = g % SB;
+                    mbar_wait(&b_full[sb], (g / SB) & 1);
+                    mbar_wait(&a_full[st], (g / TC_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem_raw + (size_t)st * A_STAGE_BYTES), a_lo = a_hi + A_TILE_FLOATS * 4;
+                    const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * b_stage_bytes), b_lo = b_hi + b_tile_bytes;
 #pragma unroll
-                for (int j = 0; j < TC_KS / 8; ++j) {
-                    const uint32_t ko = (uint32_t)j * 256;       // two 128-byte K chunks per k-step
-                    umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_hi + ko), idesc, (s | j) ? 1u : 0u);
-                    umma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(b_hi + ko), idesc, 1u);
-                    umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_lo + ko), idesc, 1u);
+                    for (int j = 0; j < TC_KS / 8; ++j) {
+                        const uint32_t ko = (uint32_t)j * 256;       // two 128-byte K chunks per k-step
+                        umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_hi + ko), idesc, (s | j) ? 1u : 0u);
+                        umma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(b_hi + ko), idesc, 1u);
+                        umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_lo + ko), idesc, 1u);
+                    }
+                    umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
+                    umma_commit(&b_empty[sb]);
                 }
-                umma_commit(&empty_bar[st]);      // stage reusable once these MMAs have read it
+                umma_commit(&accum_bar);          // this tile's accumulator is complete
             }
-            umma_commit(&accum_bar);              // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ================= weight loader (one elected lane): SB stages ahead of the MMAs =================
+        if (lane == 0) {
+            int g = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int s = 0; s < a.nstages; ++s, ++g) {
+                    const int sb = g % SB;
+                    if (g >= SB) mbar_wait(&b_empty[sb], ((g / SB) - 1) & 1);
+                    mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
+                    bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, a.wprep + (size_t)s * 2 * a.npad * TC_KS, (uint32_t)b_stage_bytes, &b_full[sb]);
+                }
+            }
         }
         __syncwarp();
     }
@@ -326,9 +352,19 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");
     ST_REQUIRE(!in2 || (w2 && ((uintptr_t)w2 & 15) == 0), "in2 needs a 16-byte aligned w2");
     const int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
-    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
-    const int smem = TC_STAGES * (2 * A_TILE_FLOATS * 4 + 2 * npad * TC_KS * 4) + 1024;
-    const unsigned grid = (unsigned)cdiv(n_out, TC_M);
+    // weight ring depth: as deep as fits next to the two A stages while keeping two CTAs per SM when the
+    // weight tile is small (the bulk copies must be issued ~2000 cycles ahead of their MMAs)
+    const int a_bytes = TC_STAGES * 2 * A_TILE_FLOATS * 4, b_stage = 2 * npad * TC_KS * 4;
+    int sb = (npad <= 32 ? (108 * 1024 - a_bytes) : (200 * 1024 - a_bytes)) / b_stage;
+    sb = sb > TC_MAX_BSTAGES ? TC_MAX_BSTAGES : (sb < 2 ? 2 : sb);
+    if (sb > nst) sb = nst;
+    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
+    const int smem = a_bytes + sb * b_stage + 1024;
+    static int n_sms = 0;
+    if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int64_t ntiles = cdiv(n_out, TC_M);
+    const int ctas_per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const unsigned grid = (unsigned)(ntiles < (int64_t)n_sms * ctas_per_sm ? ntiles : (int64_t)n_sms * ctas_per_sm);   // persistent CTAs
 #define ST_TC_CASE(CI)                                                                                              \
     if (cin == CI) {                                                                                                \
         static int smem_set = 0;                                                                                    \
