@@ -100,8 +100,16 @@ int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *keys, const in
  *         out_coords): down[27,M] = input row feeding output o through tap k (p = 2o-1+k),
  *         up[27,n] = output row fed by input p through tap k; -1 where absent.           */
 size_t st_strided_coords_workspace_bytes(int64_t n);
-int st_strided_coords(const int32_t *coords, int64_t n, int32_t *out_coords,
+int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, int32_t *out_coords,
                       int64_t *n_out_host, void *workspace, size_t workspace_bytes, void *stream);
+/* Row order is free inside the network (every encoder is undone by its inverse conv), so the engine
+ * keeps each level in (batch, Z-order): morton_order=1 above sorts the new level that way, and
+ * st_morton_perm gives the permutation that does the same for the caller's level-0 rows
+ * (perm[k] = caller row of the k-th voxel).  Gathers of spatial neighbours then hit L1/L2 lines that
+ * a CTA has just touched instead of random rows.                                              */
+size_t st_morton_workspace_bytes(int64_t n);
+int st_morton_perm(const int32_t *coords, int64_t n, int32_t *perm, void *workspace,
+                   size_t workspace_bytes, void *stream);
 int st_strided_maps(const int32_t *coords, int64_t n, int64_t n_out, const uint64_t *out_keys,
                     const int32_t *out_vals, int64_t out_capacity, int32_t *down, int32_t *up,
                     void *stream);
@@ -139,8 +147,9 @@ int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_
  * params: packed fp32 block described in smart-tree_b200/engine.py (pack_heads).
  * Outputs (any may be NULL): radius[n] (log radius), direction[n,3] (unit), class_logits[n,2],
  * medial_vector[n,3], class_l[n] (int32 argmax, first maximum).                         */
-int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params, float *radius,
-                   float *direction, float *class_logits, float *medial_vector,
+int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params,
+                   const int32_t *out_index /* optional: result of row i is written to row out_index[i] */,
+                   float *radius, float *direction, float *class_logits, float *medial_vector,
                    int32_t *class_l, void *stream);
 
 /* ------------------------------------------------------------------ K7 fixed-radius kNN

@@ -36,7 +36,9 @@ SIGNATURES = {
     "st_hash_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
     "st_subm_map": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
     "st_strided_coords_workspace_bytes": (_sz, [_i64]),
-    "st_strided_coords": (C.c_int, [_p, _i64, _p, _pi64, _p, _sz, _p]),
+    "st_strided_coords": (C.c_int, [_p, _i64, C.c_int, _p, _pi64, _p, _sz, _p]),
+    "st_morton_workspace_bytes": (_sz, [_i64]),
+    "st_morton_perm": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "st_strided_maps": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _p]),
     "st_conv_gather": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                  _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
@@ -44,7 +46,7 @@ SIGNATURES = {
     "st_conv_tc_prepare": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "st_conv_gather_tc": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                     _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
-    "st_heads_fused": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p, _p, _p, _p, _p]),
+    "st_heads_fused": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "st_knn_workspace_bytes": (_sz, [_i64]),
     "st_knn": (C.c_int, [_p, _i64, _p, _i64, C.c_int, _f, _p, _p, _p, _p, _sz, _p]),
     "st_outlier_mask": (C.c_int, [_p, _i64, _p, _f, C.c_int, _p, _p, _sz, _p]),

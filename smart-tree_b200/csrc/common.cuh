@@ -66,6 +66,33 @@ __host__ __device__ __forceinline__ void unpack_key(uint64_t k, int &b, int &z, 
     y = (int)((k >> 16) & 0xFFFF) - 1;
     x = (int)(k & 0xFFFF) - 1;
 }
+// Morton (Z-order) variant of the key: batch in the top 16 bits, then the bits of (z+1, y+1, x+1)
+// interleaved.  Sorting by it keeps spatial neighbours close in memory (gather locality in L1/L2).
+__host__ __device__ __forceinline__ uint64_t spread3(uint64_t v) {   // 16 bits -> every third bit
+    v &= 0xFFFFull;
+    v = (v | (v << 16)) & 0x0000FF0000FFull;
+    v = (v | (v << 8)) & 0x00F00F00F00Full;
+    v = (v | (v << 4)) & 0x0C30C30C30C3ull;
+    v = (v | (v << 2)) & 0x249249249249ull;
+    return v;
+}
+__host__ __device__ __forceinline__ uint64_t compact3(uint64_t v) {
+    v &= 0x249249249249ull;
+    v = (v | (v >> 2)) & 0x0C30C30C30C3ull;
+    v = (v | (v >> 4)) & 0x00F00F00F00Full;
+    v = (v | (v >> 8)) & 0x0000FF0000FFull;
+    v = (v | (v >> 16)) & 0xFFFFull;
+    return v;
+}
+__host__ __device__ __forceinline__ uint64_t morton_key(int b, int z, int y, int x) {
+    return ((uint64_t)(uint32_t)b << 48) | (spread3((uint32_t)(z + 1)) << 2) | (spread3((uint32_t)(y + 1)) << 1) | spread3((uint32_t)(x + 1));
+}
+__host__ __device__ __forceinline__ void unpack_morton(uint64_t k, int &b, int &z, int &y, int &x) {
+    b = (int)(k >> 48);
+    z = (int)compact3(k >> 2) - 1;
+    y = (int)compact3(k >> 1) - 1;
+    x = (int)compact3(k) - 1;
+}
 __device__ __forceinline__ uint32_t hash_key(uint64_t k) {
     k ^= k >> 33;
     k *= 0xff51afd7ed558ccdull;

@@ -278,7 +278,8 @@ __device__ __forceinline__ void run_head(const float *__restrict__ p, const floa
 
 __global__ void __launch_bounds__(256) k_heads(const float *__restrict__ in, int in_ld, int n, const float *__restrict__ params,
                                                float *__restrict__ radius, float *__restrict__ direction,
-                                               float *__restrict__ logits, float *__restrict__ medial, int32_t *__restrict__ cls) {
+                                               float *__restrict__ logits, float *__restrict__ medial, int32_t *__restrict__ cls,
+                                               const int32_t *__restrict__ out_index) {
     __shared__ float sp[HEADS_TOTAL];
     for (int i = threadIdx.x; i < HEADS_TOTAL; i += blockDim.x) sp[i] = params[i];
     __syncthreads();
@@ -292,6 +293,7 @@ __global__ void __launch_bounds__(256) k_heads(const float *__restrict__ in, int
     run_head<1>(sp, x, r);
     run_head<3>(sp + head_size(1), x, d);
     run_head<2>(sp + head_size(1) + head_size(3), x, c);
+    if (out_index) i = __ldg(out_index + i);      // un-permute: internal (Z-order) row -> caller's row
     // F.normalize(p=2, dim=1, eps=1e-12)
     float nrm = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2])));
     float den = fmaxf(nrm, 1e-12f);
@@ -306,12 +308,12 @@ __global__ void __launch_bounds__(256) k_heads(const float *__restrict__ in, int
     if (cls) cls[i] = c[1] > c[0] ? 1 : 0;
 }
 
-extern "C" int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params, float *radius, float *direction,
-                              float *class_logits, float *medial_vector, int32_t *class_l, void *stream) {
+extern "C" int st_heads_fused(const float *in, int in_ld, int64_t n, const float *params, const int32_t *out_index, float *radius,
+                              float *direction, float *class_logits, float *medial_vector, int32_t *class_l, void *stream) {
     if (n == 0) return ST_OK;
     ST_REQUIRE(aligned16(in) && in_ld % 4 == 0, "heads input must be 16-byte aligned rows");
     k_heads<<<(unsigned)cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, (int)n, params, radius, direction,
-                                                                        class_logits, medial_vector, class_l);
+                                                                        class_logits, medial_vector, class_l, out_index);
     ST_CHECK_LAUNCH();
     return ST_OK;
 }

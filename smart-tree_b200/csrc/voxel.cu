@@ -95,7 +95,7 @@ extern "C" int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *key
 // ------------------------------------------------------------------------------------ strided coords
 // Each input voxel p feeds outputs o = (p+1-k)/2 for taps k with p+1-k even: per axis one
 // candidate for even p (k=1), two for odd p (k=0,2) -> at most 8 candidates per voxel.
-__global__ void k_strided_candidates(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ cand) {
+__global__ void k_strided_candidates(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ cand, int morton) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int4 c = __ldg(coords + i);
@@ -110,20 +110,21 @@ __global__ void k_strided_candidates(const int4 *__restrict__ coords, int n, uin
     for (int j = 0; j < 8; ++j) {
         int jz = j >> 2, jy = (j >> 1) & 1, jx = j & 1;
         uint64_t key = KEY_EMPTY;
-        if (jz < cnt[0] && jy < cnt[1] && jx < cnt[2]) key = pack_key(c.x, lo[0] + jz, lo[1] + jy, lo[2] + jx);
+        if (jz < cnt[0] && jy < cnt[1] && jx < cnt[2])
+            key = morton ? morton_key(c.x, lo[0] + jz, lo[1] + jy, lo[2] + jx) : pack_key(c.x, lo[0] + jz, lo[1] + jy, lo[2] + jx);
         cand[(size_t)j * n + i] = key;
     }
 }
 
 __global__ void k_unpack_coords(const uint64_t *__restrict__ keys, const int *__restrict__ n_sel, int4 *__restrict__ out,
-                                int64_t *n_out) {
+                                int64_t *n_out, int morton) {
     int m = *n_sel;
     if (m > 0 && keys[m - 1] == KEY_EMPTY) --m;  // the sentinel sorts last
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *n_out = m;
     for (; i < m; i += gridDim.x * blockDim.x) {
         int b, z, y, x;
-        unpack_key(keys[i], b, z, y, x);
+        if (morton) unpack_morton(keys[i], b, z, y, x); else unpack_key(keys[i], b, z, y, x);
         out[i] = make_int4(b, z, y, x);
     }
 }
@@ -140,7 +141,7 @@ extern "C" size_t st_strided_coords_workspace_bytes(int64_t n) {
     return align_up(strided_cub_bytes(total)) + 3 * align_up(total * sizeof(uint64_t)) + 1024;
 }
 
-extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int32_t *out_coords, int64_t *n_out_host,
+extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, int32_t *out_coords, int64_t *n_out_host,
                                  void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     *n_out_host = 0;
@@ -156,11 +157,11 @@ extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int32_t *out_
     size_t cub_bytes = strided_cub_bytes(total);
     void *cub_ws = cv.take<char>(cub_bytes);
     if (!cv.ok()) { set_error("st_strided_coords: workspace too small"); return ST_ERR_WORKSPACE; }
-    k_strided_candidates<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, cand);
+    k_strided_candidates<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, cand, morton_order);
     ST_CHECK_LAUNCH();
     ST_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, cand, sorted, (int)total, 0, 64, s));
     ST_CHECK_CUDA(cub::DeviceSelect::Unique(cub_ws, cub_bytes, sorted, uniq, n_sel, (int)total, s));
-    k_unpack_coords<<<296, 256, 0, s>>>(uniq, n_sel, (int4 *)out_coords, n_out_dev);
+    k_unpack_coords<<<296, 256, 0, s>>>(uniq, n_sel, (int4 *)out_coords, n_out_dev, morton_order);
     ST_CHECK_LAUNCH();
     ST_CHECK_CUDA(cudaMemcpyAsync(n_out_host, n_out_dev, sizeof(int64_t), cudaMemcpyDeviceToHost, s));
     ST_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -192,6 +193,39 @@ extern "C" int st_strided_maps(const int32_t *coords, int64_t n, int64_t n_out, 
     k_strided_maps<<<grid, 256, 0, s>>>((const int4 *)coords, (int)n, (int)n_out, out_keys, out_vals,
                                         (uint32_t)(out_capacity - 1), down, up);
     ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// ------------------------------------------------------------------------------------ Morton permutation
+__global__ void k_morton_keys(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ keys, int32_t *__restrict__ idx) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int4 c = __ldg(coords + i);
+    keys[i] = morton_key(c.x, c.y, c.z, c.w);
+    idx[i] = i;
+}
+
+extern "C" size_t st_morton_workspace_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint64_t *)nullptr, (uint64_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)n);
+    return align_up(b) + 2 * align_up(n * 8) + align_up(n * 4) + 1024;
+}
+
+// perm[k] = row of the k-th voxel in (batch, Z-order) order; stable for duplicate coordinates.
+extern "C" int st_morton_perm(const int32_t *coords, int64_t n, int32_t *perm, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    Carver cv(workspace, workspace_bytes);
+    uint64_t *keys = cv.take<uint64_t>(n);
+    uint64_t *keys2 = cv.take<uint64_t>(n);
+    int32_t *idx = cv.take<int32_t>(n);
+    size_t cb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, cb, keys, keys2, idx, perm, (int)n);
+    void *cub_ws = cv.take<char>(cb);
+    if (!cv.ok()) { set_error("st_morton_perm: workspace too small"); return ST_ERR_WORKSPACE; }
+    k_morton_keys<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, keys, idx);
+    ST_CHECK_LAUNCH();
+    ST_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(cub_ws, cb, keys, keys2, idx, perm, (int)n, 0, 64, s));
     return ST_OK;
 }
 

@@ -80,11 +80,11 @@ class LevelIndex:
         self.up = None
 
 
-def build_levels(coords: torch.Tensor, depth: int) -> List[LevelIndex]:
+def build_levels(coords: torch.Tensor, depth: int, morton: bool = False) -> List[LevelIndex]:
     levels = [LevelIndex(coords)]
     for _ in range(depth - 1):
         cur = levels[-1]
-        oc = ops.strided_coords(cur.coords)
+        oc = ops.strided_coords(cur.coords, morton=morton)
         nxt = LevelIndex(oc)
         cur.down, cur.up = ops.strided_maps(cur.coords, oc, nxt.table)
         levels.append(nxt)
@@ -99,6 +99,7 @@ class SmartTreeEngine:
         self.device = torch.device(device)
         self.eps = eps
         self.conv_impl = conv_impl
+        self.morton = bool(int(os.environ.get("ST_MORTON", "1")))
         dev = self.device
         self.stem = ConvLayer(_conv_w(sd["input_conv.sequence.0.weight"]),
                               *_fold_bn(sd, "input_conv.sequence.1", eps)).to(dev)
@@ -196,7 +197,16 @@ class SmartTreeEngine:
         return out
 
     def build_levels(self, coords):
-        return build_levels(coords.contiguous(), self.depth)
+        """Index structures of all levels.  With `self.morton` the rows of every level are kept in
+        (batch, Z-order): level 0 through a permutation of the caller's rows (undone by the heads
+        kernel), deeper levels by construction."""
+        coords = coords.contiguous().int()
+        if not self.morton:
+            return build_levels(coords, self.depth)
+        perm = ops.morton_perm(coords)
+        levels = build_levels(coords[perm.long()].contiguous(), self.depth, morton=True)
+        levels[0].perm = perm
+        return levels
 
     @torch.no_grad()
     def forward(self, features: torch.Tensor, coords: torch.Tensor, levels=None, trace=None, fused_outputs=False):
@@ -209,13 +219,26 @@ class SmartTreeEngine:
         n = features.shape[0]
         if levels is None:
             levels = self.build_levels(coords)
+        perm = getattr(levels[0], "perm", None)
+        if perm is not None:
+            features = features[perm.long()]
         x = self._conv(features, self.stem, None, n, relu=True)
         if trace is not None:
             trace["input_conv"] = x
         x = self._ublock(x, 0, levels, trace)
+        if trace is not None and perm is not None:      # level-0 activations back in the caller's row order
+            inv = torch.empty_like(perm).long()
+            inv[perm.long()] = torch.arange(n, device=perm.device)
+            for k, v in list(trace.items()):
+                if v.shape[0] == n and k.count("U.") == 0:
+                    trace[k] = v[inv]
         if self.heads_packed is not None and x.shape[1] == 8:
-            radius, direction, logits, medial, cls = ops.heads_fused(x, self.heads_packed)
+            radius, direction, logits, medial, cls = ops.heads_fused(x, self.heads_packed, out_index=perm)
         else:
+            if perm is not None:
+                inv = torch.empty_like(perm).long()
+                inv[perm.long()] = torch.arange(n, device=perm.device)
+                x = x[inv]
             outs = {}
             for name, ls in self.head_layers.items():
                 h = x

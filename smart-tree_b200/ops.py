@@ -140,7 +140,19 @@ def subm_map(coords, table: CoordTable):
     return nbr
 
 
-def strided_coords(coords):
+def morton_perm(coords):
+    """perm[k] = row of the k-th voxel in (batch, Z-order) order."""
+    lib = _lib.load()
+    _req(coords, I32, "coords")
+    n = coords.shape[0]
+    perm = torch.empty(n, dtype=I32, device=coords.device)
+    ws = _ws(lib.st_morton_workspace_bytes(n), coords.device)
+    _count("subm_map")
+    _lib.check(lib.st_morton_perm(_ptr(coords), n, _ptr(perm), _ptr(ws), ws.numel(), _stream()), "st_morton_perm")
+    return perm
+
+
+def strided_coords(coords, morton=False):
     lib = _lib.load()
     _req(coords, I32, "coords")
     n = coords.shape[0]
@@ -148,7 +160,7 @@ def strided_coords(coords):
     ws = _ws(lib.st_strided_coords_workspace_bytes(n), coords.device)
     m = C.c_int64(0)
     _count("strided_coords")
-    _lib.check(lib.st_strided_coords(_ptr(coords), n, _ptr(out), C.byref(m), _ptr(ws), ws.numel(), _stream()),
+    _lib.check(lib.st_strided_coords(_ptr(coords), n, 1 if morton else 0, _ptr(out), C.byref(m), _ptr(ws), ws.numel(), _stream()),
                "st_strided_coords")
     return out[:m.value].clone() if m.value * 4 < out.shape[0] else out[:m.value]
 
@@ -231,7 +243,7 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
     return out
 
 
-def heads_fused(feat, params, want_logits=True):
+def heads_fused(feat, params, want_logits=True, out_index=None):
     lib = _lib.load()
     _req_rows(feat, "feat"); _req(params, F32, "params")
     n, dev = feat.shape[0], feat.device
@@ -241,7 +253,9 @@ def heads_fused(feat, params, want_logits=True):
     medial = torch.empty((n, 3), dtype=F32, device=dev)
     cls = torch.empty(n, dtype=I32, device=dev)
     _count("heads")
-    _lib.check(lib.st_heads_fused(_ptr(feat), _ld(feat), n, _ptr(params), _ptr(radius), _ptr(direction), _ptr(logits),
+    if out_index is not None:
+        _req(out_index, I32, "out_index")
+    _lib.check(lib.st_heads_fused(_ptr(feat), _ld(feat), n, _ptr(params), _ptr(out_index), _ptr(radius), _ptr(direction), _ptr(logits),
                                   _ptr(medial), _ptr(cls), _stream()), "st_heads_fused")
     return radius, direction, logits, medial, cls
 

@@ -63,6 +63,34 @@ def test_strided_maps_exact(n, extent):
     assert np.array_equal(up.cpu().numpy(), rup)
 
 
+def test_strided_maps_z_order():
+    """morton_order=1: same voxel set and the same pairs, rows of the new level in (batch, Z-order)."""
+    ops = _ops()
+    c = _random_coords(np.random.default_rng(11), 20000, 50)
+    ct = _t(c)
+    oc = ops.strided_coords(ct, morton=True)
+    down, up = ops.strided_maps(ct, oc, ops.CoordTable(oc))
+    roc, rdown, rup = U.strided_maps(c)
+    ocn = oc.cpu().numpy()
+    pos = {tuple(r): i for i, r in enumerate(roc.tolist())}
+    to_ref = np.array([pos[tuple(r)] for r in ocn.tolist()])          # our row -> oracle row
+    assert sorted(to_ref.tolist()) == list(range(len(roc)))
+    assert np.array_equal(down.cpu().numpy(), rdown[:, to_ref])
+    inv = np.empty_like(to_ref); inv[to_ref] = np.arange(len(to_ref))
+    assert np.array_equal(up.cpu().numpy(), np.where(rup >= 0, inv[np.maximum(rup, 0)], -1))
+
+    def zkey(r):
+        k = 0
+        for bit in range(16):
+            k |= (((r[1] + 1) >> bit) & 1) << (3 * bit + 2) | (((r[2] + 1) >> bit) & 1) << (3 * bit + 1) | (((r[3] + 1) >> bit) & 1) << (3 * bit)
+        return (r[0], k)
+    keys = [zkey(r) for r in ocn.tolist()]
+    assert keys == sorted(keys)
+    perm = ops.morton_perm(ct).cpu().numpy()
+    k0 = [zkey(r) for r in c[perm].tolist()]
+    assert k0 == sorted(k0) and sorted(perm.tolist()) == list(range(len(c)))
+
+
 def test_empty_inputs():
     ops = _ops()
     c = torch.zeros((0, 4), dtype=torch.int32, device=DEV)
@@ -212,8 +240,13 @@ def test_unet_forward_matches_oracle(weights, impl):
     if weights == "random":
         feats = np.random.default_rng(0).standard_normal(feats.shape).astype(np.float32)
     eng = SmartTreeEngine(sd, device=DEV, conv_impl=impl)
+    eng.morton = False                       # intermediate activations row-aligned with the oracle's levels
     tr_g = {}
     out = eng.forward(_t(feats), _t(coords), trace=tr_g)
+    eng.morton = True                        # production setting: Z-ordered rows inside, caller order outside
+    out_z = eng.forward(_t(feats), _t(coords))
+    for k in ("radius", "direction", "class_l"):
+        _rel_close(out_z[k].cpu().numpy(), out[k].cpu().numpy(), 1e-4)
     p = U.to_numpy_params(sd)
     tr_r = {}
     ref32 = U.forward(p, feats, coords, trace=tr_r)

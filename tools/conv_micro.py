@@ -19,8 +19,12 @@ dev = torch.device("cuda:0")
 tr = synth.make_tree(0, 1_000_000)
 cloud = CentreCloud()(Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev)))
 bb = SingleTreeInference(cloud, 0.01, 4, 0.4).voxelize_all()
-levels = build_levels(bb.coords.contiguous(), 4)
-print("levels", [l.n for l in levels])
+MORTON = bool(int(os.environ.get("ST_MORTON", "1")))
+coords = bb.coords.contiguous()
+if MORTON:
+    coords = coords[ops.morton_perm(coords).long()].contiguous()
+levels = build_levels(coords, 4, morton=MORTON)
+print("levels", [l.n for l in levels], "z-order" if MORTON else "input order")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 cases = [(8, 8, 0), (16, 8, 0), (16, 16, 1), (32, 16, 1), (32, 32, 2), (64, 32, 2), (64, 64, 3)]
 if only:
