@@ -198,7 +198,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     *(float4 *)(stage + off) = hi;
                     *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
                 }
-                fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+                // No proxy fence here: it would make every producer wait for its in-flight prefetch loads.
+                // The writes are released by the mbarrier arrive; the MMA thread, which has nothing in
+                // flight, issues the generic->async proxy fence after acquiring the barrier.
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
 #pragma unroll
@@ -260,6 +262,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     const int st = g % TC_STAGES, sb = g % SB;
                     mbar_wait(&b_full[sb], (g / SB) & 1);
                     mbar_wait(&a_full[st], (g / TC_STAGES) & 1);
+                    fence_proxy_async();          // producers' generic-proxy smem writes -> async (tensor core) proxy
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem_raw + (size_t)st * A_STAGE_BYTES), a_lo = a_hi + A_TILE_FLOATS * 4;
                     const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * b_stage_bytes), b_lo = b_hi + b_tile_bytes;
