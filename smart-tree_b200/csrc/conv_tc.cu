@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     const int SB = a.b_stages;
     __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
+    __shared__ int smap[2][TC_MAXTAPS][TC_M];     // gather-map entries of the current / next tile (28 KB)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
@@ -149,39 +150,52 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             else if (CIN == 16) { t0 = 2 * s + half;     c0 = 0; }
             else                { constexpr int SPT = CIN / TC_KS; t0 = s / SPT; c0 = (s % SPT) * TC_KS + 16 * half; }
         };
-        auto load_map = [&](int row, int s, int (&m)[2]) {
-            int t0, c0;
-            taps_of(s, t0, c0);
-#pragma unroll
-            for (int i = 0; i < TAPS_PER_THREAD; ++i)
-                m[i] = (row < a.n_out && s < a.nstages && t0 + i < a.ntaps) ? __ldg(a.map + (size_t)(t0 + i) * a.n_out + row) : -1;
+        // Gather-map entries are read exactly once (always cold in cache), so they are fetched one whole
+        // TILE ahead with 4-byte cp.async copies into shared memory and never touch a register scoreboard.
+        auto prefetch_map = [&](int tile, int buf) {
+            if (tile < ntiles) {
+                const int row = tile * TC_M + rloc;
+                for (int t = half; t < TC_MAXTAPS; t += 2) {
+                    if (row < a.n_out && t < a.ntaps) {
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&smap[buf][t][rloc])),
+                                     "l"(a.map + (size_t)t * a.n_out + row) : "memory");
+                    } else {
+                        smap[buf][t][rloc] = -1;
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        auto load_rows = [&](int s, const int (&m)[2], float4 (&x)[4]) {
+        auto map_ready = [&]() {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");      // producers only
+        };
+        auto load_rows = [&](int buf, int s, float4 (&x)[4]) {
             int t0, c0;
             taps_of(s, t0, c0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const int j = CIN == 8 ? m[q >> 1] : m[0];
+                const int tap = CIN == 8 ? t0 + (q >> 1) : t0;
+                const int j = tap < TC_MAXTAPS ? smap[buf][tap][rloc] : -1;
                 const int c = CIN == 8 ? (q & 1) * 4 : c0 + q * 4;
                 x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         int g = 0;                                    // global stage counter (ring position / phase)
         int tile_iter = 0;
+        prefetch_map(blockIdx.x, 0);
+        map_ready();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
+            const int buf = tile_iter & 1;
             const int row = tile * TC_M + rloc;
             const bool row_ok = row < a.n_out;
-            // software pipeline: gather-map entries two stages ahead, feature rows one stage ahead
-            int m1[2], m2[2];
+            prefetch_map(tile + gridDim.x, buf ^ 1);
+            // software pipeline: feature rows one stage ahead of the stores
             float4 xc[4], xn[4];
-            load_map(row, 0, m1);
-            load_map(row, 1, m2);
-            load_rows(0, m1, xc);
+            load_rows(buf, 0, xc);
             for (int s = 0; s < a.nstages; ++s, ++g) {
                 const int st = g % TC_STAGES;
-                m1[0] = m2[0]; m1[1] = m2[1];
-                load_map(row, s + 2, m2);
-                if (s + 1 < a.nstages) load_rows(s + 1, m1, xn);
+                if (s + 1 < a.nstages) load_rows(buf, s + 1, xn);
                 if (g >= TC_STAGES) {
                     if (lane == 0) mbar_wait(&a_empty[st], ((g / TC_STAGES) - 1) & 1);
                     __syncwarp();
@@ -251,6 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             // the accumulator has been read: order those TMEM loads before this thread's next arrivals,
             // which in turn gate the next tile's first (overwriting) MMA
             tc_fence_before();
+            map_ready();                   // next tile's gather map has landed; this tile's buffer may be refilled
         }
     } else if (warp == 8) {
         // ================= MMA issuer (one elected lane) =================
@@ -358,7 +373,7 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     // weight ring depth: as deep as fits next to the two A stages while keeping two CTAs per SM when the
     // weight tile is small (the bulk copies must be issued ~2000 cycles ahead of their MMAs)
     const int a_bytes = TC_STAGES * 2 * A_TILE_FLOATS * 4, b_stage = 2 * npad * TC_KS * 4;
-    int sb = (npad <= 32 ? (108 * 1024 - a_bytes) : (200 * 1024 - a_bytes)) / b_stage;
+    int sb = (npad <= 32 ? (80 * 1024 - a_bytes) : (180 * 1024 - a_bytes)) / b_stage;      // 28 KB of static smem for the map
     sb = sb > TC_MAX_BSTAGES ? TC_MAX_BSTAGES : (sb < 2 ? 2 : sb);
     if (sb > nst) sb = nst;
     TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
@@ -366,7 +381,7 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     static int n_sms = 0;
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int64_t ntiles = cdiv(n_out, TC_M);
-    const int ctas_per_sm = smem <= 112 * 1024 ? 2 : 1;
+    const int ctas_per_sm = smem <= 82 * 1024 ? 2 : 1;
     const unsigned grid = (unsigned)(ntiles < (int64_t)n_sms * ctas_per_sm ? ntiles : (int64_t)n_sms * ctas_per_sm);   // persistent CTAs
 #define ST_TC_CASE(CI)                                                                                              \
     if (cin == CI) {                                                                                                \
