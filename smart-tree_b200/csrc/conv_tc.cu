@@ -69,11 +69,22 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem] . B[smem]^T, tf32 inputs, fp32 accumulate.  The issuing thread is the serial
+// bottleneck of the whole CTA, so descriptors are passed as (lo, hi) words: hi is a constant and lo is
+// one integer add per MMA.
+__device__ __forceinline__ void umma_tf32_acc(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.eq.b32 p, 0, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc) : "memory");
 }
+__device__ __forceinline__ void umma_tf32_init(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc) {
+    asm volatile("{\n\t.reg .b64 da, db;\n\t.reg .pred p;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, 0, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
+                 ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc) : "memory");
+}
+// descriptor words: lo = (addr >> 4) | LBO(128 B) << 16 ; hi = SBO(1024 B) | version 1 << 14
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); }
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14);
 // K-major, no swizzle: 8-row x 16-byte core matrices; LBO = 128 B between the two K chunks of one
 // MMA, SBO = 1024 B between 8-row groups (a stage row holds 8 chunks); descriptor version 1 (sm_100)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
@@ -87,6 +98,11 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// debug timeline of CTA 0 (cycles): [0] producer warp 0 after a_empty wait, [1] after its a_full arrive,
+// [2] MMA thread after a_full wait, [3] after commit, [4] b_full wait done.  Read with st_debug_tc_trace.
+__device__ long long g_tc_trace[5][64];
+#define TC_TRACE(slot, idx) do { if (blockIdx.x == 0 && (idx) < 64) g_tc_trace[slot][idx] = clock64(); } while (0)
 
 struct TcArgs {
     const float *in;
@@ -200,6 +216,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     if (lane == 0) mbar_wait(&a_empty[st], ((g / TC_STAGES) - 1) & 1);
                     __syncwarp();
                 }
+                if (tid == 0) TC_TRACE(0, g);
                 uint8_t *stage = smem_raw + (size_t)st * A_STAGE_BYTES;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -217,6 +234,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 // flight, issues the generic->async proxy fence after acquiring the barrier.
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
+                if (tid == 0) TC_TRACE(1, g);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) xc[q] = xn[q];
             }
@@ -276,20 +294,28 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 for (int s = 0; s < a.nstages; ++s, ++g) {
                     const int st = g % TC_STAGES, sb = g % SB;
                     mbar_wait(&b_full[sb], (g / SB) & 1);
+                    TC_TRACE(4, g);
                     mbar_wait(&a_full[st], (g / TC_STAGES) & 1);
+                    TC_TRACE(2, g);
                     fence_proxy_async();          // producers' generic-proxy smem writes -> async (tensor core) proxy
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem_raw + (size_t)st * A_STAGE_BYTES), a_lo = a_hi + A_TILE_FLOATS * 4;
-                    const uint32_t b_hi = smem_u32(b_ring + (size_t)sb * b_stage_bytes), b_lo = b_hi + b_tile_bytes;
+                    // descriptor low words of the four operand tiles; a k-step advances each by 256 B = 16 units
+                    const uint32_t ah = desc_lo(smem_u32(smem_raw + (size_t)st * A_STAGE_BYTES)), al = ah + (A_TILE_FLOATS * 4 >> 4);
+                    const uint32_t bh = desc_lo(smem_u32(b_ring + (size_t)sb * b_stage_bytes)), bl = bh + (uint32_t)(b_tile_bytes >> 4);
+                    if (s == 0) umma_tf32_init(tmem_base, ah, bh, DESC_HI, idesc);
+                    else        umma_tf32_acc(tmem_base, ah, bh, DESC_HI, idesc);
+                    umma_tf32_acc(tmem_base, al, bh, DESC_HI, idesc);
+                    umma_tf32_acc(tmem_base, ah, bl, DESC_HI, idesc);
 #pragma unroll
-                    for (int j = 0; j < TC_KS / 8; ++j) {
-                        const uint32_t ko = (uint32_t)j * 256;       // two 128-byte K chunks per k-step
-                        umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_hi + ko), idesc, (s | j) ? 1u : 0u);
-                        umma_tf32(tmem_base, smem_desc(a_lo + ko), smem_desc(b_hi + ko), idesc, 1u);
-                        umma_tf32(tmem_base, smem_desc(a_hi + ko), smem_desc(b_lo + ko), idesc, 1u);
+                    for (int j = 1; j < TC_KS / 8; ++j) {
+                        const uint32_t ko = (uint32_t)j * 16;
+                        umma_tf32_acc(tmem_base, ah + ko, bh + ko, DESC_HI, idesc);
+                        umma_tf32_acc(tmem_base, al + ko, bh + ko, DESC_HI, idesc);
+                        umma_tf32_acc(tmem_base, ah + ko, bl + ko, DESC_HI, idesc);
                     }
                     umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
                     umma_commit(&b_empty[sb]);
+                    TC_TRACE(3, g);
                 }
                 umma_commit(&accum_bar);          // this tile's accumulator is complete
             }
@@ -398,4 +424,10 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
 #undef ST_TC_CASE
     set_error("st_conv_gather_tc: cin=%d not instantiated", cin);
     return ST_ERR_UNSUPPORTED;
+}
+
+// debug only (not part of include/st_b200.h)
+extern "C" int st_debug_tc_trace(long long *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_tc_trace, sizeof(long long) * 5 * 64));
+    return ST_OK;
 }

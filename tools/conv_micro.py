@@ -49,3 +49,16 @@ for cin, cout, li in cases:
     us = float(np.median(ts))
     byt = 4 * lv.n * (cin + cout)
     print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s  ({byt / us / 1e3 / 6525.2 * 100:5.2f}% of measured HBM peak)")
+
+if only and impl == "tc":
+    import ctypes as C
+    from smart_tree_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_longlong * 320)()
+    lib.st_debug_tc_trace.argtypes = [C.c_void_p]
+    lib.st_debug_tc_trace(buf)
+    t = np.array(buf[:]).reshape(5, 64)
+    t0 = t[0, 0]
+    names = ["prod: a_empty ok", "prod: arrived   ", "mma : a_full ok ", "mma : committed ", "mma : b_full ok "]
+    for g in range(0, 24):
+        print(g, "  ".join(f"{names[k].strip()}={t[k, g] - t0:7d}" for k in (0, 1, 4, 2, 3)))
