@@ -4,9 +4,11 @@
 //
 // Implicit GEMM per CTA: M = 128 output rows, N = Cout (padded to a multiple of 16), K = 27*Cin
 // walked in stages of 32.  Per stage
-//   * 8 producer warps gather the neighbour rows (128-bit loads through L2; every feature array of
-//     the network is L2 resident), split each fp32 value into a TF32 head and an fp32 tail, and
-//     store both as K-major core-matrix tiles in shared memory (conflict-free 128-bit stores);
+//   * 8 producer warps gather the neighbour rows (128-bit loads; rows are kept in Z-order so most hit
+//     L1), split each fp32 value into a TF32 head and an fp32 tail, and write both straight into
+//     TENSOR MEMORY with tcgen05.st (thread = row = TMEM lane, K along the columns): the A operand never
+//     touches shared memory -- with the 3xTF32 split an smem-resident A would be read three times per
+//     k-step and made the first version of this kernel shared-memory-bandwidth bound;
 //   * the weight tile (head + tail, pre-arranged by st_conv_tc_prepare) arrives by one 1-D bulk
 //     async copy (cp.async.bulk -> UBLKCP) into its own deeper ring, issued several stages ahead by a
 //     dedicated loader lane so that its L2 latency never sits on the MMA critical path;
@@ -25,7 +27,8 @@ namespace {
 
 constexpr int TC_M = 128;          // rows per CTA
 constexpr int TC_KS = 32;          // K elements per stage
-constexpr int TC_STAGES = 2;
+constexpr int TC_STAGES = 3;          // A stages, in tensor memory (64 columns each: 32 hi + 32 lo)
+constexpr int TC_A_COLS = 2 * TC_KS;
 constexpr int TC_MAXTAPS = 28;        // gather-map entries of a row cached in shared memory
 constexpr int TC_PRODUCERS = 256;  // 8 warps: 2 threads per row
 constexpr int TC_THREADS = TC_PRODUCERS + 64;   // + MMA issuer warp + weight-loader warp
@@ -82,6 +85,18 @@ __device__ __forceinline__ void umma_tf32_init(uint32_t tmem_d, uint32_t a_lo, u
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %4, p;\n\t}"
                  ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(desc_hi), "r"(idesc) : "memory");
 }
+// D[tmem] (+)= A[tmem] . B[smem]^T : A = 128 lanes x 8 columns (row i in lane i, k along the columns)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t desc_hi, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .b64 db;\n\t.reg .pred p;\n\tmov.b64 db, {%2, %3};\n\tsetp.ne.b32 p, %5, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(desc_hi), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                   "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // descriptor words: lo = (addr >> 4) | LBO(128 B) << 16 ; hi = SBO(1024 B) | version 1 << 14
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); }
 constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14);
@@ -127,18 +142,19 @@ struct TcArgs {
 template <int CIN>
 __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // smem: TC_STAGES x { A_hi (16 KB) | A_lo (16 KB) }  then  sb x { B_hi | B_lo } (npad*128 B each)
+    // smem: sb x { B_hi | B_lo } (npad*128 B each).  TMEM: [0, npad) accumulator, then TC_STAGES x 64 A columns.
     const int b_tile_bytes = a.npad * TC_KS * 4;
     const int b_stage_bytes = 2 * b_tile_bytes;
-    constexpr int A_STAGE_BYTES = 2 * A_TILE_FLOATS * 4;
-    uint8_t *const b_ring = smem_raw + TC_STAGES * A_STAGE_BYTES;
+    uint8_t *const b_ring = smem_raw;
     const int SB = a.b_stages;
     __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int smap[2][TC_MAXTAPS][TC_M];     // gather-map entries of the current / next tile (28 KB)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tmem_cols = a.npad <= 32 ? 32u : (a.npad <= 64 ? 64u : (a.npad <= 128 ? 128u : 256u));
+    const uint32_t tmem_need = (uint32_t)a.npad + TC_STAGES * TC_A_COLS;
+    const uint32_t tmem_cols = tmem_need <= 256 ? 256u : 512u;
+    const uint32_t a_col0 = (uint32_t)a.npad;
     const int ntiles = (a.n_out + TC_M - 1) / TC_M;
 
     if (tid == 0) {
@@ -215,23 +231,26 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 if (g >= TC_STAGES) {
                     if (lane == 0) mbar_wait(&a_empty[st], ((g / TC_STAGES) - 1) & 1);
                     __syncwarp();
+                    tc_fence_after();     // the MMAs that read this TMEM stage have completed
                 }
                 if (tid == 0) TC_TRACE(0, g);
-                uint8_t *stage = smem_raw + (size_t)st * A_STAGE_BYTES;
+                // TMEM address of this thread's 16 columns of stage st: lanes 32*(warp&3).., columns a_col0 + st*64 + half*16
+                const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + a_col0 + (uint32_t)st * TC_A_COLS + (uint32_t)half * 16;
+                uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    float4 hi, lo;
-                    hi.x = __uint_as_float(__float_as_uint(xc[q].x) & 0xFFFFE000u); lo.x = xc[q].x - hi.x;
-                    hi.y = __uint_as_float(__float_as_uint(xc[q].y) & 0xFFFFE000u); lo.y = xc[q].y - hi.y;
-                    hi.z = __uint_as_float(__float_as_uint(xc[q].z) & 0xFFFFE000u); lo.z = xc[q].z - hi.z;
-                    hi.w = __uint_as_float(__float_as_uint(xc[q].w) & 0xFFFFE000u); lo.w = xc[q].w - hi.w;
-                    const uint32_t off = row_off + (uint32_t)(half * 4 + q) * 128;
-                    *(float4 *)(stage + off) = hi;
-                    *(float4 *)(stage + A_TILE_FLOATS * 4 + off) = lo;
+                    const float v[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint32_t h = __float_as_uint(v[i]) & 0xFFFFE000u;
+                        hi[q * 4 + i] = h;
+                        lo[q * 4 + i] = __float_as_uint(v[i] - __uint_as_float(h));
+                    }
                 }
-                // No proxy fence here: it would make every producer wait for its in-flight prefetch loads.
-                // The writes are released by the mbarrier arrive; the MMA thread, which has nothing in
-                // flight, issues the generic->async proxy fence after acquiring the barrier.
+                tmem_st16(ta, hi);
+                tmem_st16(ta + TC_KS, lo);
+                tmem_st_wait();
+                tc_fence_before();        // order the TMEM writes before the arrive that hands them to the MMA thread
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
                 if (tid == 0) TC_TRACE(1, g);
@@ -297,21 +316,15 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     TC_TRACE(4, g);
                     mbar_wait(&a_full[st], (g / TC_STAGES) & 1);
                     TC_TRACE(2, g);
-                    fence_proxy_async();          // producers' generic-proxy smem writes -> async (tensor core) proxy
                     tc_fence_after();
-                    // descriptor low words of the four operand tiles; a k-step advances each by 256 B = 16 units
-                    const uint32_t ah = desc_lo(smem_u32(smem_raw + (size_t)st * A_STAGE_BYTES)), al = ah + (A_TILE_FLOATS * 4 >> 4);
+                    const uint32_t ah = tmem_base + a_col0 + (uint32_t)st * TC_A_COLS, al = ah + TC_KS;
                     const uint32_t bh = desc_lo(smem_u32(b_ring + (size_t)sb * b_stage_bytes)), bl = bh + (uint32_t)(b_tile_bytes >> 4);
-                    if (s == 0) umma_tf32_init(tmem_base, ah, bh, DESC_HI, idesc);
-                    else        umma_tf32_acc(tmem_base, ah, bh, DESC_HI, idesc);
-                    umma_tf32_acc(tmem_base, al, bh, DESC_HI, idesc);
-                    umma_tf32_acc(tmem_base, ah, bl, DESC_HI, idesc);
 #pragma unroll
-                    for (int j = 1; j < TC_KS / 8; ++j) {
-                        const uint32_t ko = (uint32_t)j * 16;
-                        umma_tf32_acc(tmem_base, ah + ko, bh + ko, DESC_HI, idesc);
-                        umma_tf32_acc(tmem_base, al + ko, bh + ko, DESC_HI, idesc);
-                        umma_tf32_acc(tmem_base, ah + ko, bl + ko, DESC_HI, idesc);
+                    for (int j = 0; j < TC_KS / 8; ++j) {
+                        const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
+                        umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s | j) ? 1u : 0u);
+                        umma_tf32_ts(tmem_base, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
+                        umma_tf32_ts(tmem_base, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
                     }
                     umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
                     umma_commit(&b_empty[sb]);
@@ -396,18 +409,18 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");
     ST_REQUIRE(!in2 || (w2 && ((uintptr_t)w2 & 15) == 0), "in2 needs a 16-byte aligned w2");
     const int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
-    // weight ring depth: as deep as fits next to the two A stages while keeping two CTAs per SM when the
-    // weight tile is small (the bulk copies must be issued ~2000 cycles ahead of their MMAs)
-    const int a_bytes = TC_STAGES * 2 * A_TILE_FLOATS * 4, b_stage = 2 * npad * TC_KS * 4;
-    int sb = (npad <= 32 ? (80 * 1024 - a_bytes) : (180 * 1024 - a_bytes)) / b_stage;      // 28 KB of static smem for the map
+    // weight ring: deep enough that the bulk copies are issued ~2000 cycles ahead of their MMAs
+    const int b_stage = 2 * npad * TC_KS * 4;
+    int sb = (npad <= 32 ? 40 * 1024 : 128 * 1024) / b_stage;
     sb = sb > TC_MAX_BSTAGES ? TC_MAX_BSTAGES : (sb < 2 ? 2 : sb);
     if (sb > nst) sb = nst;
     TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
-    const int smem = a_bytes + sb * b_stage + 1024;
+    const int smem = sb * b_stage + 1024;
     static int n_sms = 0;
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int64_t ntiles = cdiv(n_out, TC_M);
-    const int ctas_per_sm = smem <= 82 * 1024 ? 2 : 1;
+    // two CTAs per SM when both fit: 256 TMEM columns each (accumulator + 3 A stages) and ~75 KB of smem
+    const int ctas_per_sm = (npad + TC_STAGES * TC_A_COLS <= 256 && smem <= 80 * 1024) ? 2 : 1;
     const unsigned grid = (unsigned)(ntiles < (int64_t)n_sms * ctas_per_sm ? ntiles : (int64_t)n_sms * ctas_per_sm);   // persistent CTAs
 #define ST_TC_CASE(CI)                                                                                              \
     if (cin == CI) {                                                                                                \
