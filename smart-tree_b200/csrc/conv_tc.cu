@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        int g = 0;                                    // global stage counter (ring position / phase)
+        int g = 0, st = 0;                            // global stage counter, ring position
+        uint32_t pe = 1;                              // parity of the previous use of A stage `st`
         int tile_iter = 0;
         prefetch_map(blockIdx.x, 0);
         map_ready();
@@ -226,10 +227,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             float4 xc[4], xn[4];
             load_rows(buf, 0, xc);
             for (int s = 0; s < a.nstages; ++s, ++g) {
-                const int st = g % TC_STAGES;
                 if (s + 1 < a.nstages) load_rows(buf, s + 1, xn);
                 if (g >= TC_STAGES) {
-                    if (lane == 0) mbar_wait(&a_empty[st], ((g / TC_STAGES) - 1) & 1);
+                    if (lane == 0) mbar_wait(&a_empty[st], pe);
                     __syncwarp();
                     tc_fence_after();     // the MMAs that read this TMEM stage have completed
                 }
@@ -256,6 +256,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 if (tid == 0) TC_TRACE(1, g);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) xc[q] = xn[q];
+                if (++st == TC_STAGES) { st = 0; pe ^= 1; }
             }
             // ---------------- epilogue of this tile ----------------
             mbar_wait(&accum_bar, tile_iter & 1);
@@ -308,17 +309,21 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
         // ================= MMA issuer (one elected lane) =================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
         if (lane == 0) {
-            int g = 0;
+            // ring positions and phase bits are kept incrementally: this single thread is the serial
+            // bottleneck of the CTA, an integer division per stage here costs more than the MMAs
+            int g = 0, st = 0, sb = 0;
+            uint32_t pa = 0, pb = 0;
+            const uint32_t a_stage0 = tmem_base + a_col0;
+            const uint32_t b_base = desc_lo(smem_u32(b_ring)), b_stage_units = (uint32_t)(b_stage_bytes >> 4), b_lo_off = (uint32_t)(b_tile_bytes >> 4);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int s = 0; s < a.nstages; ++s, ++g) {
-                    const int st = g % TC_STAGES, sb = g % SB;
-                    mbar_wait(&b_full[sb], (g / SB) & 1);
+                    mbar_wait(&b_full[sb], pb);
                     TC_TRACE(4, g);
-                    mbar_wait(&a_full[st], (g / TC_STAGES) & 1);
+                    mbar_wait(&a_full[st], pa);
                     TC_TRACE(2, g);
                     tc_fence_after();
-                    const uint32_t ah = tmem_base + a_col0 + (uint32_t)st * TC_A_COLS, al = ah + TC_KS;
-                    const uint32_t bh = desc_lo(smem_u32(b_ring + (size_t)sb * b_stage_bytes)), bl = bh + (uint32_t)(b_tile_bytes >> 4);
+                    const uint32_t ah = a_stage0 + (uint32_t)st * TC_A_COLS, al = ah + TC_KS;
+                    const uint32_t bh = b_base + (uint32_t)sb * b_stage_units, bl = bh + b_lo_off;
 #pragma unroll
                     for (int j = 0; j < TC_KS / 8; ++j) {
                         const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
@@ -329,6 +334,8 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
                     umma_commit(&b_empty[sb]);
                     TC_TRACE(3, g);
+                    if (++st == TC_STAGES) { st = 0; pa ^= 1; }
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
                 umma_commit(&accum_bar);          // this tile's accumulator is complete
             }
@@ -337,13 +344,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     } else {
         // ================= weight loader (one elected lane): SB stages ahead of the MMAs =================
         if (lane == 0) {
-            int g = 0;
+            int g = 0, sb = 0;
+            uint32_t pb = 1;              // parity of the *previous* use of the slot
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const float *src = a.wprep;
                 for (int s = 0; s < a.nstages; ++s, ++g) {
-                    const int sb = g % SB;
-                    if (g >= SB) mbar_wait(&b_empty[sb], ((g / SB) - 1) & 1);
+                    if (g >= SB) mbar_wait(&b_empty[sb], pb);
                     mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
-                    bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, a.wprep + (size_t)s * 2 * a.npad * TC_KS, (uint32_t)b_stage_bytes, &b_full[sb]);
+                    bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[sb]);
+                    src += 2 * a.npad * TC_KS;
+                    if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
             }
         }
