@@ -58,6 +58,13 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// exactly one lane of a converged warp; the compiler then emits warp-uniform instructions (UTCHMMA, UTCBAR,
+// UBLKCP) directly instead of wrapping each one in an ELECT/branch serialisation loop
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -167,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_base_sh;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_sh, 0);
 
     if (warp < 8) {
         // ================= producers (then epilogue), persistent over tiles =================
@@ -308,9 +315,10 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
     } else if (warp == 8) {
         // ================= MMA issuer (one elected lane) =================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
-        if (lane == 0) {
-            // ring positions and phase bits are kept incrementally: this single thread is the serial
-            // bottleneck of the CTA, an integer division per stage here costs more than the MMAs
+        {
+            // The whole warp walks the stages in lock step (so every address below is warp-uniform and lives
+            // in uniform registers); one elected lane issues.  Ring positions and phase bits are kept
+            // incrementally: this warp is the serial bottleneck of the CTA.
             int g = 0, st = 0, sb = 0;
             uint32_t pa = 0, pb = 0;
             const uint32_t a_stage0 = tmem_base + a_col0;
@@ -318,40 +326,45 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 for (int s = 0; s < a.nstages; ++s, ++g) {
                     mbar_wait(&b_full[sb], pb);
-                    TC_TRACE(4, g);
+                    if (lane == 0) TC_TRACE(4, g);
                     mbar_wait(&a_full[st], pa);
-                    TC_TRACE(2, g);
+                    if (lane == 0) TC_TRACE(2, g);
                     tc_fence_after();
                     const uint32_t ah = a_stage0 + (uint32_t)st * TC_A_COLS, al = ah + TC_KS;
                     const uint32_t bh = b_base + (uint32_t)sb * b_stage_units, bl = bh + b_lo_off;
+                    if (elect_one_sync()) {
 #pragma unroll
-                    for (int j = 0; j < TC_KS / 8; ++j) {
-                        const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
-                        umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s | j) ? 1u : 0u);
-                        umma_tf32_ts(tmem_base, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
-                        umma_tf32_ts(tmem_base, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
+                        for (int j = 0; j < TC_KS / 8; ++j) {
+                            const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
+                            umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s | j) ? 1u : 0u);
+                            umma_tf32_ts(tmem_base, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
+                            umma_tf32_ts(tmem_base, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
+                        }
+                        umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
+                        umma_commit(&b_empty[sb]);
+                        if (s == a.nstages - 1) umma_commit(&accum_bar);      // this tile's accumulator is complete
                     }
-                    umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
-                    umma_commit(&b_empty[sb]);
-                    TC_TRACE(3, g);
+                    __syncwarp();
+                    if (lane == 0) TC_TRACE(3, g);
                     if (++st == TC_STAGES) { st = 0; pa ^= 1; }
                     if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
-                umma_commit(&accum_bar);          // this tile's accumulator is complete
             }
         }
-        __syncwarp();
     } else {
         // ================= weight loader (one elected lane): SB stages ahead of the MMAs =================
-        if (lane == 0) {
+        {
             int g = 0, sb = 0;
             uint32_t pb = 1;              // parity of the *previous* use of the slot
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const float *src = a.wprep;
                 for (int s = 0; s < a.nstages; ++s, ++g) {
                     if (g >= SB) mbar_wait(&b_empty[sb], pb);
-                    mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
-                    bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[sb]);
+                    if (elect_one_sync()) {
+                        mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
+                        bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[sb]);
+                    }
+                    __syncwarp();
                     src += 2 * a.npad * TC_KS;
                     if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
