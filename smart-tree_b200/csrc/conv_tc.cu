@@ -230,11 +230,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             const int row = tile * TC_M + rloc;
             const bool row_ok = row < a.n_out;
             prefetch_map(tile + gridDim.x, buf ^ 1);
-            // software pipeline: feature rows one stage ahead of the stores
-            float4 xc[4], xn[4];
+            // software pipeline: feature rows two stages ahead of the stores (covers the tail latency of the
+            // ~1000 gathers a stage consists of; the slowest one gates the whole CTA)
+            float4 xc[4], xn[4], xm[4];
             load_rows(buf, 0, xc);
+            if (a.nstages > 1) load_rows(buf, 1, xn);
             for (int s = 0; s < a.nstages; ++s, ++g) {
-                if (s + 1 < a.nstages) load_rows(buf, s + 1, xn);
+                if (s + 2 < a.nstages) load_rows(buf, s + 2, xm);
                 if (g >= TC_STAGES) {
                     if (lane == 0) mbar_wait(&a_empty[st], pe);
                     __syncwarp();
@@ -262,7 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
                 if (tid == 0) TC_TRACE(1, g);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) xc[q] = xn[q];
+                for (int q = 0; q < 4; ++q) { xc[q] = xn[q]; xn[q] = xm[q]; }
                 if (++st == TC_STAGES) { st = 0; pe ^= 1; }
             }
             // ---------------- epilogue of this tile ----------------
