@@ -229,7 +229,7 @@ def _rel_close(got, ref, tol=1e-3):
     return err
 
 
-@pytest.mark.parametrize("impl", ["fma", "tc"])
+@pytest.mark.parametrize("impl", ["fma", "tc", "auto"])
 @pytest.mark.parametrize("weights", ["noble-elevator-58", "peach-forest-65", "random"])
 def test_unet_forward_matches_oracle(weights, impl):
     from smart_tree_b200.engine import SmartTreeEngine
