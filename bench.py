@@ -289,6 +289,9 @@ def run_b200(args):
 
 
 def main():
+    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry the JSON line only
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse()
     if args.impl == "reference":
         run_reference(args)
