@@ -233,6 +233,17 @@ int st_points_to_tubes(const float *pts, int64_t n_q, const float *a, const floa
                        const float *r1, const float *r2, const int32_t *tube_off,
                        float *out_vec, int32_t *out_idx, float *out_r, void *stream);
 
+/* TreeSkeleton.repair for a whole skeleton in one launch   smart_tree/data_types/tree.py:73-92
+ * nodes[R,4] = (xyz, radius) of all branches; branch b owns rows row[b]+1 .. row[b]+len[b] and row[b] is a
+ * spare row that receives its connection point (and the first node's radius).  Branches are listed sorted
+ * by depth below the first repaired level: level_off[n_levels+1]; parent[b] indexes the same arrays
+ * (any branch, not only listed ones: give all branches, levels cover the repaired ones first ... see
+ * smart-tree_b200/data_types/tree.py); parent_repaired[b] != 0 iff the parent's spare row is already part
+ * of its polyline when b is visited (the reference visits parents before children).              */
+int st_repair_branches(float *nodes, const int32_t *row, const int32_t *len, const int32_t *parent,
+                       const uint8_t *parent_repaired, const int32_t *level_off, int32_t n_levels,
+                       void *stream);
+
 #ifdef __cplusplus
 }
 #endif

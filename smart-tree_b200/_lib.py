@@ -59,6 +59,7 @@ SIGNATURES = {
     "st_tree_distances": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "st_sample_tree_workspace_bytes": (_sz, [_i64, _i32]),
     "st_sample_tree": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "st_repair_branches": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p]),
     "st_points_to_tubes": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
 }
 

@@ -444,3 +444,56 @@ extern "C" int st_points_to_tubes(const float *pts, int64_t n_q, const float *a,
     ST_CHECK_LAUNCH();
     return ST_OK;
 }
+
+// ------------------------------------------------------------------------------------ repair, all levels in one launch
+// TreeSkeleton.repair (smart_tree/data_types/tree.py:73-92) on the shared node array nodes[R,4] (xyz, radius;
+// branch b owns rows row[b]+1 .. row[b]+len[b], row[b] is its spare row).  Branches are given sorted by tree
+// depth (level_off); a branch's connection point is the nearest-tube projection of its first node onto its
+// parent's CURRENT polyline (which includes the parent's own connection point iff parent_repaired).
+// One CTA walks the levels with a block barrier in between; one warp per branch.
+__global__ void __launch_bounds__(1024) k_repair(float *nodes, const int32_t *__restrict__ row, const int32_t *__restrict__ len,
+                                                 const int32_t *__restrict__ parent, const uint8_t *__restrict__ parent_repaired,
+                                                 const int32_t *__restrict__ level_off, int n_levels) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int lv = 0; lv < n_levels; ++lv) {
+        for (int b = level_off[lv] + warp; b < level_off[lv + 1]; b += nwarp) {
+            const int pb = parent[b];
+            const int r0 = row[b] + 1;
+            const float px = nodes[4 * r0], py = nodes[4 * r0 + 1], pz = nodes[4 * r0 + 2];
+            const int t0 = parent_repaired[b] ? row[pb] : row[pb] + 1;     // first node row of the parent polyline
+            const int t1 = row[pb] + len[pb];                              // last node row
+            float best = ST_INF, bx = 0, by = 0, bz = 0;
+            int bidx = INT_MAX;
+            for (int m = t0 + lane; m < t1; m += 32) {
+                float ax = nodes[4 * m], ay = nodes[4 * m + 1], az = nodes[4 * m + 2], r1 = nodes[4 * m + 3];
+                float cx = nodes[4 * m + 4], cy = nodes[4 * m + 5], cz = nodes[4 * m + 6], r2 = nodes[4 * m + 7];
+                float abx = cx - ax, aby = cy - ay, abz = cz - az;
+                float apx = px - ax, apy = py - ay, apz = pz - az;
+                float t = fminf(fmaxf((apx * abx + apy * aby + apz * abz) / (abx * abx + aby * aby + abz * abz), 0.f), 1.f);
+                float dx = ax + t * abx - px, dy = ay + t * aby - py, dz = az + t * abz - pz;
+                float score = fabsf(sqrtf(dx * dx + dy * dy + dz * dz) - ((1.f - t) * r1 + t * r2));
+                if (score < best) { best = score; bidx = m; bx = dx; by = dy; bz = dz; }
+            }
+            for (int o = 16; o; o >>= 1) {
+                float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+                float ox = __shfl_xor_sync(0xffffffffu, bx, o), oy = __shfl_xor_sync(0xffffffffu, by, o), oz = __shfl_xor_sync(0xffffffffu, bz, o);
+                if (ob < best || (ob == best && oi < bidx)) { best = ob; bidx = oi; bx = ox; by = oy; bz = oz; }
+            }
+            if (lane == 0) {
+                const int rs = row[b];
+                nodes[4 * rs] = px + bx; nodes[4 * rs + 1] = py + by; nodes[4 * rs + 2] = pz + bz;
+                nodes[4 * rs + 3] = nodes[4 * r0 + 3];                      // radius of the first node (tree.py:92)
+            }
+        }
+        __syncthreads();
+    }
+}
+
+extern "C" int st_repair_branches(float *nodes, const int32_t *row, const int32_t *len, const int32_t *parent,
+                                  const uint8_t *parent_repaired, const int32_t *level_off, int32_t n_levels, void *stream) {
+    if (n_levels <= 0) return ST_OK;
+    k_repair<<<1, 1024, 0, (cudaStream_t)stream>>>(nodes, row, len, parent, parent_repaired, level_off, n_levels);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

@@ -16,10 +16,19 @@ __device__ __forceinline__ bool cand_less(float d2a, int ia, float d2b, int ib) 
 template <int K>
 __global__ void __launch_bounds__(128) k_knn(const float *__restrict__ src, int n, Grid g, const int32_t *__restrict__ cell_start,
                                              const float4 *__restrict__ sorted, float r, const float *__restrict__ qrad,
-                                             int32_t *__restrict__ idx, float *__restrict__ d2out) {
+                                             int32_t *__restrict__ idx, float *__restrict__ d2out, int self_query) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float qx = src[3 * (size_t)i], qy = src[3 * (size_t)i + 1], qz = src[3 * (size_t)i + 2];
+    float qx, qy, qz;
+    if (self_query) {
+        // queries == grid points: walk them in cell order, so a warp's 32 queries scan (nearly) the same
+        // cells -- coherent branches, L1-resident candidates -- and write to their own rows
+        const float4 q = __ldg(sorted + i);
+        qx = q.x; qy = q.y; qz = q.z;
+        i = __float_as_int(q.w);
+    } else {
+        qx = src[3 * (size_t)i]; qy = src[3 * (size_t)i + 1]; qz = src[3 * (size_t)i + 2];
+    }
     const float r2 = __fmul_rn(r, r);
     const float qr = qrad ? qrad[i] : 0.f;
     float reach = qrad ? fminf(r, qr) : r;
@@ -83,7 +92,8 @@ extern "C" int st_knn(const float *src, int64_t n, const float *dst, int64_t m, 
     int rc = build_grid(dst, m, h, cv, gb, s);
     if (rc) return rc;
     unsigned g = (unsigned)cdiv(n, 128);
-#define ST_K(KK) case KK: k_knn<KK><<<g, 128, 0, s>>>(src, (int)n, gb.g, gb.cell_start, gb.sorted, r, query_radius, idx, d2); break;
+    const int self_query = (src == dst && n == m) ? 1 : 0;
+#define ST_K(KK) case KK: k_knn<KK><<<g, 128, 0, s>>>(src, (int)n, gb.g, gb.cell_start, gb.sorted, r, query_radius, idx, d2, self_query); break;
     switch (K) {
         ST_K(1) ST_K(2) ST_K(4) ST_K(8) ST_K(16) ST_K(24) ST_K(32)
         default: set_error("st_knn: K=%d not instantiated (1,2,4,8,16,24,32)", K); return ST_ERR_UNSUPPORTED;
@@ -99,7 +109,9 @@ __global__ void __launch_bounds__(128) k_outlier(const float *__restrict__ pts, 
                                                  uint8_t *__restrict__ keep) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float qx = pts[3 * (size_t)i], qy = pts[3 * (size_t)i + 1], qz = pts[3 * (size_t)i + 2];
+    const float4 qq = __ldg(sorted + i);          // cell order: coherent warps (see k_knn)
+    const float qx = qq.x, qy = qq.y, qz = qq.z;
+    i = __float_as_int(qq.w);
     const float r2 = __fmul_rn(r, r);
     const float qr = radii[i];
     // the nb nearest all lie strictly inside radius_i  <=>  at least nb points with d2 < r^2 and sqrt(d2) < radius_i

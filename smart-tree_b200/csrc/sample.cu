@@ -54,14 +54,20 @@ struct SampleArgs {
     int32_t *branch_id;
     unsigned long long *best;
     int32_t *path_out, *branch_len, *branch_parent, *comp_nb, *comp_np;
+    int32_t *touched;      // [n] segment-local list of points claimed in the current iteration
+    int32_t *touch_cnt;    // [2 * n_comp] append counters, alternating by iteration parity
 };
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered
 // 0 .. RW*RW-1 around the vertex's own cell, so a short path still spreads over every warp of the cluster.
-template <bool CLAIM>
-__device__ __forceinline__ void scan_task(const SampleArgs &a, int base, int nc, int v, unsigned pos, int row, int R, float r,
-                                          float r2, int lane, bool emit, int bid) {
-    const float px = a.pts[3 * (size_t)(base + v)], py = a.pts[3 * (size_t)(base + v) + 1], pz = a.pts[3 * (size_t)(base + v) + 2];
+constexpr int PATH_SMEM = 2048;    // path vertices whose position is staged in shared memory per iteration
+
+// One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered 0 .. RW*RW-1
+// around the vertex's own cell, so a short path still spreads over every warp of the cluster.  Every
+// point within r races a 64-bit atomicMin of (d2 bits, path position); the first claimer of a point
+// also appends it to the iteration's touched list, which is all the resolve phase has to walk.
+__device__ __forceinline__ void claim_task(const SampleArgs &a, int base, int nc, float px, float py, float pz, unsigned pos, int row,
+                                           int R, float r, float r2, int lane, int32_t *touch_cnt) {
     const Grid &g = a.g;
     const float rr = r * 1.0001f + 1e-7f;
     const int RW = 2 * R + 1;
@@ -72,26 +78,15 @@ __device__ __forceinline__ void scan_task(const SampleArgs &a, int base, int nc,
     const int x0 = cell_coord(px - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(px + rr, g.ox, g.inv_h, g.nx);
     const int rowc = (cz * g.ny + cy) * g.nx;
     const int beg = __ldg(a.cell_start + rowc + x0), end = __ldg(a.cell_start + rowc + x1 + 1);
-    const float vr = CLAIM ? 0.f : a.radii[base + v];
     for (int t = beg + lane; t < end; t += 32) {
         float4 q = __ldg(a.sorted + t);
         int gi = __float_as_int(q.w);
         if (gi < base || gi >= base + nc) continue;
         float d2 = dist2_exact(q.x, q.y, q.z, px, py, pz);
         if (!(d2 < r2)) continue;
-        if (CLAIM) {
-            unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
-            atomicMin(a.best + gi, key);
-        } else {
-            unsigned long long b = __ldcg(a.best + gi);
-            if ((unsigned)(b & 0xFFFFFFFFull) != pos || (unsigned)(b >> 32) != __float_as_uint(d2)) continue;
-            if (sqrtf(d2) < vr) {           // path.py:37-39: inside the radius of its nearest path vertex
-                a.distw[gi] = -1.f;
-                a.alloc[gi] = 1;
-                if (emit) a.branch_id[gi] = bid;
-            }
-            __stcg(a.best + gi, BEST_NONE);
-        }
+        unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
+        unsigned long long old = atomicMin(a.best + gi, key);
+        if (old == BEST_NONE) a.touched[base + atomicAdd(touch_cnt, 1)] = gi;
     }
 }
 
@@ -134,7 +129,8 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
     const int gwarp = cr * 32 + warp, nwarp = CL * 32;
     const int gtid = cr * 1024 + tid, nthr = CL * 1024;
     __shared__ int s_minpos, s_first, s_term, s_rbits;
-    int cursor = 0, bid = 0, pcur = 0;
+    __shared__ float4 s_path[PATH_SMEM];      // xyz + radius of the path vertices (first PATH_SMEM of them)
+    int cursor = 0, bid = 0, pcur = 0, iter = 0;
     __shared__ unsigned long long st[8];
     __shared__ long long s_tc;
     if (tid == 0) { for (int i = 0; i < 8; ++i) st[i] = 0; s_tc = clock64(); }
@@ -188,32 +184,52 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         ST_PHASE(1);
         if (tid == 0) { st[5] += 1; st[6] += len; }
         const int *path = out;
-        // ---- 3. search radius = max radius over the path
+        // ---- 3. stage the path (position + radius) in shared memory; search radius = max radius over the path
         float rl = 0.f;
-        for (int jj = tid; jj < len; jj += blockDim.x) rl = fmaxf(rl, a.radii[base + path[jj]]);
+        for (int jj = tid; jj < len; jj += blockDim.x) {
+            const int v = base + path[jj];
+            const float rv = a.radii[v];
+            if (jj < PATH_SMEM) s_path[jj] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+            rl = fmaxf(rl, rv);
+        }
         for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
         if (lane == 0 && rl > 0.f) atomicMax(&s_rbits, __float_as_int(rl));
         __syncthreads();
         const float r = __int_as_float(s_rbits);
         const float r2 = __fmul_rn(r, r);
         const bool emit = len >= 2;
+        int32_t *const cnt_cur = a.touch_cnt + 2 * c + (iter & 1);
         // ---- 4. claim: every point within r of the path records its nearest path vertex
         const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;       // cells reached on either side of the vertex's cell
         const int R2 = (2 * R + 1) * (2 * R + 1);
         const long long ntask = (long long)len * R2;
         if (r > 0.f)
             for (long long t = gwarp; t < ntask; t += nwarp) {
-                int jj = (int)(t / R2);
-                scan_task<true>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, emit, bid);
+                const int jj = (int)(t / R2);
+                float px, py, pz;
+                if (jj < PATH_SMEM) { const float4 p = s_path[jj]; px = p.x; py = p.y; pz = p.z; }
+                else { const int v = base + path[jj]; px = a.pts[3 * (size_t)v]; py = a.pts[3 * (size_t)v + 1]; pz = a.pts[3 * (size_t)v + 2]; }
+                claim_task(a, base, nc, px, py, pz, (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, cnt_cur);
             }
+        if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;      // next iteration's counter
         cluster_sync_all();
         ST_PHASE(2);
-        // ---- 5. resolve the winners, 6. allocate the path itself
-        if (r > 0.f)
-            for (long long t = gwarp; t < ntask; t += nwarp) {
-                int jj = (int)(t / R2);
-                scan_task<false>(a, base, nc, path[jj], (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, emit, bid);
+        // ---- 5. resolve: walk the touched list once; a point is on the branch iff it lies inside the radius of
+        //         its nearest path vertex (path.py:37-39).  6. allocate the path itself.
+        const int ntouch = __ldcg(cnt_cur);
+        for (int k = gtid; k < ntouch; k += nthr) {
+            const int gi = __ldcg(a.touched + base + k);
+            const unsigned long long bkey = __ldcg(a.best + gi);
+            const int jj = len - 1 - (int)(unsigned)(bkey & 0xFFFFFFFFull);
+            const float d2 = __uint_as_float((unsigned)(bkey >> 32));
+            const float vr = jj < PATH_SMEM ? s_path[jj].w : a.radii[base + path[jj]];
+            if (sqrtf(d2) < vr) {
+                a.distw[gi] = -1.f;
+                a.alloc[gi] = 1;
+                if (emit) a.branch_id[gi] = bid;
             }
+            __stcg(a.best + gi, BEST_NONE);
+        }
         for (int jj = gtid; jj < len; jj += nthr) {
             int v = base + path[jj];
             a.distw[v] = -1.f;
@@ -238,6 +254,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
             ++bid;
             pcur += len;
         }
+        ++iter;
         ST_PHASE(4);
     }
     if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
@@ -254,7 +271,7 @@ static size_t sort_bytes(int64_t n) {
 
 extern "C" size_t st_sample_tree_workspace_bytes(int64_t n, int32_t n_comp) {
     return grid_ws_bytes(n) + align_up(sort_bytes(n)) + 2 * align_up(n * 8) + 2 * align_up(n * 4) + align_up(n * 4) + align_up(n) +
-           align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + align_up(n * 4) + 8192;
+           align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + 2 * align_up(n * 4) + align_up((2 * (size_t)n_comp + 2) * 4) + 8192;
 }
 
 extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const int32_t *pred, const float *tree_dist,
@@ -273,6 +290,8 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     unsigned long long *keys2 = cv.take<unsigned long long>(n);
     int32_t *vals = cv.take<int32_t>(n);
     int32_t *order = cv.take<int32_t>(n);
+    int32_t *touched = cv.take<int32_t>(n);
+    int32_t *touch_cnt = cv.take<int32_t>(2 * (size_t)n_comp + 2);
     int32_t *jump = cv.take<int32_t>((size_t)JUMP_LEVELS * n);
     int32_t *vbase = cv.take<int32_t>(n);
     size_t sb = sort_bytes(n);
@@ -293,7 +312,8 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
         ST_CHECK_LAUNCH();
     }
     SampleArgs a{medial_pts, radii, pred, comp_off, gb.g, gb.cell_start, gb.sorted, order, distw, alloc, branch_id, best,
-                 path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path};
+                 path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path, touched, touch_cnt};
+    ST_CHECK_CUDA(cudaMemsetAsync(touch_cnt, 0, (2 * (size_t)n_comp + 2) * sizeof(int32_t), s));
     // largest cluster the device can co-schedule: more CTAs per component = more lanes on the scans
     static int cluster_cached = 0;
     int CL = cluster_cached;

@@ -35,13 +35,15 @@ class TreeSkeleton:
         return [t for b in self.branches.values() for t in b.to_tubes()]
 
     def _flat_store(self):
-        """The shared NodeStore if every branch is still an untouched view into one (fast paths)."""
+        """The shared NodeStore if every branch is still an unmodified view into one (fast paths).
+        `_flat` = (store, spare row, node count, connection point present)."""
         store = None
         for b in self.branches.values():
             f = b._flat
             if f is None or (store is not None and f[0] is not store):
                 return None
-            if b.xyz.shape[0] != f[2] or b.xyz.data_ptr() != f[0].host[f[1] + 1].data_ptr():
+            first = f[1] + (0 if f[3] else 1)
+            if b.xyz.shape[0] != f[2] + (1 if f[3] else 0) or b.xyz.data_ptr() != f[0].host[first].data_ptr():
                 return None
             store = f[0]
         return store
@@ -86,43 +88,38 @@ class TreeSkeleton:
                 br.radii = torch.cat((br.radii[[0]], br.radii))
 
     def _repair_flat(self, order, store):
-        """repair() on the shared node array: the tubes of all parents of a wave are read straight from
-        the device twin, connection points are written into the spare rows on the device (so the next
-        wave sees repaired parents) and copied to the host once at the end."""
+        """repair() on the shared node array in ONE kernel launch (st_repair_branches): branches sorted by
+        tree depth, a block barrier between depths so that children see repaired parents, connection
+        points written into the spare rows on the device and copied to the host once."""
         from .. import ops
         nd = store.dev
         dev = nd.device
         ids = self.branches
-        repaired = set()
-        done_rows = []
+        listed = [br for run in order for br in run]
+        in_order = {id(br) for br in listed}
+        level0 = [br for br in ids.values() if id(br) not in in_order]
+        seq = level0 + listed
+        index = {br._id: i for i, br in enumerate(seq)}
+        repaired_ids = {br._id for br in listed}
+        row = [br._flat[1] for br in seq]
+        ln = [br._flat[2] for br in seq]
+        par = [index.get(br.parent_id, -1) if id(br) in in_order else -1 for br in seq]
+        prep = [1 if (id(br) in in_order and br.parent_id in repaired_ids) else 0 for br in seq]
+        level_off = [len(level0)]
         for run in order:
-            q_row = torch.tensor([br._flat[1] for br in run], dtype=torch.int64)
-            ps, pc = [], []
-            for br in run:
-                _, o, ln = ids[br.parent_id]._flat
-                s0 = o if br.parent_id in repaired else o + 1
-                ps.append(s0); pc.append(o + ln - s0)                      # first tube row, tube count
-            meta = torch.tensor([ps, pc], dtype=torch.int64).to(dev, non_blocking=True)
-            q_row_d = q_row.to(dev, non_blocking=True)
-            cnt = meta[1]
-            off = torch.zeros(len(run) + 1, dtype=torch.int64, device=dev)
-            off[1:] = torch.cumsum(cnt, 0)
-            tube = torch.repeat_interleave(meta[0] - off[:-1], cnt) + torch.arange(int(sum(pc)), device=dev)
-            pts = nd[q_row_d + 1, :3].contiguous()
-            a, b_ = nd[tube], nd[tube + 1]
-            vec, _, _ = ops.points_to_tubes(pts, a[:, :3].contiguous(), b_[:, :3].contiguous(), a[:, 3].contiguous(),
-                                            b_[:, 3].contiguous(), off.int())
-            nd[q_row_d, :3] = pts + vec
-            repaired.update(br._id for br in run)
-            done_rows.append(q_row)
-        rows = torch.cat(done_rows)
-        store.host[rows, :3] = nd[rows.to(dev), :3].cpu()
-        for run in order:
-            for br in run:
-                _, o, ln = br._flat
-                br.xyz = store.host[o:o + ln + 1, :3]
-                br.radii = store.host[o:o + ln + 1, 3:4]
-                br._flat = None                                            # no longer the pristine view
+            level_off.append(level_off[-1] + len(run))
+        meta = torch.tensor([row, ln, par], dtype=torch.int32).to(dev, non_blocking=True)
+        ops.repair_branches(nd, meta[0].contiguous(), meta[1].contiguous(), meta[2].contiguous(),
+                            torch.tensor(prep, dtype=torch.uint8).to(dev, non_blocking=True),
+                            torch.tensor(level_off, dtype=torch.int32).to(dev, non_blocking=True))
+        rows = torch.tensor([br._flat[1] for br in listed], dtype=torch.int64)
+        store.host[rows] = nd[rows.to(dev)].cpu()
+        host = store.host
+        for br in listed:
+            st, o, n, _ = br._flat
+            br.xyz = host[o:o + n + 1, :3]
+            br.radii = host[o:o + n + 1, 3:4]
+            br._flat = (st, o, n, True)
 
     def branch_lengths(self):
         """Polyline length of every branch in one vectorised pass (== BranchSkeleton.length)."""
@@ -130,10 +127,11 @@ class TreeSkeleton:
         store = self._flat_store()
         if store is not None:
             # contiguous rows of the shared array: per-branch sums of consecutive-row distances
-            o = torch.tensor([b._flat[1] for b in bs]); n = torch.tensor([b._flat[2] for b in bs])
+            first = torch.tensor([b._flat[1] + (0 if b._flat[3] else 1) for b in bs])
+            last = torch.tensor([b._flat[1] + b._flat[2] for b in bs])
             seg = (store.host[1:, :3] - store.host[:-1, :3]).norm(dim=1)
             cs = torch.cat([seg.new_zeros(1, dtype=torch.float64), seg.double().cumsum(0)])
-            return (cs[o + n] - cs[o + 1]).float()
+            return (cs[last] - cs[first]).float()
         xyz = torch.cat([b.xyz for b in bs])
         n = torch.tensor([len(b) for b in bs])
         seg = (xyz[1:] - xyz[:-1]).norm(dim=1)
@@ -151,8 +149,9 @@ class TreeSkeleton:
         lengths = self.branch_lengths().tolist()
         store = self._flat_store()
         if store is not None:
-            o = torch.tensor([b._flat[1] for b in self.branches.values()]); n = torch.tensor([b._flat[2] for b in self.branches.values()])
-            init_r = torch.maximum(store.host[o + 1, 3], store.host[o + n, 3]).tolist()
+            first = torch.tensor([b._flat[1] + (0 if b._flat[3] else 1) for b in self.branches.values()])
+            last = torch.tensor([b._flat[1] + b._flat[2] for b in self.branches.values()])
+            init_r = torch.maximum(store.host[first, 3], store.host[last, 3]).tolist()
         else:
             init_r = [float(max(b.radii[0], b.radii[-1])) for b in self.branches.values()]
         keep = {root_id: self.branches[root_id]}
@@ -176,6 +175,9 @@ class TreeSkeleton:
         todo = [b for b in self.branches.values() if b.radii.shape[0] > kernel_size]
         if not todo:
             return
+        store = self._flat_store()
+        if store is not None and kernel_size % 2 == 1:
+            return self._smooth_flat(todo, store, kernel_size)
         pad = kernel_size // 2
         z = torch.zeros(pad)
         sig = torch.cat([t for b in todo for t in (b.radii.reshape(-1).float(), z)])
@@ -186,6 +188,24 @@ class TreeSkeleton:
             n = b.radii.shape[0]
             b.radii = out[o:o + n].clone()
             o += n + pad
+
+    def _smooth_flat(self, todo, store, kernel_size):
+        """Box filter of every branch at once on the shared array: windowed sums from one float64
+        running sum, window clipped to the branch (== zero padding), divided by the kernel size."""
+        h = kernel_size // 2
+        first = torch.tensor([b._flat[1] + (0 if b._flat[3] else 1) for b in todo])
+        cnt = torch.tensor([b.radii.shape[0] for b in todo])
+        last = first + cnt - 1
+        rows = torch.repeat_interleave(first - torch.cumsum(cnt, 0) + cnt, cnt) + torch.arange(int(cnt.sum()))
+        lo = torch.maximum(rows - h, torch.repeat_interleave(first, cnt))
+        hi = torch.minimum(rows + h, torch.repeat_interleave(last, cnt))
+        cs = torch.cat([torch.zeros(1, dtype=torch.float64), store.host[:, 3].double().cumsum(0)])
+        out = ((cs[hi + 1] - cs[lo]) / kernel_size).float()
+        o = 0
+        for b, n in zip(todo, cnt.tolist()):
+            b.radii = out[o:o + n]
+            o += n
+            b._flat = None                       # radii no longer live in the shared array
 
     @property
     def length(self):

@@ -15,7 +15,7 @@ LAUNCHES = 0
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1}
+                     "sample_tree": 5, "tubes": 1, "repair": 1}
 
 
 def _count(op):
@@ -388,3 +388,13 @@ def points_to_tubes(pts, a, b, r1, r2, tube_off):
     _lib.check(lib.st_points_to_tubes(_ptr(pts), nq, _ptr(a), _ptr(b), _ptr(r1), _ptr(r2), _ptr(tube_off), _ptr(vec),
                                       _ptr(idx), _ptr(rr), _stream()), "st_points_to_tubes")
     return vec, idx, rr
+
+
+def repair_branches(nodes, row, length, parent, parent_repaired, level_off):
+    """In-place on nodes [R,4]: writes every listed branch's connection point into its spare row."""
+    lib = _lib.load()
+    _req(nodes, F32, "nodes"); _req(row, I32, "row"); _req(length, I32, "len"); _req(parent, I32, "parent")
+    _req(parent_repaired, U8, "parent_repaired"); _req(level_off, I32, "level_off")
+    _count("repair")
+    _lib.check(lib.st_repair_branches(_ptr(nodes), _ptr(row), _ptr(length), _ptr(parent), _ptr(parent_repaired), _ptr(level_off),
+                                      level_off.shape[0] - 1, _stream()), "st_repair_branches")

@@ -61,7 +61,7 @@ class Skeletonizer:
             for bid in range(cnb_h[c]):
                 ln = lens[bi]
                 branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o + 1:o + 1 + ln, :3], nodes[o + 1:o + 1 + ln, 3:4],
-                                               _flat=(store, o, ln))
+                                               _flat=(store, o, ln, False))
                 o += ln + 1
                 bi += 1
             skeletons.append(TreeSkeleton(c, branches))
