@@ -65,6 +65,11 @@ __device__ __forceinline__ bool elect_one_sync() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -251,9 +256,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                     const float v[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const uint32_t h = __float_as_uint(v[i]) & 0xFFFFE000u;
+                        // round-to-nearest split (unbiased; the tensor core would truncate): x = hi + lo exactly,
+                        // hi and lo both TF32-representable up to 2^-23 |x|
+                        const uint32_t h = to_tf32(v[i]);
                         hi[q * 4 + i] = h;
-                        lo[q * 4 + i] = __float_as_uint(v[i] - __uint_as_float(h));
+                        lo[q * 4 + i] = to_tf32(v[i] - __uint_as_float(h));
                     }
                 }
                 tmem_st16(ta, hi);
@@ -393,8 +400,8 @@ __global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, in
     int K = s * TC_KS + kk;
     int tap = K / cin, c = K % cin;
     float v = (tap < ntaps && n < cout) ? w[((size_t)tap * cin + c) * cout + n] : 0.f;
-    float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-    float lo = v - hi;
+    float hi = __uint_as_float(to_tf32(v));
+    float lo = __uint_as_float(to_tf32(v - hi));
     size_t pos = (size_t)(n >> 3) * 256 + (size_t)(kk >> 2) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
     float *tile = wprep + (size_t)s * 2 * npad * TC_KS;
     tile[pos] = hi;
