@@ -158,15 +158,16 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 }
 
 // ------------------------------------------------------------------------------------ SSSP
-// Pull-based asynchronous relaxation in a resident grid.  Every thread owns a few vertices and
-// polls a per-vertex "dirty" word; when it is set the vertex re-evaluates
-//     d[v] = min(d[v], min_u fl32(d[u] + w(u,v)))
-// with L2-coherent loads, and if d[v] dropped it publishes the value (store, fence) and marks its
-// neighbours dirty.  fl32(+) is monotone, so ANY schedule converges to the same least fixed point
-// (== fp32 Dijkstra); a shortest-path chain advances one hop per poll period (~1 us) instead of
-// one hop per grid-wide sweep.  Grid barriers only every SSSP_PASSES polls; the kernel stops after
-// a whole chunk in which no dirty word was consumed.
+// Push-based asynchronous relaxation in a resident grid.  Distances are non-negative floats, so their bit
+// patterns order like unsigned integers and  dist[u] = min(dist[u], fl32(dist[v] + w))  is one atomicMin.
+// fl32(+) is monotone, hence ANY schedule converges to the same least fixed point (== fp32 Dijkstra).
+// Every warp owns groups of 32 consecutive vertices and polls one "dirty" word per vertex.  A dirty vertex
+// is relaxed by the whole warp (lanes stride over its arcs); of the neighbours it improved, the closest one
+// is relaxed next BY THE SAME WARP (a shortest-path chain advances in ~2 L2 round trips per hop instead of
+// waiting for another warp's poll), the others are marked dirty for their owners.  Grid barriers only every
+// SSSP_PASSES polls; the kernel stops after a whole chunk in which no warp found work.
 constexpr int SSSP_PASSES = 64;
+constexpr int SSSP_MAXCHAIN = 256;
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -176,10 +177,7 @@ struct SsspCtl {
 };
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl) {
-    // Each warp owns groups of 32 consecutive vertices.  Lanes poll their own dirty word; every dirty
-    // vertex of the group is then relaxed by the WHOLE warp (lanes stride over its arcs), so one
-    // relaxation costs ~3 L2 round trips regardless of the degree.
+                                              const float *__restrict__ w, int n, unsigned *dist, int *dirty, SsspCtl *ctl) {
     unsigned phase = 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -197,23 +195,33 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
                 __threadfence();
                 consumed = true;
                 while (mask) {
-                    const int l = __ffs(mask) - 1;
+                    int cur = (g << 5) + (__ffs(mask) - 1);
                     mask &= mask - 1;
-                    const int vv = (g << 5) + l;
-                    const int b = __ldg(row_ptr + vv), e = __ldg(row_ptr + vv + 1);
-                    const float cur = __ldcg(dist + vv);
-                    float best = cur;
-                    for (int a = b + lane; a < e; a += 32)
-                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
-                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
-                    if (best < cur) {
-                        if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
-                        __syncwarp();
+                    for (int hop = 0; cur >= 0; ++hop) {
+                        if (hop == SSSP_MAXCHAIN) { if (lane == 0) atomicExch(dirty + cur, 1); break; }   // stay fair
+                        const float dv = __uint_as_float(__ldcg(dist + cur));
+                        const int b = __ldg(row_ptr + cur), e = __ldg(row_ptr + cur + 1);
+                        unsigned best_c = 0xFFFFFFFFu;
+                        int best_u = -1;
                         for (int a = b + lane; a < e; a += 32) {
                             const int u = __ldg(col + a);
-                            // u can only improve through vv if d[vv] + w < d[u]
-                            if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicExch(dirty + u, 1);
+                            const unsigned c = __float_as_uint(__fadd_rn(dv, __ldg(w + a)));
+                            const unsigned old = atomicMin(dist + u, c);
+                            if (c < old) {                      // this lane improved u: keep the closest, hand over the rest
+                                __threadfence();
+                                if (c < best_c) { if (best_u >= 0) atomicExch(dirty + best_u, 1); best_c = c; best_u = u; }
+                                else atomicExch(dirty + u, 1);
+                            }
                         }
+                        // closest improved neighbour over the warp continues the chain here
+                        unsigned long long key = ((unsigned long long)best_c << 32) | (unsigned)(best_u & 0x7FFFFFFF) | (best_u < 0 ? 0x80000000ull : 0ull);
+                        unsigned long long kmin = key;
+                        for (int o = 16; o; o >>= 1) {
+                            unsigned long long other = __shfl_xor_sync(0xffffffffu, kmin, o);
+                            kmin = other < kmin ? other : kmin;
+                        }
+                        if (best_u >= 0 && key != kmin) atomicExch(dirty + best_u, 1);
+                        cur = (kmin & 0x80000000ull) ? -1 : (int)(kmin & 0x7FFFFFFFull);
                     }
                 }
             }
@@ -233,8 +241,7 @@ __global__ void k_sssp_seed(const int32_t *__restrict__ row_ptr, const int32_t *
                             const int32_t *__restrict__ sources, int ns) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
-    int s = sources[i];
-    for (int a = row_ptr[s]; a < row_ptr[s + 1]; ++a) dirty[col[a]] = 1;
+    dirty[sources[i]] = 1;        // push-based: the sources start the relaxation
 }
 
 __global__ void k_sssp_init(float *dist, int n) {
@@ -308,7 +315,8 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     if (rc) return rc;
     if (blocks > (int)g) blocks = (int)g;
     int nn = (int)n;
-    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl};
+    unsigned *dist_bits = (unsigned *)dist;
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist_bits, (void *)&dirty, (void *)&ctl};
     ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
     k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
     ST_CHECK_LAUNCH();
