@@ -158,16 +158,18 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 }
 
 // ------------------------------------------------------------------------------------ SSSP
-// Push-based asynchronous relaxation in a resident grid.  Distances are non-negative floats, so their bit
-// patterns order like unsigned integers and  dist[u] = min(dist[u], fl32(dist[v] + w))  is one atomicMin.
-// fl32(+) is monotone, hence ANY schedule converges to the same least fixed point (== fp32 Dijkstra).
-// Every warp owns groups of 32 consecutive vertices and polls one "dirty" word per vertex.  A dirty vertex
-// is relaxed by the whole warp (lanes stride over its arcs); of the neighbours it improved, the closest one
-// is relaxed next BY THE SAME WARP (a shortest-path chain advances in ~2 L2 round trips per hop instead of
-// waiting for another warp's poll), the others are marked dirty for their owners.  Grid barriers only every
-// SSSP_PASSES polls; the kernel stops after a whole chunk in which no warp found work.
+// Pull-based asynchronous relaxation in a resident grid.  Every warp owns up to SSSP_G groups of 32
+// consecutive vertices and polls one change COUNTER per vertex (bumped by whoever lowers a neighbour); a
+// vertex whose counter moved re-evaluates
+//     d[v] = min(d[v], min_u fl32(d[u] + w(u,v)))
+// cooperatively (lanes stride over its arcs, L2-coherent loads), publishes an improvement (store, fence) and
+// bumps the counters of exactly those neighbours the new value can still improve, judged from the distances
+// it has just read (stale values only cause harmless extra wake-ups).  No flag clearing, no second read: a
+// shortest-path chain advances one hop per poll + one round trip.  fl32(+) is monotone, so ANY schedule
+// converges to the same least fixed point (== fp32 Dijkstra).  Grid barriers only every SSSP_PASSES polls;
+// the kernel stops after a whole chunk in which no counter moved.
 constexpr int SSSP_PASSES = 64;
-constexpr int SSSP_MAXCHAIN = 256;
+constexpr int SSSP_G = 4;
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -177,7 +179,79 @@ struct SsspCtl {
 };
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                              const float *__restrict__ w, int n, unsigned *dist, int *dirty, SsspCtl *ctl) {
+                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl) {
+    unsigned phase = 0;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ngroups = (n + 31) >> 5;
+    int seen[SSSP_G], rb[SSSP_G], re[SSSP_G];
+#pragma unroll
+    for (int k = 0; k < SSSP_G; ++k) {
+        const int v = ((w0 + k * nwarps) << 5) + lane;
+        seen[k] = 0;
+        rb[k] = v < n ? __ldg(row_ptr + v) : 0;
+        re[k] = v < n ? __ldg(row_ptr + v + 1) : 0;
+    }
+    for (unsigned chunk = 0;; ++chunk) {
+        bool consumed = false;
+        for (int pass = 0; pass < SSSP_PASSES; ++pass) {
+#pragma unroll
+            for (int k = 0; k < SSSP_G; ++k) {
+                const int g = w0 + k * nwarps;
+                if (g >= ngroups) continue;
+                const int v = (g << 5) + lane;
+                const int cnt = v < n ? __ldcg(dirty + v) : seen[k];
+                unsigned mask = __ballot_sync(0xffffffffu, cnt != seen[k]);
+                seen[k] = cnt;
+                if (!mask) continue;
+                __threadfence();          // counter observed -> the distance that caused it is visible
+                consumed = true;
+                while (mask) {
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int vv = (g << 5) + l;
+                    const int b = __shfl_sync(0xffffffffu, rb[k], l), e = __shfl_sync(0xffffffffu, re[k], l);
+                    const float cur = __ldcg(dist + vv);
+                    float best = cur;
+                    // first 64 arcs stay in registers for the wake-up test
+                    int u0 = -1, u1 = -1;
+                    float c0 = ST_INF, c1 = ST_INF, d0 = 0.f, d1 = 0.f, ww0 = 0.f, ww1 = 0.f;
+                    if (b + lane < e) { u0 = __ldg(col + b + lane); ww0 = __ldg(w + b + lane); d0 = __ldcg(dist + u0); c0 = __fadd_rn(d0, ww0); }
+                    if (b + 32 + lane < e) { u1 = __ldg(col + b + 32 + lane); ww1 = __ldg(w + b + 32 + lane); d1 = __ldcg(dist + u1); c1 = __fadd_rn(d1, ww1); }
+                    best = fminf(best, fminf(c0, c1));
+                    for (int a = b + 64 + lane; a < e; a += 32)
+                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (best < cur) {
+                        if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
+                        __syncwarp();
+                        // u can only improve through vv if d[vv] + w < d[u]
+                        if (u0 >= 0 && __fadd_rn(best, ww0) < d0) atomicAdd(dirty + u0, 1);
+                        if (u1 >= 0 && __fadd_rn(best, ww1) < d1) atomicAdd(dirty + u1, 1);
+                        for (int a = b + 64 + lane; a < e; a += 32) {
+                            const int u = __ldg(col + a);
+                            if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicAdd(dirty + u, 1);
+                        }
+                    }
+                }
+            }
+        }
+        if (__syncthreads_or(consumed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->changed[(chunk + 1) % 3] = 0;
+        grid_barrier(&ctl->barrier, phase);
+        unsigned any = *(volatile unsigned *)&ctl->changed[chunk % 3];
+        if (!any) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) ctl->chunks = chunk + 1;
+            break;
+        }
+    }
+}
+
+// fallback for graphs with more than SSSP_G * 32 vertices per resident warp: same relaxation, flag-clearing
+// variant in which a warp strides over arbitrarily many groups
+__global__ void __launch_bounds__(256) k_sssp_big(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                                  const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl) {
     unsigned phase = 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -195,33 +269,22 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
                 __threadfence();
                 consumed = true;
                 while (mask) {
-                    int cur = (g << 5) + (__ffs(mask) - 1);
+                    const int l = __ffs(mask) - 1;
                     mask &= mask - 1;
-                    for (int hop = 0; cur >= 0; ++hop) {
-                        if (hop == SSSP_MAXCHAIN) { if (lane == 0) atomicExch(dirty + cur, 1); break; }   // stay fair
-                        const float dv = __uint_as_float(__ldcg(dist + cur));
-                        const int b = __ldg(row_ptr + cur), e = __ldg(row_ptr + cur + 1);
-                        unsigned best_c = 0xFFFFFFFFu;
-                        int best_u = -1;
+                    const int vv = (g << 5) + l;
+                    const int b = __ldg(row_ptr + vv), e = __ldg(row_ptr + vv + 1);
+                    const float cur = __ldcg(dist + vv);
+                    float best = cur;
+                    for (int a = b + lane; a < e; a += 32)
+                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (best < cur) {
+                        if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
+                        __syncwarp();
                         for (int a = b + lane; a < e; a += 32) {
                             const int u = __ldg(col + a);
-                            const unsigned c = __float_as_uint(__fadd_rn(dv, __ldg(w + a)));
-                            const unsigned old = atomicMin(dist + u, c);
-                            if (c < old) {                      // this lane improved u: keep the closest, hand over the rest
-                                __threadfence();
-                                if (c < best_c) { if (best_u >= 0) atomicExch(dirty + best_u, 1); best_c = c; best_u = u; }
-                                else atomicExch(dirty + u, 1);
-                            }
+                            if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicExch(dirty + u, 1);
                         }
-                        // closest improved neighbour over the warp continues the chain here
-                        unsigned long long key = ((unsigned long long)best_c << 32) | (unsigned)(best_u & 0x7FFFFFFF) | (best_u < 0 ? 0x80000000ull : 0ull);
-                        unsigned long long kmin = key;
-                        for (int o = 16; o; o >>= 1) {
-                            unsigned long long other = __shfl_xor_sync(0xffffffffu, kmin, o);
-                            kmin = other < kmin ? other : kmin;
-                        }
-                        if (best_u >= 0 && key != kmin) atomicExch(dirty + best_u, 1);
-                        cur = (kmin & 0x80000000ull) ? -1 : (int)(kmin & 0x7FFFFFFFull);
                     }
                 }
             }
@@ -241,7 +304,8 @@ __global__ void k_sssp_seed(const int32_t *__restrict__ row_ptr, const int32_t *
                             const int32_t *__restrict__ sources, int ns) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns) return;
-    dirty[sources[i]] = 1;        // push-based: the sources start the relaxation
+    int s = sources[i];
+    for (int a = row_ptr[s]; a < row_ptr[s + 1]; ++a) atomicAdd(dirty + col[a], 1);   // wake the sources' neighbours
 }
 
 __global__ void k_sssp_init(float *dist, int n) {
@@ -315,9 +379,10 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     if (rc) return rc;
     if (blocks > (int)g) blocks = (int)g;
     int nn = (int)n;
-    unsigned *dist_bits = (unsigned *)dist;
-    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist_bits, (void *)&dirty, (void *)&ctl};
-    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl};
+    // counter variant when every resident warp can own its vertices in registers, flag variant otherwise
+    const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n;
+    ST_CHECK_CUDA(cudaLaunchCooperativeKernel(small ? (const void *)k_sssp : (const void *)k_sssp_big, dim3(blocks), dim3(256), args, 0, s));
     k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
     ST_CHECK_LAUNCH();
     k_sssp_finish<<<g, 256, 0, s>>>(dist, (int)n);
