@@ -170,6 +170,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 // the kernel stops after a whole chunk in which no counter moved.
 constexpr int SSSP_PASSES = 64;
 constexpr int SSSP_G = 4;
+constexpr int SSSP_LANE_MODE = 4;     // woken vertices per group from which lane-parallel evaluation wins
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -207,6 +208,26 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
                 if (!mask) continue;
                 __threadfence();          // counter observed -> the distance that caused it is visible
                 consumed = true;
+                if (__popc(mask) >= SSSP_LANE_MODE) {
+                    // many vertices of the group woke up at once (a correction wave): one vertex per lane, all
+                    // lanes in parallel, instead of 32 cooperative evaluations back to back
+                    if ((mask >> lane) & 1u) {
+                        const int b = rb[k], e = re[k];
+                        const float cur = __ldcg(dist + v);
+                        float best = cur;
+                        for (int a = b; a < e; ++a) best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                        if (best < cur) {
+                            __stcg(dist + v, best);
+                            __threadfence();
+                            for (int a = b; a < e; ++a) {
+                                const int u = __ldg(col + a);
+                                if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicAdd(dirty + u, 1);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
                 while (mask) {
                     const int l = __ffs(mask) - 1;
                     mask &= mask - 1;

@@ -50,11 +50,28 @@ stats = (C.c_ulonglong * 8)()
 lib = _lib.load()
 lib.st_debug_sample_stats.argtypes = [C.c_void_p]
 lib.st_debug_sample_stats(stats)
+# depth of the predecessor tree (hops) by pointer jumping on the host
+import numpy as np
+last = pipe.skeletonizer.last
+try:
+    pred = last["pred"].cpu().numpy().astype(np.int64)
+    off = last["comp_off"].cpu().numpy().astype(np.int64)
+    basev = np.repeat(off[:-1], off[1:] - off[:-1])
+    jump = np.where(pred >= 0, pred + basev, -1)
+    depth = (jump >= 0).astype(np.int64)
+    for _ in range(20):
+        has = jump >= 0
+        j = np.maximum(jump, 0)
+        depth = depth + np.where(has, depth[j], 0)
+        jump = np.where(has, jump[j], jump)
+    max_depth = int(depth.max())
+except Exception as exc:
+    max_depth = repr(exc)
 names = ["find", "trace", "claim", "resolve", "finish"]
 cyc = {n: stats[i] for i, n in enumerate(names)}
 last = pipe.skeletonizer.last
 print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec, "min_med_max_ms": spread,
                   "sample_tree_cycles": cyc, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
-                  "cluster_size": stats[7], "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
+                  "cluster_size": stats[7], "sssp_tree_max_depth_hops": max_depth, "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
                   "skeleton_vertices": int(last["order"].shape[0]), "edges": int(last["edges"].shape[0]),
                   "voxels": int(pipe.model_inference.last_batch.feats.shape[0])}, indent=1))
