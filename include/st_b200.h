@@ -197,7 +197,9 @@ int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, in
                  int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host,
                  void *workspace, size_t workspace_bytes, void *stream);
 int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n,
-            const int32_t *sources, int32_t n_sources, float *dist, int32_t *pred,
+            const int32_t *sources, int32_t n_sources,
+            float delta /* threshold step of the distance-ordered schedule; any value gives the same result; <=0: default */,
+            float *dist, int32_t *pred,
             int32_t *sweeps_host, void *ctl_workspace /* 256 + 4n B, device */, void *stream);
 /* pred_graph + second sssp             smart_tree/skeleton/shortest_path.py:46-55
  * tree_dist[v] = tree_dist[pred[v]] + ||p_v - p_pred(v)||, 0 at roots (pred<0 & reachable

@@ -12,6 +12,7 @@ I32, I64, F32, U8 = torch.int32, torch.int64, torch.float32, torch.uint8
 
 # ---- instrumentation (bench.py): number of libst_b200 kernels launched, optional per-conv CUDA events
 LAUNCHES = 0
+LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
@@ -329,7 +330,7 @@ def csr_build(edges, weights, n):
     return row_ptr, col[:na.value], w[:na.value]
 
 
-def sssp(row_ptr, col, w, n, sources, want_sweeps=False):
+def sssp(row_ptr, col, w, n, sources, want_sweeps=False, delta=0.0):
     lib = _lib.load()
     _req(sources, I32, "sources")
     dev = row_ptr.device
@@ -338,8 +339,10 @@ def sssp(row_ptr, col, w, n, sources, want_sweeps=False):
     ctl = torch.empty(64 + n, dtype=I32, device=dev)
     sweeps = C.c_int32(0)
     _count("sssp")
-    _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], _ptr(dist), _ptr(pred),
+    _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], float(delta), _ptr(dist), _ptr(pred),
                            C.byref(sweeps) if want_sweeps else None, _ptr(ctl), _stream()), "st_sssp")
+    global LAST_SSSP_CTL
+    LAST_SSSP_CTL = ctl
     return (dist, pred, sweeps.value) if want_sweeps else (dist, pred)
 
 

@@ -5,6 +5,7 @@ st_sample_tree launch with one CTA per component, instead of the reference's Pyt
 components with cudf/pandas round trips."""
 from __future__ import annotations
 
+import os
 from typing import List
 
 import torch
@@ -124,7 +125,9 @@ class Skeletonizer:
                 src = torch.full((ncomp,), m, dtype=torch.int64, device=dev).scatter_reduce(0, comp_of, cand, "amin")
         # skeletonize.py:73-78
         with section("skel.sssp"):
-            dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous())
+            # threshold step of the distance-ordered SSSP schedule: a few typical edge lengths (any value is exact)
+            delta = float(os.environ.get("ST_SSSP_DELTA", 2.5 * self.min_connection_length))
+            dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous(), delta=delta)
         with section("skel.tree_dist"):
             is_root = torch.zeros(m, dtype=torch.uint8, device=dev)
             is_root[src] = 1

@@ -67,11 +67,14 @@ try:
     max_depth = int(depth.max())
 except Exception as exc:
     max_depth = repr(exc)
+sst = (C.c_uint * 5)()
+lib.st_debug_sssp_stats.argtypes = [C.c_void_p, C.c_void_p]
+lib.st_debug_sssp_stats(C.c_void_p(ops.LAST_SSSP_CTL.data_ptr()), sst)
 names = ["find", "trace", "claim", "resolve", "finish"]
 cyc = {n: stats[i] for i, n in enumerate(names)}
 last = pipe.skeletonizer.last
 print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec, "min_med_max_ms": spread,
                   "sample_tree_cycles": cyc, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
-                  "cluster_size": stats[7], "sssp_tree_max_depth_hops": max_depth, "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
+                  "cluster_size": stats[7], "sssp_chunks_evals_improvements_x_lanemode": list(sst), "sssp_tree_max_depth_hops": max_depth, "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
                   "skeleton_vertices": int(last["order"].shape[0]), "edges": int(last["edges"].shape[0]),
                   "voxels": int(pipe.model_inference.last_batch.feats.shape[0])}, indent=1))
