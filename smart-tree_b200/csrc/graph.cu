@@ -216,29 +216,43 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
                 const int cnt = v < n ? __ldcg(dirty + v) : seen[k];
                 const bool woke = cnt != seen[k] || pend[k] <= T;
                 seen[k] = cnt;
-                if (!__any_sync(0xffffffffu, woke)) continue;
+                unsigned mask = __ballot_sync(0xffffffffu, woke);
+                if (!mask) continue;
                 __threadfence();          // counter observed -> the distance that caused it is visible
-                if (woke) {
-                    const int b = rb[k], e = re[k];
-                    const float cur = __ldcg(dist + v);
+                if (woke) pend[k] = ST_INF;
+                while (mask) {            // woken vertices one after the other, each relaxed by the whole warp
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int vv = (g << 5) + l;
+                    const int b = __shfl_sync(0xffffffffu, rb[k], l), e = __shfl_sync(0xffffffffu, re[k], l);
+                    const float cur = __ldcg(dist + vv);
                     float best = cur;
-                    for (int a = b; a < e; ++a) best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
-                    pend[k] = ST_INF;
+                    // first 64 arcs stay in registers for the wake-up test
+                    int u0 = -1, u1 = -1;
+                    float c0 = ST_INF, c1 = ST_INF, d0 = 0.f, d1 = 0.f, ww0 = 0.f, ww1 = 0.f;
+                    if (b + lane < e) { u0 = __ldg(col + b + lane); ww0 = __ldg(w + b + lane); d0 = __ldcg(dist + u0); c0 = __fadd_rn(d0, ww0); }
+                    if (b + 32 + lane < e) { u1 = __ldg(col + b + 32 + lane); ww1 = __ldg(w + b + 32 + lane); d1 = __ldcg(dist + u1); c1 = __fadd_rn(d1, ww1); }
+                    best = fminf(best, fminf(c0, c1));
+                    for (int a = b + 64 + lane; a < e; a += 32)
+                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
                     if (best < cur) {
                         if (best <= T) {
                             consumed = true;
-                            __stcg(dist + v, best);
-                            __threadfence();
-                            for (int a = b; a < e; ++a) {
+                            if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
+                            __syncwarp();
+                            // u can only improve through vv if d[vv] + w < d[u]
+                            if (u0 >= 0 && __fadd_rn(best, ww0) < d0) atomicAdd(dirty + u0, 1);
+                            if (u1 >= 0 && __fadd_rn(best, ww1) < d1) atomicAdd(dirty + u1, 1);
+                            for (int a = b + 64 + lane; a < e; a += 32) {
                                 const int u = __ldg(col + a);
                                 if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicAdd(dirty + u, 1);
                             }
-                        } else {
+                        } else if (lane == l) {
                             pend[k] = best;       // parked until the threshold reaches it (or a neighbour wakes it again)
                         }
                     }
                 }
-                __syncwarp();
             }
         }
         // smallest parked candidate of this thread -> grid minimum (non-negative floats order like their bits)
