@@ -170,7 +170,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 // the kernel stops after a whole chunk in which no counter moved.
 constexpr int SSSP_PASSES = 64;
 constexpr int SSSP_G = 4;
-constexpr int SSSP_NF_PASSES = 8;     // polls between barriers in the near-far kernel (~ hops per threshold step)
+constexpr int SSSP_NF_PASSES = 32;    // polls between barriers in the near-far kernel (~ hops per threshold step)
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -182,7 +182,7 @@ struct SsspCtl {
 };
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta) {
+                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta, int npass) {
     // Distance-ordered ("near-far") discipline on top of the asynchronous relaxation: an improvement is only
     // accepted -- written and propagated -- while it lies below the current threshold T; larger candidates
     // stay parked in a register of the owning lane until T reaches them.  Vertices are therefore settled in
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
     float T = delta;
     for (unsigned chunk = 0;; ++chunk) {
         bool consumed = false;
-        for (int pass = 0; pass < SSSP_NF_PASSES; ++pass) {
+        for (int pass = 0; pass < npass; ++pass) {
 #pragma unroll
             for (int k = 0; k < SSSP_G; ++k) {
                 const int g = w0 + k * nwarps;
@@ -412,7 +412,9 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     if (blocks > (int)g) blocks = (int)g;
     int nn = (int)n;
     if (!(delta > 0.f)) delta = 0.05f;
-    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta};
+    int npass = SSSP_NF_PASSES;
+    if (const char *e = getenv("ST_SSSP_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 1024) npass = v; }
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta, (void *)&npass};
     // near-far counter variant when every resident warp can own its vertices in registers, flag variant otherwise
     const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n;
     ST_CHECK_CUDA(cudaLaunchCooperativeKernel(small ? (const void *)k_sssp : (const void *)k_sssp_big, dim3(blocks), dim3(256), args, 0, s));
