@@ -191,8 +191,11 @@ def run_b200(args):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
+        per_step = []
         for _ in range(steps):
+            ts = time.perf_counter()
             _, sk = step(resident)
+            per_step.append((time.perf_counter() - ts) * 1e3)     # the step ends with its result on the host
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -201,7 +204,7 @@ def run_b200(args):
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), sk
+        return float(t[0]), float(t[1]), sk, per_step
 
     for _ in range(args.warmup):
         step(True)
@@ -209,10 +212,10 @@ def run_b200(args):
     if rank == 0:
         clocks.start()
     launches0 = ops.LAUNCHES
-    dev_ms, wall_ms, sk = timed(True, args.steps)
+    dev_ms, wall_ms, sk, steps_res = timed(True, args.steps)
     launches = ops.LAUNCHES - launches0
     stage_t = dict(pipe.timings)
-    e2e_ms, e2e_wall_ms, sk2 = timed(False, args.steps)
+    e2e_ms, e2e_wall_ms, sk2, steps_e2e = timed(False, args.steps)
     clk = clocks.stop() if rank == 0 else None
     # the device timeline includes host gaps (the step has host sync points), so device-event time == step time
     ms_per_step = max(dev_ms, wall_ms) / args.steps
@@ -281,6 +284,7 @@ def run_b200(args):
                         "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "stages_ms": {k: v * 1e3 for k, v in stage_t.items()},
+                "step_ms": {"resident": [round(v, 2) for v in steps_res], "host_buffers": [round(v, 2) for v in steps_e2e]},
                 "result": {"skeletons": len(sk.skeletons), "branches": sum(len(s.branches) for s in sk.skeletons),
                            "voxels": int(bb.feats.shape[0]) if bb is not None else 0}}
         print(json.dumps(line), flush=True)
