@@ -15,7 +15,8 @@ What it restates (numpy / scipy / torch-CPU, fp32 like the reference):
                       Skeletonizer.forward, prune / repair / smooth
                       -- /root/reference/smart_tree/{pipeline.py,dataset/dataset.py,...}
 
-PARITY STATUS: **parity unpinned at the third-party boundary.**  The reference holds no
+PARITY STATUS: **parity unpinned at the third-party boundary, pinned for the reference's own glue** (the
+reference's Python runs unmodified on oracle/fake_thirdparty.py -> tests/golden/refglue_*.npz).  The reference holds no
 golden vectors, known-answer tests or fixtures for this path and the
 libraries that carry its arithmetic (spconv, FRNN, cugraph 23.02) are neither vendored
 nor installable here, so the oracle's spconv/FRNN/cugraph semantics are restated from
