@@ -88,7 +88,7 @@ def test_cuda_forward_matches_reference_model_code(tag):
     eng = SmartTreeEngine(sd, device="cuda")
     out = eng.forward(torch.from_numpy(g["feats"]).cuda(), torch.from_numpy(g["coords"]).cuda())
     for k in ("radius", "direction", "class_l"):
-        e = np.abs(out[k].cpu().numpy() - g[k]) / np.abs(g[k]).max()
+        e = np.abs(out[k].cpu().numpy() - g[k]) / max(np.abs(g[k]).max(), 1e-12)     # peach's class head is identically 0
         assert np.quantile(e, 0.999) < 1e-3 and e.max() < (1e-2 if k == "direction" else 1e-3), (k, e.max())
 
 
