@@ -193,8 +193,9 @@ int st_connected_components(const int32_t *edges, int64_t n_edges, int64_t n, in
  * d[v] = min_u fl32(d[u]+w); pred[v] = lowest u with fl32(d[u]+w)==d[v] (-1 at sources and
  * unreachable, dist FLT_MAX there).  st_csr_build makes the CSR from an edge list.        */
 size_t st_csr_workspace_bytes(int64_t n, int64_t n_edges);
-int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, int64_t n,
-                 int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host,
+int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges,
+                 const int32_t *vertex_map /* optional: edge endpoints are renumbered through it, < 0 drops the edge */,
+                 int64_t n, int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host,
                  void *workspace, size_t workspace_bytes, void *stream);
 int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n,
             const int32_t *sources, int32_t n_sources,

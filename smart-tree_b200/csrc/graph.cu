@@ -84,20 +84,23 @@ extern "C" int st_connected_components(const int32_t *edges, int64_t n_edges, in
 }
 
 // ------------------------------------------------------------------------------------ CSR
-__global__ void k_csr_degree(const int32_t *__restrict__ edges, int64_t ne, int32_t *deg) {
+__global__ void k_csr_degree(const int32_t *__restrict__ edges, int64_t ne, int32_t *deg, const int32_t *__restrict__ vmap) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
     int u = edges[2 * e], v = edges[2 * e + 1];
+    if (vmap) { u = __ldg(vmap + u); v = __ldg(vmap + v); if (u < 0 || v < 0) return; }
     if (u == v) return;
     atomicAdd(deg + u, 1);
     atomicAdd(deg + v, 1);
 }
 
 __global__ void k_csr_fill(const int32_t *__restrict__ edges, const float *__restrict__ weights, int64_t ne,
-                           const int32_t *__restrict__ row_ptr, int32_t *cursor, int32_t *__restrict__ col, float *__restrict__ w) {
+                           const int32_t *__restrict__ row_ptr, int32_t *cursor, int32_t *__restrict__ col, float *__restrict__ w,
+                           const int32_t *__restrict__ vmap) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
     int u = edges[2 * e], v = edges[2 * e + 1];
+    if (vmap) { u = __ldg(vmap + u); v = __ldg(vmap + v); if (u < 0 || v < 0) return; }
     if (u == v) return;
     float ww = weights[e];
     int pu = row_ptr[u] + atomicAdd(cursor + u, 1);
@@ -112,8 +115,9 @@ extern "C" size_t st_csr_workspace_bytes(int64_t n, int64_t n_edges) {
     return align_up(scan) + 2 * align_up((n + 1) * 4) + 1024;
 }
 
-extern "C" int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, int64_t n, int32_t *row_ptr,
-                            int32_t *col, float *w, int64_t *n_arcs_host, void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges, const int32_t *vertex_map, int64_t n,
+                            int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host, void *workspace, size_t workspace_bytes,
+                            void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     *n_arcs_host = 0;
     if (n == 0) return ST_OK;
@@ -127,12 +131,12 @@ extern "C" int st_csr_build(const int32_t *edges, const float *weights, int64_t 
     ST_CHECK_CUDA(cudaMemsetAsync(deg, 0, (n + 1) * 4, s));
     ST_CHECK_CUDA(cudaMemsetAsync(cursor, 0, (n + 1) * 4, s));
     if (n_edges) {
-        k_csr_degree<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, deg);
+        k_csr_degree<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, deg, vertex_map);
         ST_CHECK_LAUNCH();
     }
     ST_CHECK_CUDA(cub::DeviceScan::ExclusiveSum(scan_ws, scan_bytes, deg, row_ptr, (int)(n + 1), s));
     if (n_edges) {
-        k_csr_fill<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, weights, n_edges, row_ptr, cursor, col, w);
+        k_csr_fill<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, weights, n_edges, row_ptr, cursor, col, w, vertex_map);
         ST_CHECK_LAUNCH();
     }
     int32_t arcs = 0;

@@ -14,10 +14,15 @@ from .branch import BranchSkeleton
 
 
 class NodeStore:
-    """Shared node array of a skeletoniser call: host [R,4] (xyz, radius) + its device twin."""
+    """Shared node array of a skeletoniser call: host [R,4] (xyz, radius) + a device twin made on demand."""
 
-    def __init__(self, host, dev):
-        self.host, self.dev = host, dev
+    def __init__(self, host, dev=None):
+        self.host, self._dev = host, dev
+
+    def device_twin(self, device):
+        if self._dev is None or self._dev.device != torch.device(device):
+            self._dev = self.host.to(device)
+        return self._dev
 
 
 @dataclass
@@ -72,8 +77,8 @@ class TreeSkeleton:
         if not order:
             return
         store = self._flat_store()
-        if store is not None and store.dev.device == dev:
-            return self._repair_flat(order, store)
+        if store is not None and dev.type == "cuda":
+            return self._repair_flat(order, store, dev)
         for run in order:
             pts = torch.stack([br.xyz[0] for br in run])
             pa = [ids[br.parent_id] for br in run]
@@ -87,13 +92,12 @@ class TreeSkeleton:
                 br.xyz = torch.cat((conn[k:k + 1], br.xyz))
                 br.radii = torch.cat((br.radii[[0]], br.radii))
 
-    def _repair_flat(self, order, store):
+    def _repair_flat(self, order, store, dev):
         """repair() on the shared node array in ONE kernel launch (st_repair_branches): branches sorted by
         tree depth, a block barrier between depths so that children see repaired parents, connection
         points written into the spare rows on the device and copied to the host once."""
         from .. import ops
-        nd = store.dev
-        dev = nd.device
+        nd = store.device_twin(dev)
         ids = self.branches
         listed = [br for run in order for br in run]
         in_order = {id(br) for br in listed}

@@ -315,9 +315,13 @@ def connected_components(edges, n):
     return label, size
 
 
-def csr_build(edges, weights, n):
+def csr_build(edges, weights, n, vertex_map=None):
+    """CSR over both directions of every edge (self loops dropped).  With vertex_map [n_old] i32 the endpoints
+    are renumbered on the fly (entries < 0 drop the edge) and n is the number of NEW vertices."""
     lib = _lib.load()
     _req(edges, I32, "edges"); _req(weights, F32, "weights")
+    if vertex_map is not None:
+        _req(vertex_map, I32, "vertex_map")
     ne, dev = edges.shape[0], edges.device
     row_ptr = torch.empty(n + 1, dtype=I32, device=dev)
     col = torch.empty(max(2 * ne, 1), dtype=I32, device=dev)
@@ -325,7 +329,7 @@ def csr_build(edges, weights, n):
     ws = _ws(lib.st_csr_workspace_bytes(n, ne), dev)
     na = C.c_int64(0)
     _count("csr")
-    _lib.check(lib.st_csr_build(_ptr(edges), _ptr(weights), ne, n, _ptr(row_ptr), _ptr(col), _ptr(w), C.byref(na), _ptr(ws),
+    _lib.check(lib.st_csr_build(_ptr(edges), _ptr(weights), ne, _ptr(vertex_map), n, _ptr(row_ptr), _ptr(col), _ptr(w), C.byref(na), _ptr(ws),
                                 ws.numel(), _stream()), "st_csr_build")
     return row_ptr, col[:na.value], w[:na.value]
 

@@ -31,39 +31,46 @@ class Skeletonizer:
 
     @staticmethod
     def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp) -> List[TreeSkeleton]:
-        """One gather + one device->host copy for the node coordinates / radii of every branch of
-        every component.  Nodes live in one shared [P+B,4] array (xyz, radius) with a spare row in
-        front of each branch, pre-filled with the branch's first node: `repair` later only has to
-        write the connection point there (its radius is the first node's radius by definition)."""
+        """Two device->host copies in total: the per-component counts, then ONE packed buffer holding the path
+        vertex ids, branch lengths, parent ids and the gathered node coordinates / radii of every branch of
+        every component.  Nodes end up in one shared [P+B,4] host array (xyz, radius) with a spare row in
+        front of each branch, pre-filled with the branch's first node: `repair` later only has to write the
+        connection point there (its radius is the first node's radius by definition)."""
+        import numpy as np
+
         from ..data_types.branch import BranchSkeleton
         from ..data_types.tree import NodeStore
-        counts = torch.stack([cnb, cnp]).cpu()
-        cnb_h, cnp_h, off_h = counts[0].tolist(), counts[1].tolist(), comp_off.cpu().tolist()
-        dev = path.device
-        if sum(cnb_h) == 0:
+        hdr = torch.cat([cnb, cnp, comp_off.int()]).cpu().numpy()
+        cnb_h, cnp_h, off_h = hdr[:ncomp], hdr[ncomp:2 * ncomp], hdr[2 * ncomp:]
+        nb, npth = int(cnb_h.sum()), int(cnp_h.sum())
+        if nb == 0:
             return [TreeSkeleton(c, {}) for c in range(ncomp)]
-        seg = torch.cat([torch.arange(off_h[c], off_h[c] + cnp_h[c], device=dev) for c in range(ncomp)])
-        bseg = torch.cat([torch.arange(off_h[c], off_h[c] + cnb_h[c], device=dev) for c in range(ncomp)])
-        base = torch.repeat_interleave(comp_off[:-1], torch.tensor(cnp_h, device=dev))
-        gidx = path[seg].long() + base
-        lens_d = blen[bseg].long()
-        starts = torch.cumsum(lens_d, 0) - lens_d
-        rep = torch.ones_like(gidx)
-        rep[starts] = 2                                          # first node of every branch twice
-        gidx = torch.repeat_interleave(gidx, rep)
-        nodes_dev = torch.cat([sub_medial[gidx], sub_radius[gidx].unsqueeze(1)], 1).contiguous()
-        nodes = nodes_dev.cpu()
-        lens = lens_d.cpu().tolist()
-        pars = bpar[bseg].cpu().tolist()
-        store = NodeStore(nodes, nodes_dev)
-        skeletons, o, bi = [], 0, 0
+        dev = path.device
+        pseg = torch.cat([path[off_h[c]:off_h[c] + cnp_h[c]] for c in range(ncomp)]) if ncomp > 1 else path[:npth]
+        lseg = torch.cat([blen[off_h[c]:off_h[c] + cnb_h[c]] for c in range(ncomp)]) if ncomp > 1 else blen[:nb]
+        qseg = torch.cat([bpar[off_h[c]:off_h[c] + cnb_h[c]] for c in range(ncomp)]) if ncomp > 1 else bpar[:nb]
+        gidx = pseg.long()
+        if ncomp > 1:
+            gidx = gidx + torch.from_numpy(np.repeat(off_h[:ncomp].astype(np.int64), cnp_h)).to(dev)
+        payload = torch.cat([lseg, qseg, sub_medial[gidx].reshape(-1).view(torch.int32), sub_radius[gidx].view(torch.int32)]).cpu().numpy()
+        lens, pars = payload[:nb].astype(np.int64), payload[nb:2 * nb]
+        xyz = payload[2 * nb:2 * nb + 3 * npth].view(np.float32).reshape(npth, 3)
+        rad = payload[2 * nb + 3 * npth:].view(np.float32)
+        # host node array with one spare row per branch (copy of the branch's first node)
+        start = np.cumsum(lens) - lens
+        rep = np.ones(npth, np.int64)
+        rep[start] = 2
+        src = np.repeat(np.arange(npth), rep)
+        nodes = torch.from_numpy(np.concatenate([xyz[src], rad[src, None]], 1))
+        store = NodeStore(nodes, None)
+        row = start + np.arange(nb)                   # spare row of every branch
+        skeletons, bi = [], 0
         for c in range(ncomp):
             branches = {}
-            for bid in range(cnb_h[c]):
-                ln = lens[bi]
+            for bid in range(int(cnb_h[c])):
+                o, ln = int(row[bi]), int(lens[bi])
                 branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o + 1:o + 1 + ln, :3], nodes[o + 1:o + 1 + ln, 3:4],
                                                _flat=(store, o, ln, False))
-                o += ln + 1
                 bi += 1
             skeletons.append(TreeSkeleton(c, branches))
         return skeletons
@@ -105,12 +112,8 @@ class Skeletonizer:
             comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
             comp_off[1:] = torch.cumsum(sizes, 0)
             comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
-            # induced edges, renumbered (skeletonize.py:60-71)
-            e = graph.edges.long()
-            esel = new_id[e[:, 0]] >= 0
-            sub_edges = new_id[e[esel]].contiguous()
-            sub_w = graph.edge_weights[esel].contiguous()
-            row_ptr, col, w = ops.csr_build(sub_edges, sub_w, m)
+            # induced edges, renumbered (skeletonize.py:60-71): done inside the CSR build through new_id
+            row_ptr, col, w = ops.csr_build(graph.edges, graph.edge_weights, m, vertex_map=new_id)
             sub_xyz = cloud.xyz[order]
             sub_medial = medial[order].contiguous()
             sub_radius = radius[order].contiguous()
