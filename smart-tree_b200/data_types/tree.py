@@ -119,10 +119,19 @@ class TreeSkeleton:
         rows = torch.tensor([br._flat[1] for br in listed], dtype=torch.int64)
         store.host[rows] = nd[rows.to(dev)].cpu()
         host = store.host
-        for br in listed:
+        # views of the repaired branches (spare row included) from two split calls
+        listed_sorted = sorted(listed, key=lambda b: b._flat[1])
+        sizes, prev = [], 0
+        for br in listed_sorted:
+            _, o, n, _ = br._flat
+            sizes += [o - prev, n + 1]
+            prev = o + n + 1
+        sizes.append(host.shape[0] - prev)
+        xv = host[:, :3].split(sizes)[1::2]
+        rv = host[:, 3:4].split(sizes)[1::2]
+        for br, x, r in zip(listed_sorted, xv, rv):
             st, o, n, _ = br._flat
-            br.xyz = host[o:o + n + 1, :3]
-            br.radii = host[o:o + n + 1, 3:4]
+            br.xyz, br.radii = x, r
             br._flat = (st, o, n, True)
 
     def branch_lengths(self):
@@ -205,10 +214,8 @@ class TreeSkeleton:
         hi = torch.minimum(rows + h, torch.repeat_interleave(last, cnt))
         cs = torch.cat([torch.zeros(1, dtype=torch.float64), store.host[:, 3].double().cumsum(0)])
         out = ((cs[hi + 1] - cs[lo]) / kernel_size).float()
-        o = 0
-        for b, n in zip(todo, cnt.tolist()):
-            b.radii = out[o:o + n]
-            o += n
+        for b, r in zip(todo, out.split(cnt.tolist())):
+            b.radii = r
             b._flat = None                       # radii no longer live in the shared array
 
     @property

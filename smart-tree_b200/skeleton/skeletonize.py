@@ -63,14 +63,17 @@ class Skeletonizer:
         src = np.repeat(np.arange(npth), rep)
         nodes = torch.from_numpy(np.concatenate([xyz[src], rad[src, None]], 1))
         store = NodeStore(nodes, None)
-        row = start + np.arange(nb)                   # spare row of every branch
+        row = (start + np.arange(nb)).tolist()        # spare row of every branch
+        lens_l, pars_l = lens.tolist(), pars.tolist()
+        # all per-branch views from two split calls (per-branch slicing costs ~10 us of Python each)
+        sizes = [v for ln in lens_l for v in (1, ln)]
+        xyz_views = nodes[:, :3].split(sizes)[1::2]
+        rad_views = nodes[:, 3:4].split(sizes)[1::2]
         skeletons, bi = [], 0
         for c in range(ncomp):
             branches = {}
             for bid in range(int(cnb_h[c])):
-                o, ln = int(row[bi]), int(lens[bi])
-                branches[bid] = BranchSkeleton(bid, int(pars[bi]), nodes[o + 1:o + 1 + ln, :3], nodes[o + 1:o + 1 + ln, 3:4],
-                                               _flat=(store, o, ln, False))
+                branches[bid] = BranchSkeleton(bid, pars_l[bi], xyz_views[bi], rad_views[bi], _flat=(store, row[bi], lens_l[bi], False))
                 bi += 1
             skeletons.append(TreeSkeleton(c, branches))
         return skeletons
