@@ -50,7 +50,9 @@ class Cloud:
     # cloud.py:72-95 -- boolean mask or index tensor; every field is gathered
     def filter(self, mask) -> "Cloud":
         mask = mask.to(self.xyz.device)
-        return self._map(lambda t: t[mask])
+        if mask.dtype == torch.bool:          # one compaction of the mask, then plain row gathers for every field
+            mask = mask.nonzero().squeeze(1)
+        return self._map(lambda t: t.index_select(0, mask))
 
     # cloud.py:97-103
     def filter_by_class(self, classes) -> "Cloud":

@@ -51,10 +51,11 @@ class ModelInference:
             levels = self.model.build_levels(bb.coords)
         with section("infer.unet"):
             preds = self.model.forward(bb.feats[:, :3], bb.coords, levels=levels, fused_outputs=True)
-        lc = Cloud(xyz=bb.feats[:, :3], rgb=bb.feats[:, 3:6], medial_vector=preds["medial_vector"],
-                   class_l=preds["class_idx"].long().unsqueeze(1))
-        self.last_preds = preds
-        return lc.filter(bb.mask) if return_masked else lc
+        with section("infer.tail"):
+            lc = Cloud(xyz=bb.feats[:, :3], rgb=bb.feats[:, 3:6], medial_vector=preds["medial_vector"],
+                       class_l=preds["class_idx"].long().unsqueeze(1))
+            self.last_preds = preds
+            return lc.filter(bb.mask) if return_masked else lc
 
     @staticmethod
     def from_cfg(cfg):

@@ -45,13 +45,15 @@ class Pipeline:
         t = {}
         sync = (lambda: torch.cuda.synchronize(self.device)) if self.device.type == "cuda" else (lambda: None)
         t0 = time.perf_counter()
-        cloud = cloud.to_device(self.device)
-        cloud = self.preprocessing(cloud)
+        with section("pipe.preprocess"):
+            cloud = cloud.to_device(self.device)
+            cloud = self.preprocessing(cloud)
         sync(); t["preprocess"] = time.perf_counter() - t0; t0 = time.perf_counter()
         lc: Cloud = self.model_inference.forward(cloud).to_device(self.device)      # pipeline.py:63
         sync(); t["inference"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.labelled_cloud = lc
-        branch_cloud = lc.filter_by_class(self.branch_classes)                      # pipeline.py:68
+        with section("pipe.filter_class"):
+            branch_cloud = lc.filter_by_class(self.branch_classes)                  # pipeline.py:68
         skeleton = self.skeletonizer.forward(branch_cloud)                          # pipeline.py:71
         sync(); t["skeleton"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.post_process(skeleton)

@@ -89,8 +89,9 @@ class Skeletonizer:
         n = len(cloud)
         if n == 0:
             return DisjointTreeSkeleton([])
-        medial = cloud.medial_pts.contiguous()
-        radius = cloud.radius.contiguous()
+        with section("skel.medial"):
+            medial = cloud.medial_pts.contiguous()
+            radius = cloud.radius.contiguous()
         # skeletonize.py:37-41 (the clamp applies to graph building only, quirk C-21)
         with section("skel.nn_graph"):
             graph: Graph = nn_graph(medial, radius.clamp(min=self.min_connection_length), K=self.K)
