@@ -50,11 +50,35 @@ class SingleTreeInference:
         self.point_index, self.point_block = pidx, pblk
         self.block_lo, self.block_hi = lo, hi
 
+    MAX_BLOCKS_PER_LAUNCH = 16384      # the batch index has 15 bits in the packed voxel key
+
+    def voxelize_chunks(self):
+        """Yields one BlockBatch per <= 16384 blocks (block indices in `coords` are local to the chunk).  A tree
+        is a single chunk; plots tiled into tens of thousands of 64^3 blocks are cut into several forwards, which
+        changes nothing numerically (eval-mode BatchNorm: blocks do not interact)."""
+        nb = self.block_centres.shape[0]
+        if nb <= self.MAX_BLOCKS_PER_LAUNCH:
+            yield self._voxelize()
+            return
+        dev = self.cloud.xyz.device
+        for b0 in range(0, nb, self.MAX_BLOCKS_PER_LAUNCH):
+            b1 = min(b0 + self.MAX_BLOCKS_PER_LAUNCH, nb)
+            lo_hi = torch.searchsorted(self.point_block, torch.tensor([b0, b1], dtype=self.point_block.dtype, device=dev)).tolist()
+            sub = SingleTreeInference.__new__(SingleTreeInference)
+            sub.__dict__.update(self.__dict__)
+            sub.point_index = self.point_index[lo_hi[0]:lo_hi[1]]
+            sub.point_block = (self.point_block[lo_hi[0]:lo_hi[1]] - b0).contiguous()
+            sub.block_centres, sub.block_lo, sub.block_hi = self.block_centres[b0:b1], self.block_lo[b0:b1], self.block_hi[b0:b1]
+            yield sub._voxelize()
+
     def voxelize_all(self) -> BlockBatch:
         """Every block through the PointToVoxel restatement in one launch (dataset.py:192-226)."""
+        assert self.block_centres.shape[0] <= self.MAX_BLOCKS_PER_LAUNCH, "use voxelize_chunks() for this many blocks"
+        return self._voxelize()
+
+    def _voxelize(self) -> BlockBatch:
         xyz, rgb = self.cloud.xyz, self.cloud.rgb
         dev = xyz.device
-        nb = self.block_centres.shape[0]
         if rgb is None:
             rgb = torch.zeros_like(xyz)
         pts = torch.cat((xyz, rgb), 1)[self.point_index].contiguous().float()

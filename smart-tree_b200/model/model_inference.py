@@ -41,21 +41,27 @@ class ModelInference:
             cloud = cloud.to_device(self.device)
         with section("infer.blocks"):
             ds = load_dataloader(cloud, self.voxel_size, self.block_size, self.buffer_size, self.num_workers, self.batch_size)
-        with section("infer.voxelize"):
-            bb = ds.voxelize_all()
-        self.last_batch = bb
-        if bb.feats.shape[0] == 0:
+        clouds, all_preds = [], []
+        for bb in ds.voxelize_chunks():
+            self.last_batch = bb
+            if bb.feats.shape[0] == 0:
+                continue
+            with section("infer.levels"):
+                levels = self.model.build_levels(bb.coords)
+            with section("infer.unet"):
+                preds = self.model.forward(bb.feats[:, :3], bb.coords, levels=levels, fused_outputs=True)
+            with section("infer.tail"):
+                lc = Cloud(xyz=bb.feats[:, :3], rgb=bb.feats[:, 3:6], medial_vector=preds["medial_vector"],
+                           class_l=preds["class_idx"].long().unsqueeze(1))
+                self.last_preds = preds
+                clouds.append(lc.filter(bb.mask) if return_masked else lc)
+        if not clouds:
             z = torch.zeros(0, 3, device=cloud.xyz.device)
             return Cloud(xyz=z, rgb=z.clone(), medial_vector=z.clone(), class_l=torch.zeros(0, 1, dtype=torch.int64, device=z.device))
-        with section("infer.levels"):
-            levels = self.model.build_levels(bb.coords)
-        with section("infer.unet"):
-            preds = self.model.forward(bb.feats[:, :3], bb.coords, levels=levels, fused_outputs=True)
-        with section("infer.tail"):
-            lc = Cloud(xyz=bb.feats[:, :3], rgb=bb.feats[:, 3:6], medial_vector=preds["medial_vector"],
-                       class_l=preds["class_idx"].long().unsqueeze(1))
-            self.last_preds = preds
-            return lc.filter(bb.mask) if return_masked else lc
+        if len(clouds) == 1:
+            return clouds[0]
+        return Cloud(xyz=torch.cat([c.xyz for c in clouds]), rgb=torch.cat([c.rgb for c in clouds]),
+                     medial_vector=torch.cat([c.medial_vector for c in clouds]), class_l=torch.cat([c.class_l for c in clouds]))
 
     @staticmethod
     def from_cfg(cfg):

@@ -459,6 +459,34 @@ def test_points_to_tubes_matches_oracle():
         np.testing.assert_allclose(vec[q].cpu().numpy(), v, rtol=1e-5, atol=1e-6)
 
 
+# ------------------------------------------------------------------ the other BASELINE configs, at oracle-sized scale
+@pytest.mark.parametrize("weights,voxel,block,chunk", [("peach-forest-65", 0.005, 4, None),      # C4: 5 mm voxels, peach
+                                                       ("noble-elevator-58", 0.01, 0.64, None),   # C5: 64^3-voxel blocks
+                                                       ("noble-elevator-58", 0.01, 0.64, 7)])     # C5 cut into several forwards
+def test_inference_other_configs_match_oracle(weights, voxel, block, chunk):
+    from smart_tree_b200.data_types.cloud import Cloud
+    from smart_tree_b200.dataset import dataset as ds_mod
+    from smart_tree_b200.model.model_inference import ModelInference
+    tr = _synth(6, 20000)
+    xyz = P.centre_cloud(tr.xyz)[::2 if block == 4 else 1]
+    if block != 4:                                                      # a 1.6 m slab keeps the CPU oracle fast
+        xyz = xyz[xyz[:, 1] < 1.6]
+    sd = _load(weights)
+    old = ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH
+    try:
+        if chunk:
+            ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH = chunk
+        mi = ModelInference(None, os.path.join(WEIGHTS, f"{weights}_model_weights.pt"), voxel, block, 0.4, device=torch.device(DEV))
+        lc = mi.forward(Cloud(xyz=_t(xyz), rgb=torch.zeros(len(xyz), 3, device=DEV)))
+    finally:
+        ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH = old
+    lab = P.infer(U.to_numpy_params(sd), xyz, np.zeros_like(xyz), voxel, block, 0.4)
+    assert np.array_equal(lc.xyz.cpu().numpy(), lab["xyz"])              # same voxels, same (block-major) order
+    mv = lc.medial_vector.cpu().numpy()
+    assert np.abs(mv - lab["medial_vector"]).max() <= 1e-3 * np.abs(lab["medial_vector"]).max()
+    assert (lc.class_l.cpu().numpy().reshape(-1) == lab["class_l"]).mean() > 0.999
+
+
 # ------------------------------------------------------------------ end to end through the reference-shaped API
 def test_pipeline_end_to_end_matches_oracle():
     from smart_tree_b200.config import instantiate, load_config
