@@ -47,7 +47,7 @@ def workload_config(args, world):
     return {"workload": "noble-elevator-58 UNet inference + skeleton, 1M-point synthetic tube tree per GPU, 1cm voxels "
                         "(BASELINE.json configs[1])",
             "points_per_gpu": args.points, "voxel_size": args.voxel, "block_size": 4, "buffer_size": 0.4, "K": 16,
-            "weights": "noble-elevator-58", "trees": world, "parallelism": f"tree-sharded x{world}",
+            "weights": "noble-elevator-58", "trees": world, "tree_seed": 0, "parallelism": f"tree-sharded x{world}, NCCL all-gather of packed skeletons",
             "l2": "256 MiB scratch write between timed iterations (inputs < 126 MB L2)"}
 
 
@@ -164,7 +164,8 @@ def run_b200(args):
     pipe = Pipeline(AugmentationPipeline([CentreCloud()]), mi, Skeletonizer(16, 0.02, 32, device=dev), repair_skeletons=True,
                     smooth_skeletons=True, smooth_kernel_size=11, prune_skeletons=True, min_skeleton_radius=0.01,
                     min_skeleton_length=0.02, device=dev)
-    tr = synth.make_tree(rank, args.points)
+    # weak scaling: every GPU gets the SAME workload tree (seed 0), so per-GPU work is exactly fixed as N grows
+    tr = synth.make_tree(0, args.points)
     h_xyz = torch.from_numpy(tr.xyz).pin_memory()
     h_rgb = torch.from_numpy(tr.rgb).pin_memory()
     d_cloud = Cloud(xyz=h_xyz.to(dev), rgb=h_rgb.to(dev))

@@ -34,19 +34,18 @@ def shard(items: List, rank: int, world: int) -> List:
 
 
 def pack_skeletons(skeletons: List[TreeSkeleton], unit_ids: List[int]):
-    """-> (float32 payload [P,4] = xyz,radius per node ; int64 header [B,4] = unit, skeleton, branch id, parent, + counts)."""
-    nodes, meta = [], []
+    """-> float32 node table [P,4] (xyz, radius) and int64 branch table [B,5] = (unit, skeleton id, branch id,
+    parent id, node count): the reference's npz skeleton schema (util/file.py:73-93) plus a unit column."""
+    xyz, rad, meta = [], [], []
     for unit, sk in zip(unit_ids, skeletons):
-        a = skeleton_arrays(sk)
-        if len(a["branch_id"]) == 0:
-            continue
-        nodes.append(np.concatenate([a["skeleton_xyz"].astype(np.float32), a["skeleton_radii"].astype(np.float32).reshape(-1, 1)], 1))
-        m = np.stack([np.full(len(a["branch_id"]), unit), np.full(len(a["branch_id"]), int(a["tree_id"])), a["branch_id"],
-                      a["branch_parent_id"], a["branch_num_elements"]], 1).astype(np.int64)
-        meta.append(m)
-    nodes = np.concatenate(nodes) if nodes else np.zeros((0, 4), np.float32)
-    meta = np.concatenate(meta) if meta else np.zeros((0, 5), np.int64)
-    return torch.from_numpy(nodes), torch.from_numpy(meta)
+        for b in sk.branches.values():
+            xyz.append(b.xyz)
+            rad.append(b.radii.reshape(-1))
+            meta.append((unit, sk._id, b._id, b.parent_id, b.xyz.shape[0]))
+    if not meta:
+        return torch.zeros((0, 4), dtype=torch.float32), torch.zeros((0, 5), dtype=torch.int64)
+    nodes = torch.cat([torch.cat(xyz).float(), torch.cat(rad).float().unsqueeze(1)], 1)
+    return nodes, torch.tensor(meta, dtype=torch.int64)
 
 
 def unpack_skeletons(nodes: torch.Tensor, meta: torch.Tensor):
@@ -65,16 +64,51 @@ def unpack_skeletons(nodes: torch.Tensor, meta: torch.Tensor):
     return out
 
 
-def gather_skeletons(local: List[DisjointTreeSkeleton], unit_ids: List[int], device=None):
-    """All-gather every rank's skeletons (NCCL on GPUs, gloo on CPU).  `local[i]` is the result for
-    global unit `unit_ids[i]`.  Returns {(unit, skeleton id): TreeSkeleton} on every rank."""
+class GatheredSkeletons:
+    """Result of the gather: every rank's packed tables, materialised into TreeSkeleton objects on demand
+    (building thousands of Python objects on every rank is not part of the exchange)."""
+
+    def __init__(self, tables):
+        self.tables = tables                      # list of (nodes [P,4], meta [B,5]) per rank, CPU tensors
+
+    @property
+    def n_branches(self):
+        return int(sum(m.shape[0] for _, m in self.tables))
+
+    @property
+    def n_nodes(self):
+        return int(sum(n.shape[0] for n, _ in self.tables))
+
+    def skeletons(self):
+        out = {}
+        for nodes, meta in self.tables:
+            out.update(unpack_skeletons(nodes, meta))
+        return out
+
+    # dict-like access for callers that want the objects
+    def __getitem__(self, key):
+        return self.skeletons()[key]
+
+    def keys(self):
+        return self.skeletons().keys()
+
+    def items(self):
+        return self.skeletons().items()
+
+    def __len__(self):
+        return len({(int(u), int(s)) for _, m in self.tables for u, s in m[:, :2].tolist()})
+
+
+def gather_skeletons(local: List[DisjointTreeSkeleton], unit_ids: List[int], device=None) -> GatheredSkeletons:
+    """All-gather every rank's skeletons (NCCL on GPUs, gloo on CPU).  `local[i]` is the result for global
+    unit `unit_ids[i]`.  Every rank receives every rank's packed tables."""
     sk, units = [], []
     for d, u in zip(local, unit_ids):
         for s in d.skeletons:
             sk.append(s); units.append(u)
     nodes, meta = pack_skeletons(sk, units)
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return unpack_skeletons(nodes, meta)
+        return GatheredSkeletons([(nodes, meta)])
     world = dist.get_world_size()
     dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu"))
     counts = torch.tensor([nodes.shape[0], meta.shape[0]], dtype=torch.int64, device=dev)
@@ -82,13 +116,11 @@ def gather_skeletons(local: List[DisjointTreeSkeleton], unit_ids: List[int], dev
     dist.all_gather(all_counts, counts)
     all_counts = torch.stack(all_counts).cpu()
     max_n, max_m = int(all_counts[:, 0].max()), int(all_counts[:, 1].max())
+    # one padded payload per rank: node table followed by the branch table viewed as float32 pairs
     nbuf = torch.zeros((max(max_n, 1), 4), dtype=torch.float32, device=dev); nbuf[:nodes.shape[0]] = nodes.to(dev)
     mbuf = torch.zeros((max(max_m, 1), 5), dtype=torch.int64, device=dev); mbuf[:meta.shape[0]] = meta.to(dev)
-    ng = [torch.zeros_like(nbuf) for _ in range(world)]
-    mg = [torch.zeros_like(mbuf) for _ in range(world)]
+    ng = [torch.empty_like(nbuf) for _ in range(world)]
+    mg = [torch.empty_like(mbuf) for _ in range(world)]
     dist.all_gather(ng, nbuf)
     dist.all_gather(mg, mbuf)
-    out = {}
-    for r in range(world):
-        out.update(unpack_skeletons(ng[r][:int(all_counts[r, 0])], mg[r][:int(all_counts[r, 1])]))
-    return out
+    return GatheredSkeletons([(ng[r][:int(all_counts[r, 0])].cpu(), mg[r][:int(all_counts[r, 1])].cpu()) for r in range(world)])

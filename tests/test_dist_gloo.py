@@ -38,6 +38,7 @@ def _worker(rank, world, port, out):
     if rank == 1:
         local[-1] = DisjointTreeSkeleton([])                         # a unit with no skeleton at all
     merged = stdist.gather_skeletons(local, units, device=torch.device("cpu"))
+    assert merged.n_branches > 0 and len(merged) == len(merged.skeletons())
     out[rank] = {k: (len(v.branches), float(sum(b.xyz.sum() + b.radii.sum() for b in v.branches.values()))) for k, v in merged.items()}
     dist.destroy_process_group()
 
