@@ -152,7 +152,7 @@ struct TcArgs {
 };
 
 template <int CIN>
-__global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // smem: sb x { B_hi | B_lo } (npad*128 B each).  TMEM: [0, npad) accumulator, then TC_STAGES x 64 A columns.
     const int b_tile_bytes = a.npad * TC_KS * 4;
@@ -236,12 +236,11 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
             const bool row_ok = row < a.n_out;
             prefetch_map(tile + gridDim.x, buf ^ 1);
             // software pipeline: feature rows two stages ahead of the stores (covers the tail latency of the
-            // ~1000 gathers a stage consists of; the slowest one gates the whole CTA)
-            float4 xc[4], xn[4], xm[4];
-            load_rows(buf, 0, xc);
-            if (a.nstages > 1) load_rows(buf, 1, xn);
-            for (int s = 0; s < a.nstages; ++s, ++g) {
-                if (s + 2 < a.nstages) load_rows(buf, s + 2, xm);
+            // ~1000 gathers a stage consists of; the slowest one gates the whole CTA).  The three register
+            // sets rotate by unrolling the stage loop three times -- no register-to-register copies.
+            float4 x0[4], x1[4], x2[4];
+            auto do_stage = [&](int s, float4 (&cur)[4], float4 (&fill)[4]) {
+                if (s + 2 < a.nstages) load_rows(buf, s + 2, fill);
                 if (g >= TC_STAGES) {
                     if (lane == 0) mbar_wait(&a_empty[st], pe);
                     __syncwarp();
@@ -253,14 +252,13 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float v[4] = {xc[q].x, xc[q].y, xc[q].z, xc[q].w};
+                    const float v[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        // round-to-nearest split (unbiased; the tensor core would truncate): x = hi + lo exactly,
-                        // hi and lo both TF32-representable up to 2^-23 |x|
-                        const uint32_t h = to_tf32(v[i]);
+                        // x = hi + lo exactly; hi carries the top 10 mantissa bits (what kind::tf32 reads), lo the rest
+                        const uint32_t h = __float_as_uint(v[i]) & 0xFFFFE000u;
                         hi[q * 4 + i] = h;
-                        lo[q * 4 + i] = to_tf32(v[i] - __uint_as_float(h));
+                        lo[q * 4 + i] = __float_as_uint(v[i] - __uint_as_float(h));
                     }
                 }
                 tmem_st16(ta, hi);
@@ -270,9 +268,15 @@ __global__ void __launch_bounds__(TC_THREADS) k_conv_tc(TcArgs a) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&a_full[st]);      // one arrival per producer warp
                 if (tid == 0) TC_TRACE(1, g);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { xc[q] = xn[q]; xn[q] = xm[q]; }
+                ++g;
                 if (++st == TC_STAGES) { st = 0; pe ^= 1; }
+            };
+            load_rows(buf, 0, x0);
+            if (a.nstages > 1) load_rows(buf, 1, x1);
+            for (int s = 0; s < a.nstages; s += 3) {
+                do_stage(s, x0, x2);
+                if (s + 1 < a.nstages) do_stage(s + 1, x1, x0);
+                if (s + 2 < a.nstages) do_stage(s + 2, x2, x1);
             }
             // ---------------- epilogue of this tile ----------------
             mbar_wait(&accum_bar, tile_iter & 1);
@@ -400,8 +404,8 @@ __global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, in
     int K = s * TC_KS + kk;
     int tap = K / cin, c = K % cin;
     float v = (tap < ntaps && n < cout) ? w[((size_t)tap * cin + c) * cout + n] : 0.f;
-    float hi = __uint_as_float(to_tf32(v));
-    float lo = __uint_as_float(to_tf32(v - hi));
+    float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    float lo = v - hi;
     size_t pos = (size_t)(n >> 3) * 256 + (size_t)(kk >> 2) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
     float *tile = wprep + (size_t)s * 2 * npad * TC_KS;
     tile[pos] = hi;
