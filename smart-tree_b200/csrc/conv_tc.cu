@@ -162,7 +162,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
     __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar;
     __shared__ uint32_t tmem_base_sh;
     __shared__ int smap[2][TC_MAXTAPS][TC_M];     // gather-map entries of the current / next tile (28 KB)
-    __shared__ float4 stage_buf[8 * 128];          // per-warp transpose staging (16 KB)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t tmem_need = (uint32_t)a.npad + TC_STAGES * TC_A_COLS;
@@ -215,25 +214,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");      // producers only
         };
-        // Gather mapping: 4 consecutive lanes read the 4 chunks (64 contiguous bytes) of one row and a warp
-        // instruction covers 8 rows, so a scattered LDG.128 touches 8 cache lines instead of 32 -- the L1
-        // wavefront count, not the byte count, is what bounded the first version of this kernel.  The rows a
-        // thread loads (lr + 8j) are not the row it owns in TMEM (= its lane), so the chunks are transposed
-        // through a 2 KB per-warp staging area in shared memory (XOR-swizzled, conflict-free both ways).
-        const int lr = lane >> 2, lc = lane & 3;
         auto load_rows = [&](int buf, int s, float4 (&x)[4]) {
             int t0, c0;
             taps_of(s, t0, c0);
-            const int tap = CIN == 8 ? t0 + (lc >> 1) : t0;
-            const int c = CIN == 8 ? (lc & 1) * 4 : c0 + lc * 4;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int rl = 32 * (warp & 3) + lr + 8 * j;
-                const int jm = tap < TC_MAXTAPS ? smap[buf][tap][rl] : -1;
-                x[j] = jm >= 0 ? __ldg((const float4 *)(a.in + (size_t)jm * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = 0; q < 4; ++q) {
+                const int tap = CIN == 8 ? t0 + (q >> 1) : t0;
+                const int j = tap < TC_MAXTAPS ? smap[buf][tap][rloc] : -1;
+                const int c = CIN == 8 ? (q & 1) * 4 : c0 + q * 4;
+                x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        float4 *const stg = stage_buf + warp * 128;     // 32 rows x 4 chunks of 16 bytes
         int g = 0, st = 0;                            // global stage counter, ring position
         uint32_t pe = 1;                              // parity of the previous use of A stage `st`
         int tile_iter = 0;
@@ -258,21 +249,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 if (tid == 0) TC_TRACE(0, g);
                 // TMEM address of this thread's 16 columns of stage st: lanes 32*(warp&3).., columns a_col0 + st*64 + half*16
                 const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + a_col0 + (uint32_t)st * TC_A_COLS + (uint32_t)half * 16;
-                // transpose: rows lr+8j / chunk lc  ->  own row (lane) / chunks 0..3
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int r = lr + 8 * j;
-                    stg[r * 4 + (lc ^ ((r >> 1) & 3))] = cur[j];
-                }
-                __syncwarp();
-                float4 own[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) own[q] = stg[lane * 4 + (q ^ ((lane >> 1) & 3))];
-                __syncwarp();
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    const float v[4] = {own[q].x, own[q].y, own[q].z, own[q].w};
+                    const float v[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         // x = hi + lo exactly; hi carries the top 10 mantissa bits (what kind::tf32 reads), lo the rest
