@@ -108,6 +108,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
                  ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
                    "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
+// 16x256b.x2: thread t = 4*g + q writes {r0,r1 | r4,r5} to lane g, columns {2q,2q+1 | 8+2q,8+2q+1} and
+// {r2,r3 | r6,r7} to lane g+8, same columns (layout measured with tools/tmem_probe.cu)
+__device__ __forceinline__ void tmem_st_quad(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // descriptor words: lo = (addr >> 4) | LBO(128 B) << 16 ; hi = SBO(1024 B) | version 1 << 14
 __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); }
@@ -214,15 +220,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             asm volatile("cp.async.wait_group 0;" ::: "memory");
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PRODUCERS) : "memory");      // producers only
         };
+        // Gather: a QUAD of lanes reads 64 contiguous bytes of one feature row, so a warp-wide load touches
+        // 8 cache lines instead of 32 (the L1 data stage serialises per line: it was the busiest unit with
+        // one lane per row).  Thread 4*gq + q fetches chunk q of rows gq, gq+8, gq+16, gq+24 of its warp's
+        // 32-row quadrant -- exactly the fragment tcgen05.st.16x256b scatters into TMEM lanes.
+        const int gq = lane >> 2, q4 = lane & 3;
+        const int rq = 32 * (warp & 3) + gq;
         auto load_rows = [&](int buf, int s, float4 (&x)[4]) {
             int t0, c0;
             taps_of(s, t0, c0);
+            const int tap = CIN == 8 ? t0 + (q4 >> 1) : t0;
+            const int c = CIN == 8 ? (q4 & 1) * 4 : c0 + q4 * 4;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int tap = CIN == 8 ? t0 + (q >> 1) : t0;
-                const int j = tap < TC_MAXTAPS ? smap[buf][tap][rloc] : -1;
-                const int c = CIN == 8 ? (q & 1) * 4 : c0 + q * 4;
-                x[q] = j >= 0 ? __ldg((const float4 *)(a.in + (size_t)j * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) {
+                const int src = tap < TC_MAXTAPS ? smap[buf][tap][rq + 8 * j] : -1;
+                x[j] = src >= 0 ? __ldg((const float4 *)(a.in + (size_t)src * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
         int g = 0, st = 0;                            // global stage counter, ring position
@@ -249,20 +261,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 if (tid == 0) TC_TRACE(0, g);
                 // TMEM address of this thread's 16 columns of stage st: lanes 32*(warp&3).., columns a_col0 + st*64 + half*16
                 const uint32_t ta = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + a_col0 + (uint32_t)st * TC_A_COLS + (uint32_t)half * 16;
-                uint32_t hi[16], lo[16];
+                // x = hi + lo exactly; hi carries the top 10 mantissa bits (what kind::tf32 reads), lo the rest
+                auto split = [](float v, uint32_t &h, uint32_t &l) {
+                    h = __float_as_uint(v) & 0xFFFFE000u;
+                    l = __float_as_uint(v - __uint_as_float(h));
+                };
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float v[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        // x = hi + lo exactly; hi carries the top 10 mantissa bits (what kind::tf32 reads), lo the rest
-                        const uint32_t h = __float_as_uint(v[i]) & 0xFFFFE000u;
-                        hi[q * 4 + i] = h;
-                        lo[q * 4 + i] = __float_as_uint(v[i] - __uint_as_float(h));
-                    }
+                for (int p = 0; p < 2; ++p) {             // lanes +0..15 (rows gq, gq+8) then +16..31
+                    const float4 u = cur[2 * p], w = cur[2 * p + 1];
+                    uint32_t hi[8], lo[8];
+                    split(u.x, hi[0], lo[0]); split(u.y, hi[1], lo[1]); split(w.x, hi[2], lo[2]); split(w.y, hi[3], lo[3]);
+                    split(u.z, hi[4], lo[4]); split(u.w, hi[5], lo[5]); split(w.z, hi[6], lo[6]); split(w.w, hi[7], lo[7]);
+                    tmem_st_quad(ta + ((uint32_t)(16 * p) << 16), hi);
+                    tmem_st_quad(ta + ((uint32_t)(16 * p) << 16) + TC_KS, lo);
                 }
-                tmem_st16(ta, hi);
-                tmem_st16(ta + TC_KS, lo);
                 tmem_st_wait();
                 tc_fence_before();        // order the TMEM writes before the arrive that hands them to the MMA thread
                 __syncwarp();
@@ -401,7 +413,10 @@ __global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, in
     int s = (int)(idx / (npad * TC_KS));
     int rem = (int)(idx % (npad * TC_KS));
     int n = rem / TC_KS, kk = rem % TC_KS;
-    int K = s * TC_KS + kk;
+    // TMEM column kk of a stage holds logical K element 16*(kk/16) + 4*q + m, where the quad fragment puts
+    // (q, m) at column 2q+m (m < 2) or 8+2q+(m-2) of its 16-column half (see load_rows / tmem_st_quad)
+    const int cc = kk & 15, q = (cc & 7) >> 1, m = (cc & 1) + ((cc >> 3) << 1);
+    int K = s * TC_KS + (kk & 16) + 4 * q + m;
     int tap = K / cin, c = K % cin;
     float v = (tap < ntaps && n < cout) ? w[((size_t)tap * cin + c) * cout + n] : 0.f;
     float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);

@@ -94,8 +94,9 @@ def build_levels(coords: torch.Tensor, depth: int, morton: bool = False) -> List
 class SmartTreeEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = None):
         import os
-        # "auto": tensor cores (tcgen05) where they win on B200 -- every 3x3x3 layer with >= 16 output
-        # channels; the 8-channel layers are gather-issue bound and stay on the FMA kernel
+        # "auto": tensor cores (tcgen05) where they win on B200 -- every 3x3x3 layer with >= 16 input or
+        # output channels; the 8 -> 8 layers are bound by the L1 line-visit rate either way (tools/conv_micro.py:
+        # 85 us fma vs 87 us tc) and stay on the FMA kernel
         conv_impl = conv_impl or os.environ.get("ST_CONV_IMPL", "auto")
         sd = {k: v.detach().cpu() for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
         self.device = torch.device(device)
@@ -165,7 +166,7 @@ class SmartTreeEngine:
     # ---- execution
     def _conv(self, x, layer: ConvLayer, nbr, n_out, relu, out=None, residual=None, in2=None, w2=None):
         taps, cin, cout = layer.w.shape
-        use_tc = (self.conv_impl == "tc" or (self.conv_impl == "auto" and cout >= 16)) and taps > 1 and ops.conv_tc_supported(taps, cin, cout)
+        use_tc = (self.conv_impl == "tc" or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and taps > 1 and ops.conv_tc_supported(taps, cin, cout)
         return ops.conv_gather(x, nbr, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2,
                                out=out, relu=relu, impl="tc" if use_tc else "fma", weight_tc=layer.tc_weights() if use_tc else None)
 
