@@ -247,6 +247,27 @@ int st_repair_branches(float *nodes, const int32_t *row, const int32_t *len, con
                        const uint8_t *parent_repaired, const int32_t *level_off, int32_t n_levels,
                        void *stream);
 
+/* ------------------------------------------------------------------ K12 skeleton finishing, all components, one launch
+ * replaces the branch assembly of sample_tree   smart_tree/skeleton/path.py:118-129
+ *          TreeSkeleton.prune / repair / smooth smart_tree/data_types/tree.py:94-121, 73-92, 123-134
+ *          (DisjointTreeSkeleton.prune touches the first skeleton only, tree.py:164-168)
+ * Inputs are st_sample_tree's outputs (segment-local) plus the component-grouped medial points / radii.
+ * out (int32 words, 16-byte aligned, st_finish_skeletons_out_ints(n) words):
+ *   header[4]   = { B = total branches, R = total node rows (= path vertices + B), 0, 0 }
+ *   bmeta[B][4] = { spare row index, node count, parent branch id (component-local), flags }
+ *                 flags: 1 = kept by prune, 2 = spare row holds the repair connection point, 4 = smoothed
+ *   nodes[R][4] = float (x, y, z, raw radius); branch b owns rows row+1 .. row+len, `row` is its spare row
+ *   smooth[R]   = float radius after the box filter (== raw radius where the branch was not smoothed)
+ * Components appear in order; branches in emission order (= branch id).  smooth_kernel: 0 = off, else odd.
+ * depth_workspace: n int32.                                                                             */
+size_t st_finish_skeletons_out_ints(int64_t n);
+int st_finish_skeletons(const float *medial_pts, const float *radii, const int32_t *comp_off,
+                        int32_t n_comp, int64_t n, const int32_t *path_vertices,
+                        const int32_t *branch_len, const int32_t *branch_parent,
+                        const int32_t *comp_n_branches, const int32_t *comp_n_path, int prune_first,
+                        float min_radius, float min_length, int repair, int smooth_kernel,
+                        int32_t *depth_workspace, int32_t *out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -61,6 +61,8 @@ SIGNATURES = {
     "st_sample_tree": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "st_repair_branches": (C.c_int, [_p, _p, _p, _p, _p, _p, _i32, _p]),
     "st_points_to_tubes": (C.c_int, [_p, _i64, _p, _p, _p, _p, _p, _p, _p, _p, _p]),
+    "st_finish_skeletons_out_ints": (C.c_size_t, [_i64]),
+    "st_finish_skeletons": (C.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _p, _p, _p, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, _p, _p, _p]),
 }
 
 

@@ -14,6 +14,7 @@ constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 
 // debug counters of the last launch's block 0 (cycles per phase, iterations, path vertices)
 __device__ unsigned long long g_st_stats[8];
+__device__ int g_st_iter[1024][4];    // per iteration of block 0: route length, R, cycles of the claim phase, cycles of the iteration
 
 __global__ void k_st_init(const int32_t *__restrict__ pred, const float *__restrict__ tree_dist, int n, float *distw,
                           uint8_t *alloc, int32_t *branch_id, unsigned long long *best, const int32_t *__restrict__ comp_off,
@@ -60,7 +61,7 @@ struct SampleArgs {
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered
 // 0 .. RW*RW-1 around the vertex's own cell, so a short path still spreads over every warp of the cluster.
-constexpr int PATH_SMEM = 2048;    // path vertices whose position is staged in shared memory per iteration
+constexpr int PATH_SMEM = 1536;    // path vertices whose position is staged in shared memory per iteration
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered 0 .. RW*RW-1
 // around the vertex's own cell, so a short path still spreads over every warp of the cluster.  Every
@@ -87,6 +88,101 @@ __device__ __forceinline__ void claim_task(const SampleArgs &a, int base, int nc
         unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
         unsigned long long old = atomicMin(a.best + gi, key);
         if (old == BEST_NONE) a.touched[base + atomicAdd(touch_cnt, 1)] = gi;
+    }
+}
+
+// ---- claim with a neighbour pre-filter -----------------------------------------------------------------
+// A point usually lies within r of dozens of consecutive path vertices but only its NEAREST one (smallest
+// (d2 bits, path position) key) decides it.  A (point, vertex jj) pair whose key is beaten by one of the
+// path neighbours jj-2 .. jj+2 can never be that minimum, so it is dropped after four extra distance
+// evaluations; ~1 pair in 20 survives.  Survivors of a SHORT route (whole path in shared memory) are
+// compacted into a per-warp queue and settled on the spot by a full scan of the path -- no atomics, no
+// second pass; survivors of a long route race the 64-bit atomicMin and are settled by the resolve pass.
+constexpr int SCAN_PATH = 512;
+constexpr int QUEUE_LEN = 64;
+
+__device__ __forceinline__ unsigned long long claim_key(float4 q, float4 o, unsigned pos) {
+    return ((unsigned long long)__float_as_uint(dist2_exact(q.x, q.y, q.z, o.x, o.y, o.z)) << 32) | pos;
+}
+
+// lanes < count each settle one queued (sorted position, path index) pair
+__device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s_path, int len, const int2 *queue, int first, int count,
+                                            int lane, int bid) {
+    if (lane >= count) return;
+    const int2 e = queue[first + lane];
+    const float4 q = __ldg(a.sorted + e.x);
+    const float4 p = s_path[e.y];
+    const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - e.y);
+    bool own = true;
+    for (int j2 = 0; j2 < len; ++j2) own = own && !(claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key);
+    if (own && sqrtf(d2) < p.w) {
+        const int gi = __float_as_int(q.w);
+        a.distw[gi] = -1.f;
+        a.alloc[gi] = 1;
+        if (bid >= 0) a.branch_id[gi] = bid;
+    }
+}
+
+template <bool SHORT>
+__device__ __forceinline__ void claim_row(const SampleArgs &a, int base, int nc, const float4 *s_path, int jj, int len, int row, int R,
+                                          float r, float r2, int lane, int bid, int32_t *touch_cnt, int2 *queue, int &qn) {
+    const Grid &g = a.g;
+    const float4 p = s_path[jj];
+    const float rr = r * 1.0001f + 1e-7f;
+    const int RW = 2 * R + 1;
+    const int cz = cell_coord(p.z, g.oz, g.inv_h, g.nz) + row / RW - R;
+    const int cy = cell_coord(p.y, g.oy, g.inv_h, g.ny) + row % RW - R;
+    if (cz < cell_coord(p.z - rr, g.oz, g.inv_h, g.nz) || cz > cell_coord(p.z + rr, g.oz, g.inv_h, g.nz)) return;
+    if (cy < cell_coord(p.y - rr, g.oy, g.inv_h, g.ny) || cy > cell_coord(p.y + rr, g.oy, g.inv_h, g.ny)) return;
+    const int x0 = cell_coord(p.x - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(p.x + rr, g.ox, g.inv_h, g.nx);
+    const int rowc = (cz * g.ny + cy) * g.nx;
+    const int beg = __ldg(a.cell_start + rowc + x0), end = __ldg(a.cell_start + rowc + x1 + 1);
+    if (beg >= end) return;
+    const unsigned pos = (unsigned)(len - 1 - jj);
+    const int lim = len < PATH_SMEM ? len : PATH_SMEM;
+    float4 nb[4];
+    bool has[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int j2 = jj + (k < 2 ? k - 2 : k - 1);
+        has[k] = j2 >= 0 && j2 < lim;
+        nb[k] = has[k] ? s_path[j2] : p;
+    }
+    const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    float4 qnext = beg + lane < end ? __ldg(a.sorted + beg + lane) : none;
+    for (int t0 = beg; t0 < end; t0 += 32) {
+        const float4 q = qnext;
+        qnext = t0 + 32 + lane < end ? __ldg(a.sorted + t0 + 32 + lane) : none;      // next batch in flight while this one is filtered
+        const int gi = __float_as_int(q.w);
+        bool cand = false;
+        unsigned long long key = 0;
+        if (gi >= base && gi < base + nc) {
+            const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+            if (d2 < r2) {
+                key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
+                cand = true;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j2 = jj + (k < 2 ? k - 2 : k - 1);
+                    if (has[k] && claim_key(q, nb[k], (unsigned)(len - 1 - j2)) < key) cand = false;
+                }
+            }
+        }
+        if (SHORT) {
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = make_int2(t0 + lane, jj);
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                qn -= 32;
+                claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
+                __syncwarp();
+            }
+        } else if (cand) {
+            const unsigned long long old = atomicMin(a.best + gi, key);
+            if (old == BEST_NONE) a.touched[base + atomicAdd(touch_cnt, 1)] = gi;
+        }
     }
 }
 
@@ -130,10 +226,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
     const int gtid = cr * 1024 + tid, nthr = CL * 1024;
     __shared__ int s_minpos, s_first, s_term, s_rbits;
     __shared__ float4 s_path[PATH_SMEM];      // xyz + radius of the path vertices (first PATH_SMEM of them)
+    __shared__ int2 s_queue[32][QUEUE_LEN];   // per-warp survivors of the neighbour pre-filter (short routes)
     int cursor = 0, bid = 0, pcur = 0, iter = 0;
     __shared__ unsigned long long st[8];
-    __shared__ long long s_tc;
-    if (tid == 0) { for (int i = 0; i < 8; ++i) st[i] = 0; s_tc = clock64(); }
+    __shared__ long long s_tc, s_t0;
+    if (tid == 0) { for (int i = 0; i < 8; ++i) st[i] = 0; s_tc = clock64(); s_t0 = s_tc; }
 #define ST_PHASE(i) do { if (tid == 0) { long long _t = clock64(); st[i] += (unsigned long long)(_t - s_tc); s_tc = _t; } } while (0)
     while (true) {
         // ---- 1. farthest live vertex: next entry of the (distance desc, index asc) list that is still unallocated
@@ -157,17 +254,21 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         // ---- 2. route to the first allocated ancestor (path.py:9-16), 1024 hops per round
         int len = 0, cur = f, term = -1;
         int *out = a.path_out + base + pcur;      // farthest first here; reversed when the branch is emitted
+        int span = 64;                            // most routes are a few dozen hops: try 64 ancestors (<= 6 dependent loads) first
         while (true) {
             if (tid == 0) s_first = 1024;
             __syncthreads();
             int x = cur;
+            if (tid < span) {
 #pragma unroll
-            for (int k = 0; k < 10; ++k)
-                if (((tid >> k) & 1) && x >= 0) x = __ldg(jump + (size_t)k * n_total + base + x);
-            bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
-            if (stop) atomicMin(&s_first, tid);
+                for (int k = 0; k < 10; ++k)
+                    if (((tid >> k) & 1) && x >= 0) x = __ldg(jump + (size_t)k * n_total + base + x);
+                bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
+                if (stop) atomicMin(&s_first, tid);
+            }
             __syncthreads();
             const int first = s_first;
+            if (first == 1024 && span < 1024) { span = 1024; __syncthreads(); continue; }   // not within 64 hops: full width
             if (tid == first) s_term = x;
             const int cnt = min(first, max(nc - pcur - len, 0));
             if (tid < cnt) out[len + tid] = x;
@@ -199,37 +300,53 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         const float r2 = __fmul_rn(r, r);
         const bool emit = len >= 2;
         int32_t *const cnt_cur = a.touch_cnt + 2 * c + (iter & 1);
-        // ---- 4. claim: every point within r of the path records its nearest path vertex
+        if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;      // next iteration's counter (idle since iter-1's last barrier)
         const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;       // cells reached on either side of the vertex's cell
         const int R2 = (2 * R + 1) * (2 * R + 1);
         const long long ntask = (long long)len * R2;
-        if (r > 0.f)
-            for (long long t = gwarp; t < ntask; t += nwarp) {
-                const int jj = (int)(t / R2);
-                float px, py, pz;
-                if (jj < PATH_SMEM) { const float4 p = s_path[jj]; px = p.x; py = p.y; pz = p.z; }
-                else { const int v = base + path[jj]; px = a.pts[3 * (size_t)v]; py = a.pts[3 * (size_t)v + 1]; pz = a.pts[3 * (size_t)v + 2]; }
-                claim_task(a, base, nc, px, py, pz, (unsigned)(len - 1 - jj), (int)(t % R2), R, r, r2, lane, cnt_cur);
+        if (len <= SCAN_PATH) {
+            // ---- 4s. short route (the common case): claim and resolve in one pass, no atomics (path.py:37-39)
+            if (r > 0.f) {
+                int qn = 0;
+                for (long long t = gwarp; t < ntask; t += nwarp)
+                    claim_row<true>(a, base, nc, s_path, (int)(t / R2), len, (int)(t % R2), R, r, r2, lane, emit ? bid : -1, nullptr, s_queue[warp], qn);
+                __syncwarp();
+                claim_drain(a, s_path, len, s_queue[warp], 0, qn, lane, emit ? bid : -1);
             }
-        if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;      // next iteration's counter
-        cluster_sync_all();
-        ST_PHASE(2);
-        // ---- 5. resolve: walk the touched list once; a point is on the branch iff it lies inside the radius of
-        //         its nearest path vertex (path.py:37-39).  6. allocate the path itself.
-        const int ntouch = __ldcg(cnt_cur);
-        for (int k = gtid; k < ntouch; k += nthr) {
-            const int gi = __ldcg(a.touched + base + k);
-            const unsigned long long bkey = __ldcg(a.best + gi);
-            const int jj = len - 1 - (int)(unsigned)(bkey & 0xFFFFFFFFull);
-            const float d2 = __uint_as_float((unsigned)(bkey >> 32));
-            const float vr = jj < PATH_SMEM ? s_path[jj].w : a.radii[base + path[jj]];
-            if (sqrtf(d2) < vr) {
-                a.distw[gi] = -1.f;
-                a.alloc[gi] = 1;
-                if (emit) a.branch_id[gi] = bid;
+        } else {
+            // ---- 4. claim: every point within r of the path records its nearest path vertex
+            if (r > 0.f)
+                for (long long t = gwarp; t < ntask; t += nwarp) {
+                    const int jj = (int)(t / R2);
+                    int qn = 0;
+                    if (jj < PATH_SMEM) {
+                        claim_row<false>(a, base, nc, s_path, jj, len, (int)(t % R2), R, r, r2, lane, -1, cnt_cur, nullptr, qn);
+                    } else {
+                        const int v = base + path[jj];
+                        claim_task(a, base, nc, a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], (unsigned)(len - 1 - jj),
+                                   (int)(t % R2), R, r, r2, lane, cnt_cur);
+                    }
+                }
+            cluster_sync_all();
+            ST_PHASE(2);
+            // ---- 5. resolve: walk the touched list once; a point is on the branch iff it lies inside the radius of
+            //         its nearest path vertex (path.py:37-39).
+            const int ntouch = __ldcg(cnt_cur);
+            for (int k = gtid; k < ntouch; k += nthr) {
+                const int gi = __ldcg(a.touched + base + k);
+                const unsigned long long bkey = __ldcg(a.best + gi);
+                const int jj = len - 1 - (int)(unsigned)(bkey & 0xFFFFFFFFull);
+                const float d2 = __uint_as_float((unsigned)(bkey >> 32));
+                const float vr = jj < PATH_SMEM ? s_path[jj].w : a.radii[base + path[jj]];
+                if (sqrtf(d2) < vr) {
+                    a.distw[gi] = -1.f;
+                    a.alloc[gi] = 1;
+                    if (emit) a.branch_id[gi] = bid;
+                }
+                __stcg(a.best + gi, BEST_NONE);
             }
-            __stcg(a.best + gi, BEST_NONE);
         }
+        // ---- 6. allocate the path itself
         for (int jj = gtid; jj < len; jj += nthr) {
             int v = base + path[jj];
             a.distw[v] = -1.f;
@@ -237,6 +354,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
             if (emit) a.branch_id[v] = bid;
         }
         cluster_sync_all();
+        if (tid == 0 && c == 0 && cr == 0 && iter < 1024) {
+            g_st_iter[iter][0] = len; g_st_iter[iter][1] = R; g_st_iter[iter][2] = (int)(clock64() - s_tc); g_st_iter[iter][3] = (int)(clock64() - s_t0);
+            s_t0 = clock64();
+        }
         ST_PHASE(3);
         // ---- 7. emit the branch (root side first); only rank 0 touches the output
         if (emit) {
@@ -351,6 +472,10 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
 
 // debug only (not part of include/st_b200.h): cycles spent by component 0 in
 // [find, trace, claim, resolve, finish], iterations, traced path vertices
+extern "C" int st_debug_sample_iters(int *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_iter, sizeof(int) * 4096));
+    return ST_OK;
+}
 extern "C" int st_debug_sample_stats(unsigned long long *out_host) {
     ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_stats, sizeof(unsigned long long) * 8));
     return ST_OK;

@@ -230,6 +230,8 @@ class TreeSkeleton:
 @dataclass
 class DisjointTreeSkeleton:
     skeletons: List[TreeSkeleton]
+    # post-processing already done on the device by Skeletonizer.forward(post=...): {"prune", "repair", "smooth"}
+    post_applied: dict = None
 
     def prune(self, min_radius, min_length):
         # only the first skeleton is pruned (tree.py:164-168, quirk C-18)

@@ -16,7 +16,7 @@ LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1, "repair": 1}
+                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1}
 
 
 def _count(op):
@@ -395,6 +395,24 @@ def points_to_tubes(pts, a, b, r1, r2, tube_off):
     _lib.check(lib.st_points_to_tubes(_ptr(pts), nq, _ptr(a), _ptr(b), _ptr(r1), _ptr(r2), _ptr(tube_off), _ptr(vec),
                                       _ptr(idx), _ptr(rr), _stream()), "st_points_to_tubes")
     return vec, idx, rr
+
+
+def finish_skeletons(medial_pts, radii, comp_off, path, blen, bpar, cnb, cnp, prune_first=False, min_radius=0.0, min_length=0.0,
+                     repair=False, smooth_kernel=0):
+    """Node gather + prune + repair + smooth for every component in one launch.  Returns the packed int32
+    device buffer described in include/st_b200.h (header | bmeta | nodes | smooth)."""
+    lib = _lib.load()
+    _req(medial_pts, F32, "medial_pts"); _req(radii, F32, "radii"); _req(comp_off, I32, "comp_off")
+    for t, nm in ((path, "path"), (blen, "blen"), (bpar, "bpar"), (cnb, "cnb"), (cnp, "cnp")):
+        _req(t, I32, nm)
+    n = medial_pts.shape[0]
+    out = torch.empty(lib.st_finish_skeletons_out_ints(n), dtype=torch.int32, device=medial_pts.device)
+    depth = torch.empty(max(n, 1), dtype=torch.int32, device=medial_pts.device)
+    _count("finish_skeletons")
+    _lib.check(lib.st_finish_skeletons(_ptr(medial_pts), _ptr(radii), _ptr(comp_off), comp_off.shape[0] - 1, n, _ptr(path), _ptr(blen),
+                                       _ptr(bpar), _ptr(cnb), _ptr(cnp), int(bool(prune_first)), float(min_radius), float(min_length),
+                                       int(bool(repair)), int(smooth_kernel), _ptr(depth), _ptr(out), _stream()), "st_finish_skeletons")
+    return out
 
 
 def repair_branches(nodes, row, length, parent, parent_repaired, level_off):

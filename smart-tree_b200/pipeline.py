@@ -54,7 +54,7 @@ class Pipeline:
         self.labelled_cloud = lc
         with section("pipe.filter_class"):
             branch_cloud = lc.filter_by_class(self.branch_classes)                  # pipeline.py:68
-        skeleton = self.skeletonizer.forward(branch_cloud)                          # pipeline.py:71
+        skeleton = self.skeletonizer.forward(branch_cloud, post=self._fused_post())  # pipeline.py:71 (+ fused 76-88)
         sync(); t["skeleton"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.post_process(skeleton)
         sync(); t["post_process"] = time.perf_counter() - t0
@@ -66,7 +66,26 @@ class Pipeline:
                 save_skeleton(s, f"{self.save_path}/skeleton_{s._id}.npz")
         return skeleton
 
+    def _fused_post(self):
+        """The part of post_process (pipeline.py:76-88) the skeletoniser can run on the device in its branch
+        assembly launch.  Steps are order-dependent (prune -> repair -> smooth), so fusing stops at the first
+        step the kernel cannot do (an even smoothing kernel)."""
+        post = {}
+        if self.prune_skeletons:
+            post["prune"] = (float(self.min_skeleton_radius), float(self.min_skeleton_length))
+        if self.repair_skeletons:
+            post["repair"] = True
+        if self.smooth_skeletons and int(self.smooth_kernel_size) % 2 == 1:
+            post["smooth"] = int(self.smooth_kernel_size)
+        return post or None
+
     def post_process(self, skeleton: DisjointTreeSkeleton):
+        done = getattr(skeleton, "post_applied", None) or {}
+        if done:
+            if self.smooth_skeletons and "smooth" not in done:
+                with section("post.smooth"):
+                    skeleton.smooth(self.smooth_kernel_size)
+            return
         if self.prune_skeletons:
             with section("post.prune"):
                 skeleton.prune(min_length=self.min_skeleton_length, min_radius=self.min_skeleton_radius)

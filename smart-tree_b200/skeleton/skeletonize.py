@@ -30,55 +30,64 @@ class Skeletonizer:
         self.last = None       # intermediate tensors of the last call (for tests / diagnostics)
 
     @staticmethod
-    def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp) -> List[TreeSkeleton]:
-        """Two device->host copies in total: the per-component counts, then ONE packed buffer holding the path
-        vertex ids, branch lengths, parent ids and the gathered node coordinates / radii of every branch of
-        every component.  Nodes end up in one shared [P+B,4] host array (xyz, radius) with a spare row in
-        front of each branch, pre-filled with the branch's first node: `repair` later only has to write the
-        connection point there (its radius is the first node's radius by definition)."""
+    def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post=None) -> List[TreeSkeleton]:
+        """Branch assembly and (optionally) prune / repair / smooth on the device in one launch
+        (st_finish_skeletons), then two device->host copies in total: a 4-word header + the per-component
+        branch counts, and ONE packed buffer with the branch table, the node array [R,4] (xyz, radius; one
+        spare row in front of each branch for the repair connection point) and the smoothed radii.
+        `post` = dict(prune=(min_radius, min_length) | None, repair=bool, smooth=kernel_size) or None."""
         import numpy as np
 
         from ..data_types.branch import BranchSkeleton
         from ..data_types.tree import NodeStore
-        hdr = torch.cat([cnb, cnp, comp_off.int()]).cpu().numpy()
-        cnb_h, cnp_h, off_h = hdr[:ncomp], hdr[ncomp:2 * ncomp], hdr[2 * ncomp:]
-        nb, npth = int(cnb_h.sum()), int(cnp_h.sum())
+        post = post or {}
+        prune = post.get("prune")
+        k = int(post.get("smooth") or 0)
+        out = ops.finish_skeletons(sub_medial, sub_radius, off32, path, blen, bpar, cnb, cnp, prune_first=prune is not None,
+                                   min_radius=prune[0] if prune else 0.0, min_length=prune[1] if prune else 0.0,
+                                   repair=bool(post.get("repair")), smooth_kernel=k)
+        hdr = torch.cat([out[:4], cnb]).cpu().numpy()
+        nb, nrow = int(hdr[0]), int(hdr[1])
+        cnb_h = hdr[4:4 + ncomp]
         if nb == 0:
             return [TreeSkeleton(c, {}) for c in range(ncomp)]
-        dev = path.device
-        pseg = torch.cat([path[off_h[c]:off_h[c] + cnp_h[c]] for c in range(ncomp)]) if ncomp > 1 else path[:npth]
-        lseg = torch.cat([blen[off_h[c]:off_h[c] + cnb_h[c]] for c in range(ncomp)]) if ncomp > 1 else blen[:nb]
-        qseg = torch.cat([bpar[off_h[c]:off_h[c] + cnb_h[c]] for c in range(ncomp)]) if ncomp > 1 else bpar[:nb]
-        gidx = pseg.long()
-        if ncomp > 1:
-            gidx = gidx + torch.from_numpy(np.repeat(off_h[:ncomp].astype(np.int64), cnp_h)).to(dev)
-        payload = torch.cat([lseg, qseg, sub_medial[gidx].reshape(-1).view(torch.int32), sub_radius[gidx].view(torch.int32)]).cpu().numpy()
-        lens, pars = payload[:nb].astype(np.int64), payload[nb:2 * nb]
-        xyz = payload[2 * nb:2 * nb + 3 * npth].view(np.float32).reshape(npth, 3)
-        rad = payload[2 * nb + 3 * npth:].view(np.float32)
-        # host node array with one spare row per branch (copy of the branch's first node)
-        start = np.cumsum(lens) - lens
-        rep = np.ones(npth, np.int64)
-        rep[start] = 2
-        src = np.repeat(np.arange(npth), rep)
-        nodes = torch.from_numpy(np.concatenate([xyz[src], rad[src, None]], 1))
+        payload = out[4:4 + 4 * nb + 5 * nrow].cpu().numpy()
+        bmeta = payload[:4 * nb].reshape(nb, 4)
+        nodes = torch.from_numpy(payload[4 * nb:4 * nb + 4 * nrow].view(np.float32).reshape(nrow, 4))
+        smooth = torch.from_numpy(payload[4 * nb + 4 * nrow:].view(np.float32))
         store = NodeStore(nodes, None)
-        row = (start + np.arange(nb)).tolist()        # spare row of every branch
-        lens_l, pars_l = lens.tolist(), pars.tolist()
-        # all per-branch views from two split calls (per-branch slicing costs ~10 us of Python each)
-        sizes = [v for ln in lens_l for v in (1, ln)]
+        flags = bmeta[:, 3]
+        kept = np.flatnonzero(flags & 1)
+        conn = (flags[kept] & 2) != 0
+        first = bmeta[kept, 0] + np.where(conn, 0, 1)
+        cnt = bmeta[kept, 0] + bmeta[kept, 1] + 1 - first
+        # all per-branch views from three split calls (per-branch slicing costs ~10 us of Python each)
+        gaps = np.empty(2 * len(kept) + 1, np.int64)
+        gaps[0:-1:2] = first - np.concatenate([[0], (first + cnt)[:-1]])
+        gaps[1::2] = cnt
+        gaps[-1] = nrow - (first[-1] + cnt[-1]) if len(kept) else nrow
+        sizes = gaps.tolist()
         xyz_views = nodes[:, :3].split(sizes)[1::2]
         rad_views = nodes[:, 3:4].split(sizes)[1::2]
-        skeletons, bi = [], 0
-        for c in range(ncomp):
-            branches = {}
-            for bid in range(int(cnb_h[c])):
-                branches[bid] = BranchSkeleton(bid, pars_l[bi], xyz_views[bi], rad_views[bi], _flat=(store, row[bi], lens_l[bi], False))
-                bi += 1
-            skeletons.append(TreeSkeleton(c, branches))
-        return skeletons
+        smooth_views = smooth.split(sizes)[1::2]
+        comp_of = np.repeat(np.arange(ncomp), cnb_h)
+        local = np.arange(nb) - np.repeat(np.cumsum(cnb_h) - cnb_h, cnb_h)
+        rows_l, lens_l, pars_l, flags_l = bmeta[kept, 0].tolist(), bmeta[kept, 1].tolist(), bmeta[kept, 2].tolist(), flags[kept].tolist()
+        comp_l, bid_l = comp_of[kept].tolist(), local[kept].tolist()
+        per_comp = [dict() for _ in range(ncomp)]
+        for i in range(len(rows_l)):
+            f = flags_l[i]
+            br = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i], _flat=(store, rows_l[i], lens_l[i], bool(f & 2)))
+            if f & 4:                       # smoothed radii are 1-D and no longer live in the shared array (quirk C-17)
+                br.radii = smooth_views[i]
+                br._flat = None
+            per_comp[comp_l[i]][bid_l[i]] = br
+        return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
 
-    def forward(self, cloud: Cloud) -> DisjointTreeSkeleton:
+    def forward(self, cloud: Cloud, post: dict = None) -> DisjointTreeSkeleton:
+        """`post` (optional, not in the reference signature): post-processing to fuse into the device-side branch
+        assembly -- see _emit.  The returned skeleton records it in `.post_applied` so that Pipeline.post_process
+        does not repeat it."""
         cloud = cloud.to_device(self.device)
         if len(cloud) == 0:
             return DisjointTreeSkeleton([])
@@ -146,8 +155,8 @@ class Skeletonizer:
         with section("skel.sample_tree"):
             path, blen, bpar, cnb, cnp = ops.sample_tree(sub_medial, sub_radius, pred_local, tdist, off32, _cell_size(sub_radius))
         with section("skel.emit"):
-            skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, comp_off, ncomp)
+            skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post)
         self.last = dict(keep=keep, order=order, comp_off=comp_off, pred=pred_local, dist=dist, tree_dist=tdist, roots=src,
                          path=path, branch_len=blen, branch_parent=bpar, comp_n_branches=cnb, comp_n_path=cnp,
                          n_components=ncomp, edges=graph.edges, edge_weights=graph.edge_weights)
-        return DisjointTreeSkeleton(skeletons)
+        return DisjointTreeSkeleton(skeletons, post_applied=dict(post) if post else None)

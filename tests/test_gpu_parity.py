@@ -518,3 +518,35 @@ def test_pipeline_end_to_end_matches_oracle():
             assert gb.parent_id == par and gb.xyz.shape[0] == len(xyz)
             np.testing.assert_allclose(gb.xyz.numpy(), xyz, rtol=0, atol=1e-4)
             np.testing.assert_allclose(gb.radii.numpy().reshape(-1), rad.reshape(-1), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("prune,repair,smooth", [((0.01, 0.02), True, 11), ((0.03, 0.2), True, 5), (None, True, 0), ((0.02, 0.1), False, 7),
+                                                 (None, False, 0), ((0.01, 0.02), True, 4)])
+def test_fused_post_processing_equals_object_level(prune, repair, smooth):
+    """st_finish_skeletons (prune / repair / smooth inside the branch-assembly launch) against the object-level
+    TreeSkeleton methods that mirror tree.py:73-134 one by one."""
+    from smart_tree_b200.data_types.cloud import Cloud
+    from smart_tree_b200.pipeline import Pipeline
+    from smart_tree_b200.skeleton.skeletonize import Skeletonizer
+    xyz, mv = _medial_case(0, 50000, 0.02)
+    sk = Skeletonizer(K=16, min_connection_length=0.02, minimum_graph_vertices=32, device=torch.device(DEV))
+    mk = lambda: Cloud(xyz=_t(xyz), medial_vector=_t(mv))
+    pipe = Pipeline(None, None, sk, repair_skeletons=repair, smooth_skeletons=smooth > 0, smooth_kernel_size=smooth,
+                    prune_skeletons=prune is not None, min_skeleton_radius=prune[0] if prune else 0.0,
+                    min_skeleton_length=prune[1] if prune else 0.0, device=torch.device(DEV))
+    fused = sk.forward(mk(), post=pipe._fused_post())
+    pipe.post_process(fused)
+    plain = sk.forward(mk())
+    assert plain.post_applied is None
+    pipe.post_process(plain)
+    assert len(fused.skeletons) == len(plain.skeletons) >= 1
+    total = 0
+    for f, p in zip(fused.skeletons, plain.skeletons):
+        assert list(f.branches.keys()) == list(p.branches.keys())
+        for bid, pb in p.branches.items():
+            fb = f.branches[bid]
+            assert fb.parent_id == pb.parent_id and fb.xyz.shape == pb.xyz.shape and fb.radii.shape == pb.radii.shape
+            assert np.array_equal(fb.xyz.numpy(), pb.xyz.numpy())
+            np.testing.assert_allclose(fb.radii.numpy(), pb.radii.numpy(), rtol=1e-6, atol=1e-9)
+            total += 1
+    assert total > 5
