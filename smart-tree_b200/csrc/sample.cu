@@ -14,7 +14,7 @@ constexpr unsigned long long BEST_NONE = 0xFFFFFFFFFFFFFFFFull;
 
 // debug counters of the last launch's block 0 (cycles per phase, iterations, path vertices)
 __device__ unsigned long long g_st_stats[8];
-__device__ int g_st_iter[1024][4];    // per iteration of block 0: route length, R, cycles of the claim phase, cycles of the iteration
+__device__ int g_st_iter[1024][8];    // per iteration of block 0: route length, R, cycles of the claim phase, cycles of the iteration
 
 __global__ void k_st_init(const int32_t *__restrict__ pred, const float *__restrict__ tree_dist, int n, float *distw,
                           uint8_t *alloc, int32_t *branch_id, unsigned long long *best, const int32_t *__restrict__ comp_off,
@@ -61,7 +61,7 @@ struct SampleArgs {
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered
 // 0 .. RW*RW-1 around the vertex's own cell, so a short path still spreads over every warp of the cluster.
-constexpr int PATH_SMEM = 1536;    // path vertices whose position is staged in shared memory per iteration
+constexpr int PATH_SMEM = 1024;    // path vertices whose position is staged in shared memory per iteration
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered 0 .. RW*RW-1
 // around the vertex's own cell, so a short path still spreads over every warp of the cluster.  Every
@@ -124,65 +124,135 @@ __device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s
     }
 }
 
-template <bool SHORT>
-__device__ __forceinline__ void claim_row(const SampleArgs &a, int base, int nc, const float4 *s_path, int jj, int len, int row, int R,
-                                          float r, float r2, int lane, int bid, int32_t *touch_cnt, int2 *queue, int &qn) {
+// Range [beg, end) of the cell-sorted point array covered by grid row `row` (numbered 0 .. RW*RW-1 around the
+// cell of path vertex p) within the search sphere of radius rr: the chord of the sphere along that row.
+__device__ __forceinline__ void row_range(const SampleArgs &a, float4 p, int row, int R, float rr, int &beg, int &end) {
     const Grid &g = a.g;
-    const float4 p = s_path[jj];
-    const float rr = r * 1.0001f + 1e-7f;
+    beg = end = 0;
     const int RW = 2 * R + 1;
-    const int cz = cell_coord(p.z, g.oz, g.inv_h, g.nz) + row / RW - R;
-    const int cy = cell_coord(p.y, g.oy, g.inv_h, g.ny) + row % RW - R;
+    const int pcz = cell_coord(p.z, g.oz, g.inv_h, g.nz), pcy = cell_coord(p.y, g.oy, g.inv_h, g.ny);
+    const int cz = pcz + row / RW - R;
+    const int cy = pcy + row % RW - R;
     if (cz < cell_coord(p.z - rr, g.oz, g.inv_h, g.nz) || cz > cell_coord(p.z + rr, g.oz, g.inv_h, g.nz)) return;
     if (cy < cell_coord(p.y - rr, g.oy, g.inv_h, g.ny) || cy > cell_coord(p.y + rr, g.oy, g.inv_h, g.ny)) return;
-    const int x0 = cell_coord(p.x - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(p.x + rr, g.ox, g.inv_h, g.nx);
+    // binning is monotone, so every point of row (cy, cz) is at least dy / dz away from p in y / z (near-side cell
+    // boundary, with slack for the rounding of the binning)
+    const float slack = 1e-4f * g.h + 1e-6f;
+    float dy = 0.f, dz = 0.f;
+    if (cy > pcy) dy = fmaxf(0.f, (g.oy + (float)cy * g.h - slack) - p.y);
+    else if (cy < pcy) dy = fmaxf(0.f, p.y - (g.oy + (float)(cy + 1) * g.h + slack));
+    if (cz > pcz) dz = fmaxf(0.f, (g.oz + (float)cz * g.h - slack) - p.z);
+    else if (cz < pcz) dz = fmaxf(0.f, p.z - (g.oz + (float)(cz + 1) * g.h + slack));
+    const float rem = rr * rr - dy * dy - dz * dz;
+    if (rem < 0.f) return;
+    const float half = sqrtf(rem) * 1.0001f + slack;
+    const int x0 = cell_coord(p.x - half, g.ox, g.inv_h, g.nx), x1 = cell_coord(p.x + half, g.ox, g.inv_h, g.nx);
     const int rowc = (cz * g.ny + cy) * g.nx;
-    const int beg = __ldg(a.cell_start + rowc + x0), end = __ldg(a.cell_start + rowc + x1 + 1);
-    if (beg >= end) return;
-    const unsigned pos = (unsigned)(len - 1 - jj);
-    const int lim = len < PATH_SMEM ? len : PATH_SMEM;
-    float4 nb[4];
-    bool has[4];
+    beg = __ldg(a.cell_start + rowc + x0);
+    end = __ldg(a.cell_start + rowc + x1 + 1);
+}
+
+__device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int j2 = jj + (k < 2 ? k - 2 : k - 1);
-        has[k] = j2 >= 0 && j2 < lim;
-        nb[k] = has[k] ? s_path[j2] : p;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
     }
-    const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
-    float4 qnext = beg + lane < end ? __ldg(a.sorted + beg + lane) : none;
-    for (int t0 = beg; t0 < end; t0 += 32) {
-        const float4 q = qnext;
-        qnext = t0 + 32 + lane < end ? __ldg(a.sorted + t0 + 32 + lane) : none;      // next batch in flight while this one is filtered
-        const int gi = __float_as_int(q.w);
-        bool cand = false;
-        unsigned long long key = 0;
-        if (gi >= base && gi < base + nc) {
-            const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
-            if (d2 < r2) {
-                key = ((unsigned long long)__float_as_uint(d2) << 32) | pos;
-                cand = true;
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int j2 = jj + (k < 2 ? k - 2 : k - 1);
-                    if (has[k] && claim_key(q, nb[k], (unsigned)(len - 1 - j2)) < key) cand = false;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    total = s_warp[31];
+    return x - v + (warp ? s_warp[warp - 1] : 0);
+}
+
+// Claim pass of one CTA over its share of the (path vertex, grid row) tasks, FLATTENED: medial points pile up
+// along the branch axes, so a few rows hold most of the candidates and a warp per row leaves the cluster
+// waiting for one warp.  Per round every thread looks up the range of ONE task (a single round trip for
+// 1024 tasks), a block scan lays the ranges end to end, and the 1024 threads walk the concatenated points.
+template <bool SHORT>
+__device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc, const float4 *s_path, int len, int nflat, int R2, int R,
+                                           float r, float r2, int bid, int32_t *touch_cnt, int2 *queue, int *s_off, int *s_beg,
+                                           int *s_jj, int *s_warp, unsigned cr, unsigned CL) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float rr = r * 1.0001f + 1e-7f;
+    const int lim = len < PATH_SMEM ? len : PATH_SMEM;
+    const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+    int qn = 0;
+    for (int tb = 0; (long long)tb * CL < nflat; tb += 1024) {
+        const long long t = (long long)(tb + tid) * CL + cr;      // tasks interleaved over the CTAs of the cluster
+        int beg = 0, end = 0, jj = 0;
+        if (t < nflat) {
+            jj = (int)(t / R2);
+            row_range(a, s_path[jj], (int)(t % R2), R, rr, beg, end);
+        }
+        int total;
+        const int ex = block_excl_scan_1024(end > beg ? end - beg : 0, s_warp, total);
+        s_off[tid] = ex; s_beg[tid] = beg; s_jj[tid] = jj;
+        __syncthreads();
+        auto locate = [&](int e, int &tp, int &j) -> float4 {
+            if (e >= total) { tp = 0; j = 0; return none; }
+            int lo = 0, hi = 1023;
+            while (lo < hi) {                       // last task whose offset is <= e (empty tasks share the offset of their successor)
+                const int mid = (lo + hi + 1) >> 1;
+                if (s_off[mid] <= e) lo = mid; else hi = mid - 1;
+            }
+            tp = s_beg[lo] + (e - s_off[lo]);
+            j = s_jj[lo];
+            return __ldg(a.sorted + tp);
+        };
+        int tpn, jn;
+        float4 qnext = locate(tid, tpn, jn);
+        for (int e0 = 0; e0 < total; e0 += 1024) {
+            const float4 q = qnext;
+            const int tp = tpn, j = jn;
+            qnext = locate(e0 + 1024 + tid, tpn, jn);       // next batch in flight while this one is filtered
+            const int gi = __float_as_int(q.w);
+            bool cand = false;
+            unsigned long long key = 0;
+            if (gi >= base && gi < base + nc) {
+                const float4 p = s_path[j];
+                const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+                if (d2 < r2) {
+                    key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
+                    cand = true;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int j2 = j + (k < 2 ? k - 2 : k - 1);
+                        if (j2 >= 0 && j2 < lim && claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key) cand = false;
+                    }
                 }
             }
-        }
-        if (SHORT) {
-            const unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = make_int2(t0 + lane, jj);
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                qn -= 32;
-                claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
+            if (SHORT) {
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (cand) queue[qn + __popc(m & ((1u << lane) - 1u))] = make_int2(tp, j);
+                qn += __popc(m);
                 __syncwarp();
+                if (qn >= 32) {
+                    qn -= 32;
+                    claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
+                    __syncwarp();
+                }
+            } else if (cand) {
+                const unsigned long long old = atomicMin(a.best + gi, key);
+                if (old == BEST_NONE) a.touched[base + atomicAdd(touch_cnt, 1)] = gi;
             }
-        } else if (cand) {
-            const unsigned long long old = atomicMin(a.best + gi, key);
-            if (old == BEST_NONE) a.touched[base + atomicAdd(touch_cnt, 1)] = gi;
         }
+        __syncthreads();
+    }
+    if (SHORT) {
+        __syncwarp();
+        claim_drain(a, s_path, len, queue, 0, qn, lane, bid);
     }
 }
 
@@ -200,15 +270,33 @@ __device__ __forceinline__ unsigned cluster_size() {
     return r;
 }
 
-constexpr int JUMP_LEVELS = 11;   // ancestors 2^0 .. 2^10: a 1024-thread CTA resolves 1024 hops per round
+// Ancestor table in base 8: jump[(7*L + d-1)][v] = (d * 8^L)-th ancestor of v in the predecessor tree
+// (component-local ids, -1 past the root), L = 0..3, d = 1..7.  Hop count h < 4096 = up to four dependent
+// loads (one per non-zero octal digit); the 64 nearest ancestors cost at most two.
+constexpr int JUMP_L = 4;
+constexpr int JUMP_LEVELS = 7 * JUMP_L;
 
-// jump[k][v] = 2^k-th ancestor of v in the predecessor tree (component-local ids, -1 past the root)
-__global__ void k_jump_level(const int32_t *__restrict__ prev, int32_t *__restrict__ next, const int32_t *__restrict__ comp_of_base,
-                             int n) {
+// digit 1 of level L: 8^L = 7 * 8^(L-1) + 8^(L-1)
+__global__ void k_jump_first(const int32_t *__restrict__ pred, int32_t *__restrict__ jump, const int32_t *__restrict__ vbase, int n, int L) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
-    int p = prev[v];
-    next[v] = p < 0 ? -1 : prev[comp_of_base[v] + p];
+    int32_t *dst = jump + (size_t)(7 * L) * n;
+    if (L == 0) { dst[v] = pred[v]; return; }
+    const int32_t *p7 = jump + (size_t)(7 * (L - 1) + 6) * n, *p1 = jump + (size_t)(7 * (L - 1)) * n;
+    const int x = p7[v];
+    dst[v] = x < 0 ? -1 : p1[vbase[v] + x];
+}
+// digits 2..7 of level L by repeated application of digit 1
+__global__ void k_jump_rest(int32_t *__restrict__ jump, const int32_t *__restrict__ vbase, int n, int L) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int32_t *p1 = jump + (size_t)(7 * L) * n;
+    const int b = vbase[v];
+    int x = p1[v];
+    for (int d = 2; d <= 7; ++d) {
+        x = x < 0 ? -1 : p1[b + x];
+        jump[(size_t)(7 * L + d - 1) * n + v] = x;
+    }
 }
 
 // One thread-block CLUSTER per connected component.  Every CTA of the cluster redundantly (and
@@ -227,6 +315,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
     __shared__ int s_minpos, s_first, s_term, s_rbits;
     __shared__ float4 s_path[PATH_SMEM];      // xyz + radius of the path vertices (first PATH_SMEM of them)
     __shared__ int2 s_queue[32][QUEUE_LEN];   // per-warp survivors of the neighbour pre-filter (short routes)
+    __shared__ int s_off[1024], s_beg[1024], s_jj[1024], s_scan[32];     // flattened claim: per-task offset / range start / path index
     int cursor = 0, bid = 0, pcur = 0, iter = 0;
     __shared__ unsigned long long st[8];
     __shared__ long long s_tc, s_t0;
@@ -253,16 +342,19 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         ST_PHASE(0);
         // ---- 2. route to the first allocated ancestor (path.py:9-16), 1024 hops per round
         int len = 0, cur = f, term = -1;
+        float rl = 0.f;                           // largest radius among the path vertices this thread staged
         int *out = a.path_out + base + pcur;      // farthest first here; reversed when the branch is emitted
-        int span = 64;                            // most routes are a few dozen hops: try 64 ancestors (<= 6 dependent loads) first
+        int span = 64;                            // most routes are a few dozen hops: try 64 ancestors (<= 2 dependent loads) first
         while (true) {
             if (tid == 0) s_first = 1024;
             __syncthreads();
             int x = cur;
             if (tid < span) {
 #pragma unroll
-                for (int k = 0; k < 10; ++k)
-                    if (((tid >> k) & 1) && x >= 0) x = __ldg(jump + (size_t)k * n_total + base + x);
+                for (int L = 0; L < JUMP_L; ++L) {
+                    const int d = (tid >> (3 * L)) & 7;
+                    if (d && x >= 0) x = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + x);
+                }
                 bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
                 if (stop) atomicMin(&s_first, tid);
             }
@@ -271,12 +363,19 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
             if (first == 1024 && span < 1024) { span = 1024; __syncthreads(); continue; }   // not within 64 hops: full width
             if (tid == first) s_term = x;
             const int cnt = min(first, max(nc - pcur - len, 0));
-            if (tid < cnt) out[len + tid] = x;
+            if (tid < cnt) {
+                out[len + tid] = x;
+                // stage position + radius of this path vertex straight from the register that holds its id
+                const int v = base + x;
+                const float rv = a.radii[v];
+                if (len + tid < PATH_SMEM) s_path[len + tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                rl = fmaxf(rl, rv);
+            }
             __syncthreads();
             len += cnt;
             if (first < 1024) { term = s_term; break; }
             if (cnt < 1024) { term = -1; break; }           // defensive: path longer than the component
-            cur = __ldg(jump + (size_t)10 * n_total + base + cur);
+            cur = __ldg(jump + (size_t)(7 * 3 + 1) * n_total + base + cur);      // 2 * 8^3 = 1024 hops further
             __syncthreads();
         }
         const int parent = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));   // -1 wraps to the last vertex (path.py:132)
@@ -285,48 +384,35 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         ST_PHASE(1);
         if (tid == 0) { st[5] += 1; st[6] += len; }
         const int *path = out;
-        // ---- 3. stage the path (position + radius) in shared memory; search radius = max radius over the path
-        float rl = 0.f;
-        for (int jj = tid; jj < len; jj += blockDim.x) {
-            const int v = base + path[jj];
-            const float rv = a.radii[v];
-            if (jj < PATH_SMEM) s_path[jj] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
-            rl = fmaxf(rl, rv);
-        }
+        // ---- 3. search radius = max radius over the path (staged in shared memory by the trace above)
         for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
         if (lane == 0 && rl > 0.f) atomicMax(&s_rbits, __float_as_int(rl));
         __syncthreads();
         const float r = __int_as_float(s_rbits);
         const float r2 = __fmul_rn(r, r);
+        long long t_a = clock64(), t_b = t_a, t_c = t_a;
         const bool emit = len >= 2;
         int32_t *const cnt_cur = a.touch_cnt + 2 * c + (iter & 1);
         if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;      // next iteration's counter (idle since iter-1's last barrier)
         const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;       // cells reached on either side of the vertex's cell
         const int R2 = (2 * R + 1) * (2 * R + 1);
         const long long ntask = (long long)len * R2;
+        const int nflat = (int)min((long long)min(len, PATH_SMEM) * R2, (long long)INT_MAX);
         if (len <= SCAN_PATH) {
             // ---- 4s. short route (the common case): claim and resolve in one pass, no atomics (path.py:37-39)
-            if (r > 0.f) {
-                int qn = 0;
-                for (long long t = gwarp; t < ntask; t += nwarp)
-                    claim_row<true>(a, base, nc, s_path, (int)(t / R2), len, (int)(t % R2), R, r, r2, lane, emit ? bid : -1, nullptr, s_queue[warp], qn);
-                __syncwarp();
-                claim_drain(a, s_path, len, s_queue[warp], 0, qn, lane, emit ? bid : -1);
-            }
+            if (r > 0.f)
+                claim_flat<true>(a, base, nc, s_path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, s_queue[warp], s_off, s_beg, s_jj, s_scan, cr, CL);
         } else {
             // ---- 4. claim: every point within r of the path records its nearest path vertex
-            if (r > 0.f)
-                for (long long t = gwarp; t < ntask; t += nwarp) {
+            if (r > 0.f) {
+                claim_flat<false>(a, base, nc, s_path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, s_off, s_beg, s_jj, s_scan, cr, CL);
+                for (long long t = (long long)nflat + gwarp; t < ntask; t += nwarp) {      // vertices beyond the staged part of the path
                     const int jj = (int)(t / R2);
-                    int qn = 0;
-                    if (jj < PATH_SMEM) {
-                        claim_row<false>(a, base, nc, s_path, jj, len, (int)(t % R2), R, r, r2, lane, -1, cnt_cur, nullptr, qn);
-                    } else {
-                        const int v = base + path[jj];
-                        claim_task(a, base, nc, a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], (unsigned)(len - 1 - jj),
-                                   (int)(t % R2), R, r, r2, lane, cnt_cur);
-                    }
+                    const int v = base + path[jj];
+                    claim_task(a, base, nc, a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], (unsigned)(len - 1 - jj),
+                               (int)(t % R2), R, r, r2, lane, cnt_cur);
                 }
+            }
             cluster_sync_all();
             ST_PHASE(2);
             // ---- 5. resolve: walk the touched list once; a point is on the branch iff it lies inside the radius of
@@ -346,6 +432,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
                 __stcg(a.best + gi, BEST_NONE);
             }
         }
+        t_b = clock64();
         // ---- 6. allocate the path itself
         for (int jj = gtid; jj < len; jj += nthr) {
             int v = base + path[jj];
@@ -353,9 +440,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
             a.alloc[v] = 1;
             if (emit) a.branch_id[v] = bid;
         }
+        t_c = clock64();
         cluster_sync_all();
         if (tid == 0 && c == 0 && cr == 0 && iter < 1024) {
             g_st_iter[iter][0] = len; g_st_iter[iter][1] = R; g_st_iter[iter][2] = (int)(clock64() - s_tc); g_st_iter[iter][3] = (int)(clock64() - s_t0);
+            g_st_iter[iter][4] = (int)(t_a - s_tc); g_st_iter[iter][5] = (int)(t_b - t_a); g_st_iter[iter][6] = (int)(t_c - t_b); g_st_iter[iter][7] = (int)(clock64() - t_c);
             s_t0 = clock64();
         }
         ST_PHASE(3);
@@ -427,9 +516,10 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     // binary-lifting table over the (static) predecessor tree
     k_vertex_base<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(comp_off, n_comp, (int)n, vbase);
     ST_CHECK_LAUNCH();
-    ST_CHECK_CUDA(cudaMemcpyAsync(jump, pred, n * 4, cudaMemcpyDeviceToDevice, s));
-    for (int k = 1; k < JUMP_LEVELS; ++k) {
-        k_jump_level<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(jump + (size_t)(k - 1) * n, jump + (size_t)k * n, vbase, (int)n);
+    for (int L = 0; L < JUMP_L; ++L) {
+        k_jump_first<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(pred, jump, vbase, (int)n, L);
+        ST_CHECK_LAUNCH();
+        k_jump_rest<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(jump, vbase, (int)n, L);
         ST_CHECK_LAUNCH();
     }
     SampleArgs a{medial_pts, radii, pred, comp_off, gb.g, gb.cell_start, gb.sorted, order, distw, alloc, branch_id, best,
@@ -473,7 +563,7 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
 // debug only (not part of include/st_b200.h): cycles spent by component 0 in
 // [find, trace, claim, resolve, finish], iterations, traced path vertices
 extern "C" int st_debug_sample_iters(int *out_host) {
-    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_iter, sizeof(int) * 4096));
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_iter, sizeof(int) * 8192));
     return ST_OK;
 }
 extern "C" int st_debug_sample_stats(unsigned long long *out_host) {

@@ -58,30 +58,45 @@ class Skeletonizer:
         store = NodeStore(nodes, None)
         flags = bmeta[:, 3]
         kept = np.flatnonzero(flags & 1)
+        if len(kept) == 0:
+            return [TreeSkeleton(c, {}) for c in range(ncomp)]
         conn = (flags[kept] & 2) != 0
         first = bmeta[kept, 0] + np.where(conn, 0, 1)
         cnt = bmeta[kept, 0] + bmeta[kept, 1] + 1 - first
-        # all per-branch views from three split calls (per-branch slicing costs ~10 us of Python each)
-        gaps = np.empty(2 * len(kept) + 1, np.int64)
-        gaps[0:-1:2] = first - np.concatenate([[0], (first + cnt)[:-1]])
-        gaps[1::2] = cnt
-        gaps[-1] = nrow - (first[-1] + cnt[-1]) if len(kept) else nrow
-        sizes = gaps.tolist()
-        xyz_views = nodes[:, :3].split(sizes)[1::2]
-        rad_views = nodes[:, 3:4].split(sizes)[1::2]
-        smooth_views = smooth.split(sizes)[1::2]
         comp_of = np.repeat(np.arange(ncomp), cnb_h)
         local = np.arange(nb) - np.repeat(np.cumsum(cnb_h) - cnb_h, cnb_h)
         rows_l, lens_l, pars_l, flags_l = bmeta[kept, 0].tolist(), bmeta[kept, 1].tolist(), bmeta[kept, 2].tolist(), flags[kept].tolist()
         comp_l, bid_l = comp_of[kept].tolist(), local[kept].tolist()
         per_comp = [dict() for _ in range(ncomp)]
+        if post:
+            # post-processing is complete: pack the surviving rows (one gather) so that the per-branch views come
+            # from two gap-free split calls (a view costs ~0.5 us; gaps would double their number)
+            csum = np.cumsum(cnt)
+            rows = np.repeat(first - (csum - cnt), cnt) + np.arange(int(csum[-1]))
+            sm_row = np.repeat((flags[kept] & 4) != 0, cnt)
+            packed = nodes[torch.from_numpy(rows)]
+            radcol = torch.where(torch.from_numpy(sm_row), smooth[torch.from_numpy(rows)], packed[:, 3])
+            sizes = cnt.tolist()
+            xyz_views = packed[:, :3].split(sizes)
+            rad_views = radcol.split(sizes)
+            for i in range(len(rows_l)):
+                # smoothed radii are 1-D (quirk C-17), untouched ones [N,1]
+                br = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i].unsqueeze(1))
+                if flags_l[i] & 4:
+                    br.radii = rad_views[i]
+                per_comp[comp_l[i]][bid_l[i]] = br
+            return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
+        # plain assembly: keep the spare rows (object-level repair writes the connection points there)
+        gaps = np.empty(2 * len(kept) + 1, np.int64)
+        gaps[0:-1:2] = first - np.concatenate([[0], (first + cnt)[:-1]])
+        gaps[1::2] = cnt
+        gaps[-1] = nrow - (first[-1] + cnt[-1])
+        sizes = gaps.tolist()
+        xyz_views = nodes[:, :3].split(sizes)[1::2]
+        rad_views = nodes[:, 3:4].split(sizes)[1::2]
         for i in range(len(rows_l)):
-            f = flags_l[i]
-            br = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i], _flat=(store, rows_l[i], lens_l[i], bool(f & 2)))
-            if f & 4:                       # smoothed radii are 1-D and no longer live in the shared array (quirk C-17)
-                br.radii = smooth_views[i]
-                br._flat = None
-            per_comp[comp_l[i]][bid_l[i]] = br
+            per_comp[comp_l[i]][bid_l[i]] = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i],
+                                                           _flat=(store, rows_l[i], lens_l[i], False))
         return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
 
     def forward(self, cloud: Cloud, post: dict = None) -> DisjointTreeSkeleton:

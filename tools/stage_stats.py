@@ -50,11 +50,11 @@ stats = (C.c_ulonglong * 8)()
 lib = _lib.load()
 lib.st_debug_sample_stats.argtypes = [C.c_void_p]
 lib.st_debug_sample_stats(stats)
-iters = (C.c_int * 4096)()
+iters = (C.c_int * 8192)()
 lib.st_debug_sample_iters.argtypes = [C.c_void_p]
 lib.st_debug_sample_iters(iters)
 import numpy as _np
-_np.save("gpurun_out/sample_iters.npy", _np.array(iters[:]).reshape(1024, 4))
+_np.save("gpurun_out/sample_iters.npy", _np.array(iters[:]).reshape(1024, 8))
 # depth of the predecessor tree (hops) by pointer jumping on the host
 import numpy as np
 last = pipe.skeletonizer.last
