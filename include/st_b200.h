@@ -141,6 +141,24 @@ int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_
                       const float *residual, int res_ld, const float *in2, int in2_ld,
                       const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
 
+/* Tile-plan variant of the tensor-core conv: the DISTINCT source rows of every 128-row output tile are
+ * staged in shared memory once (rows are in Z-order, so a tile's 27 x 128 map entries name only ~2 x 128
+ * distinct rows) and the A fragments are gathered from there instead of through the L1.  The plan is
+ * built once per gather map (spconv builds its rulebook per indice_key the same way:
+ * smart_tree/model/model_blocks.py:24-32,58-67,91-98) and shared by every conv that uses the map:
+ *   plan = [ per tile: split flag + distinct-row counts | 16-bit local gather map [28][128] | row lists ]
+ * st_conv_plan_bytes(n_out) bytes, 256-byte aligned, caller-allocated.  n_in = rows of the source array.
+ * st_conv_gather_tp has the contract of st_conv_gather_tc with `plan` in place of `map`
+ * (st_conv_tp_supported: 3x3x3 maps, cin in {8,16,32}, cout a multiple of 8).                      */
+size_t st_conv_plan_bytes(int64_t n_out);
+int st_conv_plan_build(const int32_t *map, int64_t n_out, int ntaps, int64_t n_in, void *plan,
+                       size_t plan_bytes, void *stream);
+int st_conv_tp_supported(int ntaps, int cin, int cout);
+int st_conv_gather_tp(const float *in, int in_ld, const void *plan, int64_t n_out, int ntaps,
+                      const float *wprep, int cin, int cout, const float *scale, const float *shift,
+                      const float *residual, int res_ld, const float *in2, int in2_ld,
+                      const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
+
 /* Fused heads: the three SparseFC stacks (8->8,BN,ReLU, 8->4,BN,ReLU, 4->{1,3,2}), F.normalize,
  * exp(radius)*direction and argmax     smart_tree/model/model.py:83-85 ; model_blocks.py:258-282 ;
  *                                      smart_tree/model/model_inference.py:87-88

@@ -46,6 +46,11 @@ SIGNATURES = {
     "st_conv_tc_prepare": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "st_conv_gather_tc": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                     _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
+    "st_conv_plan_bytes": (_sz, [_i64]),
+    "st_conv_plan_build": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _sz, _p]),
+    "st_conv_tp_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "st_conv_gather_tp": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
+                                    _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
     "st_heads_fused": (C.c_int, [_p, C.c_int, _i64, _p, _p, _p, _p, _p, _p, _p, _p]),
     "st_knn_workspace_bytes": (_sz, [_i64]),
     "st_knn": (C.c_int, [_p, _i64, _p, _i64, C.c_int, _f, _p, _p, _p, _p, _sz, _p]),

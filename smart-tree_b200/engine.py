@@ -78,6 +78,15 @@ class LevelIndex:
         self.nbr = ops.subm_map(coords, self.table)
         self.down = None
         self.up = None
+        self._plans = {}
+
+    def plan(self, name, n_in):
+        """Tile plan (distinct source rows + local map per 128-row tile) of gather map `name`, built on first use
+        and shared by every conv of the level that gathers through that map."""
+        p = self._plans.get(name)
+        if p is None:
+            p = self._plans[name] = ops.conv_plan_build(getattr(self, name), n_in)
+        return p
 
 
 def build_levels(coords: torch.Tensor, depth: int, morton: bool = False) -> List[LevelIndex]:
@@ -94,9 +103,12 @@ def build_levels(coords: torch.Tensor, depth: int, morton: bool = False) -> List
 class SmartTreeEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = None):
         import os
-        # "auto": tensor cores (tcgen05) where they win on B200 -- every 3x3x3 layer with >= 16 input or
-        # output channels; the 8 -> 8 layers are bound by the L1 line-visit rate either way (tools/conv_micro.py:
-        # 85 us fma vs 87 us tc) and stay on the FMA kernel
+        # "auto": tensor cores (tcgen05, per-thread gathers) where they win on B200 -- every 3x3x3 layer with >= 16
+        # input or output channels; the 8 -> 8 layers stay on the FMA kernel (tools/conv_micro.py: 85 us fma vs 87 tc).
+        # "tp": the tile-plan kernel (source rows of a 128-row tile staged in shared memory by bulk copies) for the
+        # sub-manifold and inverse convs with <= 32 input channels.  Measured equal to "tc" per launch (both are
+        # bound by the producer <-> MMA handshake, not by the gather: DESIGN.md section 4) and it pays for the plan
+        # builds, so it is opt-in (ST_CONV_IMPL=tp), kept parity-tested
         conv_impl = conv_impl or os.environ.get("ST_CONV_IMPL", "auto")
         sd = {k: v.detach().cpu() for k, v in state_dict.items() if not k.endswith("num_batches_tracked")}
         self.device = torch.device(device)
@@ -164,37 +176,44 @@ class SmartTreeEngine:
         return torch.cat([c.float().reshape(-1).to(self.device) for c in chunks]).contiguous()
 
     # ---- execution
-    def _conv(self, x, layer: ConvLayer, nbr, n_out, relu, out=None, residual=None, in2=None, w2=None):
+    def _conv(self, x, layer: ConvLayer, nbr, n_out, relu, out=None, residual=None, in2=None, w2=None, lv=None, which=None):
+        """`lv`/`which` name the LevelIndex map behind `nbr` ("nbr" | "up"): with them the conv may take the
+        tile-plan path (source rows staged in shared memory)."""
         taps, cin, cout = layer.w.shape
-        use_tc = (self.conv_impl == "tc" or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and taps > 1 and ops.conv_tc_supported(taps, cin, cout)
+        impl, plan = "fma", None
+        if taps > 1:
+            if self.conv_impl == "tp" and lv is not None and ops.conv_tp_supported(taps, cin, cout):
+                impl, plan = "tp", lv.plan(which, x.shape[0])
+            elif (self.conv_impl in ("tc", "tp") or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and ops.conv_tc_supported(taps, cin, cout):
+                impl = "tc"
         return ops.conv_gather(x, nbr, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2,
-                               out=out, relu=relu, impl="tc" if use_tc else "fma", weight_tc=layer.tc_weights() if use_tc else None)
+                               out=out, relu=relu, impl=impl, weight_tc=layer.tc_weights() if impl != "fma" else None, plan=plan)
 
-    def _resblock_run(self, x, rb: ResBlockPlan, nbr, out):
+    def _resblock_run(self, x, rb: ResBlockPlan, lv, out):
         n = x.shape[0]
-        t = self._conv(x, rb.c1, nbr, n, relu=True)
+        t = self._conv(x, rb.c1, lv.nbr, n, relu=True, lv=lv, which="nbr")
         if rb.ident_w is None:
-            return self._conv(t, rb.c2, nbr, n, relu=True, out=out, residual=x)
-        return self._conv(t, rb.c2, nbr, n, relu=True, out=out, in2=x, w2=rb.ident_w)
+            return self._conv(t, rb.c2, lv.nbr, n, relu=True, out=out, residual=x, lv=lv, which="nbr")
+        return self._conv(t, rb.c2, lv.nbr, n, relu=True, out=out, in2=x, w2=rb.ident_w, lv=lv, which="nbr")
 
     def _ublock(self, x, li, levels, trace, pre="UNet."):
         lp, lv = self.levels[li], levels[li]
         n, c = lv.n, self.planes[li]
         if lp.encode is None:
-            y = self._resblock_run(x, lp.head, lv.nbr, None)
+            y = self._resblock_run(x, lp.head, lv, None)
             if trace is not None:
                 trace[pre + "Head"] = y
             return y
         cat = torch.empty((n, 2 * c), dtype=F32, device=x.device)
         skip = cat[:, :c]
-        self._resblock_run(x, lp.head, lv.nbr, skip)
+        self._resblock_run(x, lp.head, lv, skip)
         nxt = levels[li + 1]
         y = self._conv(skip, lp.encode, lv.down, nxt.n, relu=True)
         if trace is not None:
             trace[pre + "Head"] = skip.clone(); trace[pre + "Encode"] = y
         y = self._ublock(y, li + 1, levels, trace, pre + "U.")
-        self._conv(y, lp.decode, lv.up, n, relu=True, out=cat[:, c:])
-        out = self._resblock_run(cat, lp.tail, lv.nbr, None)
+        self._conv(y, lp.decode, lv.up, n, relu=True, out=cat[:, c:], lv=lv, which="up")
+        out = self._resblock_run(cat, lp.tail, lv, None)
         if trace is not None:
             trace[pre + "Decode"] = cat[:, c:].clone(); trace[pre + "Tail"] = out
         return out

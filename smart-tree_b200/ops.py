@@ -16,7 +16,7 @@ LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1}
+                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1}
 
 
 def _count(op):
@@ -206,10 +206,28 @@ def conv_tc_prepare(weight):
     return wprep
 
 
+def conv_tp_supported(ntaps, cin, cout):
+    return bool(_lib.load().st_conv_tp_supported(ntaps, cin, cout))
+
+
+def conv_plan_build(nbr_map, n_in):
+    """Tile plan of a gather map [ntaps, n_out] into a source array of n_in rows (st_conv_plan_build):
+    distinct source rows + 16-bit local map per 128-row tile, for conv_gather(..., impl="tp")."""
+    lib = _lib.load()
+    _req(nbr_map, I32, "map")
+    ntaps, n_out = nbr_map.shape
+    plan = torch.empty(max(lib.st_conv_plan_bytes(n_out), 256), dtype=U8, device=nbr_map.device)
+    _count("plan")
+    _lib.check(lib.st_conv_plan_build(_ptr(nbr_map), n_out, ntaps, n_in, _ptr(plan), plan.numel(), _stream()), "st_conv_plan_build")
+    return plan
+
+
 def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=None, in2=None, w2=None,
-                out=None, relu=False, impl="fma", weight_tc=None):
+                out=None, relu=False, impl="fma", weight_tc=None, plan=None):
     """out[i] = act(scale * sum_k W[k] . in[map[k,i]] + shift + residual[i] + w2 . in2[i]).
-    weight [ntaps, cin, cout]; nbr_map [ntaps, n_out] i32 or None (identity, ntaps == 1)."""
+    weight [ntaps, cin, cout]; nbr_map [ntaps, n_out] i32 or None (identity, ntaps == 1).
+    impl: "fma" | "tc" (tcgen05, per-thread gathers) | "tp" (tcgen05, shared-memory staged tiles; needs
+    plan = conv_plan_build(nbr_map, inp.shape[0]))."""
     lib = _lib.load()
     _req_rows(inp, "inp"); _req(weight, F32, "weight")
     ntaps, cin, cout = weight.shape
@@ -225,16 +243,22 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
     if in2 is not None:
         _req_rows(in2, "in2"); _req(w2, F32, "w2")
     fn, wptr = lib.st_conv_gather, weight
-    if impl == "tc":
+    mptr = nbr_map
+    if impl in ("tc", "tp"):
         if weight_tc is None:
             weight_tc = conv_tc_prepare(weight)
         fn, wptr = lib.st_conv_gather_tc, weight_tc
+        if impl == "tp":
+            if plan is None:
+                plan = conv_plan_build(nbr_map, inp.shape[0])
+            _req(plan, U8, "plan")
+            fn, mptr = lib.st_conv_gather_tp, plan
     _count("conv")
     prof = _conv_profile
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    _lib.check(fn(_ptr(inp), _ld(inp), _ptr(nbr_map), n_out, ntaps, _ptr(wptr), cin, cout, _ptr(scale), _ptr(shift),
+    _lib.check(fn(_ptr(inp), _ld(inp), _ptr(mptr), n_out, ntaps, _ptr(wptr), cin, cout, _ptr(scale), _ptr(shift),
                   _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (w2.shape[0] if w2 is not None else 0),
                   _ptr(out), _ld(out), 1 if relu else 0, _stream()), "st_conv_gather")
     if prof is not None:

@@ -151,11 +151,15 @@ CONV_CASES = [(8, 8), (8, 16), (16, 8), (16, 16), (16, 32), (32, 16), (32, 32), 
 
 
 @pytest.mark.parametrize("cin,cout", CONV_CASES)
-@pytest.mark.parametrize("impl", ["fma", "tc"])
+@pytest.mark.parametrize("impl", ["fma", "tc", "tp"])
 def test_conv_gather_matches_oracle(cin, cout, impl):
+    """Rows in random order: for "tp" almost every tile has more distinct source rows than the staging buffer
+    holds, i.e. this exercises the 16-row sub-tile split of the tile plan."""
     ops = _ops()
     if impl == "tc" and not ops.conv_tc_supported(27, cin, cout):
         pytest.skip("channel counts outside the tensor-core path")
+    if impl == "tp" and not ops.conv_tp_supported(27, cin, cout):
+        pytest.skip("channel counts outside the tile-plan path")
     rng = np.random.default_rng(cin * 100 + cout)
     c = _random_coords(rng, 3000, 14)
     n = len(c)
@@ -171,7 +175,36 @@ def test_conv_gather_matches_oracle(cin, cout, impl):
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
 
 
-def test_conv_slices_and_fused_identity():
+@pytest.mark.parametrize("cin,cout", [(8, 8), (16, 8), (16, 16), (32, 16), (32, 32)])
+@pytest.mark.parametrize("n,extent", [(40000, 48), (300, 40), (129, 6)])
+def test_conv_tile_plan_z_order(cin, cout, n, extent):
+    """Tile-plan path on Z-ordered rows (whole tiles staged in shared memory: the production case), on a
+    sparse cloud (few neighbours) and on a ragged last tile; plan reused across two convs; also checked
+    bit for bit against the per-thread-gather tensor-core kernel (same arithmetic, different staging)."""
+    ops = _ops()
+    rng = np.random.default_rng(n + cin + cout)
+    c = _random_coords(rng, n, extent)
+    perm = ops.morton_perm(_t(c, torch.int32)).cpu().numpy()
+    c = c[perm]
+    n = len(c)
+    nbr = U.subm_map(c)
+    x = rng.standard_normal((n, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 2, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    ref = np.maximum(U.gather_conv(x.astype(np.float64), w, nbr, n) * scale + shift, 0)
+    wt = torch.from_numpy(w).reshape(cout, 27, cin).permute(1, 2, 0).contiguous().to(DEV)
+    nbr_d = _t(nbr, torch.int32)
+    plan = ops.conv_plan_build(nbr_d, n)
+    for _ in range(2):
+        out = ops.conv_gather(_t(x), nbr_d, wt, n, _t(scale), _t(shift), relu=True, impl="tp", plan=plan)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+    tc = ops.conv_gather(_t(x), nbr_d, wt, n, _t(scale), _t(shift), relu=True, impl="tc")
+    assert torch.equal(out, tc)
+
+
+@pytest.mark.parametrize("impl", ["fma", "tp"])
+def test_conv_slices_and_fused_identity(impl):
     """Reads from / writes into column slices of the concat buffer, fused 1x1 identity conv."""
     ops = _ops()
     rng = np.random.default_rng(5)
@@ -184,7 +217,7 @@ def test_conv_slices_and_fused_identity():
     catd = _t(cat)
     outbuf = torch.zeros((n, 32), device=DEV)
     wt = torch.from_numpy(w).reshape(16, 27, 16).permute(1, 2, 0).contiguous().to(DEV)
-    ops.conv_gather(catd[:, 16:], _t(nbr, torch.int32), wt, n, in2=catd, w2=_t(w2), out=outbuf[:, :16], relu=True)
+    ops.conv_gather(catd[:, 16:], _t(nbr, torch.int32), wt, n, in2=catd, w2=_t(w2), out=outbuf[:, :16], relu=True, impl=impl)
     ref = np.maximum(U.gather_conv(cat[:, 16:].astype(np.float64), w, nbr, n) + cat.astype(np.float64) @ w2, 0)
     np.testing.assert_allclose(outbuf[:, :16].cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * np.abs(ref).max())
     assert torch.all(outbuf[:, 16:] == 0)
@@ -236,7 +269,7 @@ def _rel_close(got, ref, tol=1e-3, unit_rows=False):
     return err
 
 
-@pytest.mark.parametrize("impl", ["fma", "tc", "auto"])
+@pytest.mark.parametrize("impl", ["fma", "tc", "tp", "auto"])
 @pytest.mark.parametrize("weights", ["noble-elevator-58", "peach-forest-65", "random"])
 def test_unet_forward_matches_oracle(weights, impl):
     from smart_tree_b200.engine import SmartTreeEngine

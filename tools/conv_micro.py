@@ -1,5 +1,5 @@
 """Micro-benchmark of the gather-conv kernels on the level shapes of the bench workload
-(one synthetic 1M-point tree -> ~495k voxels).  Usage: python tools/conv_micro.py [fma|tc] [cin cout level]"""
+(one synthetic 1M-point tree -> ~495k voxels).  Usage: python tools/conv_micro.py [fma|tc|tp] [cin cout level]"""
 import os
 import sys
 
@@ -29,20 +29,29 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 cases = [(8, 8, 0), (16, 8, 0), (16, 16, 1), (32, 16, 1), (32, 32, 2), (64, 32, 2), (64, 64, 3)]
 if only:
     cases = [only]
+if os.environ.get("ST_TC_DBG"):
+    from smart_tree_b200 import _lib as _l
+    _l.load().st_debug_tc_set(int(os.environ["ST_TC_DBG"]))
 for cin, cout, li in cases:
     lv = levels[li]
     x = torch.randn(lv.n, cin, device=dev)
     w = torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5
-    wtc = ops.conv_tc_prepare(w) if impl == "tc" else None
+    wtc = ops.conv_tc_prepare(w) if impl in ("tc", "tp") else None
+    plan = ops.conv_plan_build(lv.nbr, lv.n) if impl == "tp" else None
+    if plan is not None:
+        import numpy as _np
+        nb = (lv.n + 127) // 128
+        hdr = plan[:nb * 48].view(torch.int32).reshape(nb, 12).cpu().numpy()
+        print(f"  plan: {nb} tiles, {int(hdr[:, 0].sum())} split, distinct rows mean {hdr[hdr[:, 0] == 0, 1].mean():.0f} max {hdr[:, 1:9].max()}")
     out = torch.empty(lv.n, cout, device=dev)
     for _ in range(3):
-        ops.conv_gather(x, lv.nbr, w, lv.n, out=out, relu=True, impl=impl, weight_tc=wtc)
+        ops.conv_gather(x, lv.nbr, w, lv.n, out=out, relu=True, impl=impl, weight_tc=wtc, plan=plan)
     ts = []
     for _ in range(10):
         flush.fill_(1)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ops.conv_gather(x, lv.nbr, w, lv.n, out=out, relu=True, impl=impl, weight_tc=wtc)
+        ops.conv_gather(x, lv.nbr, w, lv.n, out=out, relu=True, impl=impl, weight_tc=wtc, plan=plan)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
@@ -50,15 +59,22 @@ for cin, cout, li in cases:
     byt = 4 * lv.n * (cin + cout)
     print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s  ({byt / us / 1e3 / 6525.2 * 100:5.2f}% of measured HBM peak)")
 
-if only and impl == "tc":
+if only and impl in ("tc", "tp"):
     import ctypes as C
     from smart_tree_b200 import _lib
     lib = _lib.load()
-    buf = (C.c_longlong * 320)()
+    buf = (C.c_longlong * 1024)()
     lib.st_debug_tc_trace.argtypes = [C.c_void_p]
     lib.st_debug_tc_trace(buf)
-    t = np.array(buf[:]).reshape(5, 64)
-    t0 = t[0, 0]
-    names = ["prod: a_empty ok", "prod: arrived   ", "mma : a_full ok ", "mma : committed ", "mma : b_full ok "]
-    for g in range(0, 24):
-        print(g, "  ".join(f"{names[k].strip()}={t[k, g] - t0:7d}" for k in (0, 1, 4, 2, 3)))
+    t = np.array(buf[:]).reshape(8, 128)
+    t0 = t[6, 0]
+    ns = -(-27 * only[0] // 32)
+    print("traced CTA", os.environ.get("ST_TC_DBG", "0"), "stages per tile", ns)
+    print(f"kernel span of this CTA: {t[5, 122] - t[5, 120]} ns = {t[5, 123] - t[5, 121]} cycles; entry -> first P.start {t0 - t[5, 121]} cycles; entry -> after TMEM alloc {t[5, 124] - t[5, 121]}; last arrive -> exit {t[5, 123] - t[1, :].max()}")
+    for tile in range(0, 128 // ns):
+        g0, g1 = tile * ns, tile * ns + ns - 1
+        if t[6, g0] == 0:
+            break
+        st = np.diff(t[6, g0:g1 + 1])
+        print(f"tile {tile}: start {t[6, g0] - t0:7d}  f_wait {t[5, g0] - t0:7d} f_ok {t[5, g0 + 1] - t0:7d}  last arrive {t[1, g1] - t0:7d}  "
+              f"mma first b_full {t[4, g0] - t0:7d} a_full {t[2, g0] - t0:7d} last commit {t[3, g1] - t0:7d}  stage min/med/max {st.min()}/{int(np.median(st))}/{st.max()}")
