@@ -52,6 +52,44 @@ __device__ __forceinline__ int cell_coord(float v, float o, float inv_h, int n) 
     return max(0, min(n - 1, c));
 }
 
+// Visits the grid rows (runs of cells along x) that can hold a point within sqrt(lim2) of q, NEAREST ROWS FIRST
+// (cell offsets 0, +1, -1, +2, ... in z and y), and hands each row's range of the cell-sorted array to
+// row_fn(beg, end).  row_fn may shrink lim2 (e.g. to the K-th best squared distance found so far): rows and
+// cells that lie farther than that are skipped, so in a dense neighbourhood only a few cells are ever read.
+// Bounds are conservative (binning is monotone; `slack` covers its rounding): no point with d2 <= lim2 is missed.
+template <typename F>
+__device__ __forceinline__ void for_rows_near_first(const Grid &g, const int32_t *__restrict__ cell_start, float qx, float qy, float qz,
+                                                    float reach, float &lim2, F &&row_fn) {
+    const float rr = reach * 1.0001f + 1e-7f;
+    const int x0 = cell_coord(qx - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(qx + rr, g.ox, g.inv_h, g.nx);
+    const int y0 = cell_coord(qy - rr, g.oy, g.inv_h, g.ny), y1 = cell_coord(qy + rr, g.oy, g.inv_h, g.ny);
+    const int z0 = cell_coord(qz - rr, g.oz, g.inv_h, g.nz), z1 = cell_coord(qz + rr, g.oz, g.inv_h, g.nz);
+    const int cyq = cell_coord(qy, g.oy, g.inv_h, g.ny), czq = cell_coord(qz, g.oz, g.inv_h, g.nz);
+    const float slack = 1e-4f * g.h + 1e-6f;
+    const int nz2 = 2 * max(czq - z0, z1 - czq), ny2 = 2 * max(cyq - y0, y1 - cyq);
+    for (int az = 0; az <= nz2; ++az) {
+        const int cz = czq + ((az & 1) ? ((az + 1) >> 1) : -((az + 1) >> 1));
+        if (cz < z0 || cz > z1) continue;
+        float dz = 0.f;
+        if (cz > czq) dz = fmaxf(0.f, (g.oz + (float)cz * g.h - slack) - qz);
+        else if (cz < czq) dz = fmaxf(0.f, qz - (g.oz + (float)(cz + 1) * g.h + slack));
+        if (dz * dz > lim2 * 1.00001f) continue;
+        for (int ay = 0; ay <= ny2; ++ay) {
+            const int cy = cyq + ((ay & 1) ? ((ay + 1) >> 1) : -((ay + 1) >> 1));
+            if (cy < y0 || cy > y1) continue;
+            float dy = 0.f;
+            if (cy > cyq) dy = fmaxf(0.f, (g.oy + (float)cy * g.h - slack) - qy);
+            else if (cy < cyq) dy = fmaxf(0.f, qy - (g.oy + (float)(cy + 1) * g.h + slack));
+            const float rem = lim2 * 1.00001f - dz * dz - dy * dy;
+            if (rem < 0.f) continue;
+            const float half = sqrtf(rem) * 1.0001f + slack;
+            const int xa = max(x0, cell_coord(qx - half, g.ox, g.inv_h, g.nx)), xb = min(x1, cell_coord(qx + half, g.ox, g.inv_h, g.nx));
+            const int rowc = (cz * g.ny + cy) * g.nx;
+            row_fn(__ldg(cell_start + rowc + xa), __ldg(cell_start + rowc + xb + 1));      // cells contiguous in x
+        }
+    }
+}
+
 static __global__ void k_cell_count(const float *__restrict__ p, int m, Grid g, int32_t *__restrict__ cell_of, int32_t *count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;

@@ -36,33 +36,32 @@ __global__ void __launch_bounds__(128) k_knn(const float *__restrict__ src, int 
     int bi[K];
 #pragma unroll
     for (int s = 0; s < K; ++s) { bd[s] = FLT_MAX; bi[s] = INT_MAX; }
-    // cells overlapped by the ball (one extra ulp-safe margin)
+    // Rows of cells nearest first; once K candidates are known the search radius shrinks to the K-th best, so in
+    // the dense parts of the cloud (thousands of medial points within r of a trunk vertex) only the few cells
+    // around the query are read.  Ties at the K-th distance stay reachable (rows are skipped only when strictly
+    // farther), so the result is the exact ascending (d2, index) top-K.
     float rr = reach * 1.0001f + 1e-7f;
-    int x0 = cell_coord(qx - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(qx + rr, g.ox, g.inv_h, g.nx);
-    int y0 = cell_coord(qy - rr, g.oy, g.inv_h, g.ny), y1 = cell_coord(qy + rr, g.oy, g.inv_h, g.ny);
-    int z0 = cell_coord(qz - rr, g.oz, g.inv_h, g.nz), z1 = cell_coord(qz + rr, g.oz, g.inv_h, g.nz);
-    for (int cz = z0; cz <= z1; ++cz)
-        for (int cy = y0; cy <= y1; ++cy) {
-            int rowc = (cz * g.ny + cy) * g.nx;
-            int beg = __ldg(cell_start + rowc + x0), end = __ldg(cell_start + rowc + x1 + 1);  // cells contiguous in x
-            for (int t = beg; t < end; ++t) {
-                float4 p = __ldg(sorted + t);
-                float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                if (!(d2 < r2)) continue;
-                if (qrad && sqrtf(d2) > qr) continue;
-                int j = __float_as_int(p.w);
-                if (!cand_less(d2, j, bd[K - 1], bi[K - 1])) continue;
+    float lim2 = rr * rr;
+    for_rows_near_first(g, cell_start, qx, qy, qz, reach, lim2, [&](int beg, int end) {
+        for (int t = beg; t < end; ++t) {
+            float4 p = __ldg(sorted + t);
+            float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+            if (!(d2 < r2)) continue;
+            if (qrad && sqrtf(d2) > qr) continue;
+            int j = __float_as_int(p.w);
+            if (!cand_less(d2, j, bd[K - 1], bi[K - 1])) continue;
 #pragma unroll
-                for (int s = K - 1; s >= 0; --s) {
-                    bool lt_prev = (s > 0) && cand_less(d2, j, bd[s > 0 ? s - 1 : 0], bi[s > 0 ? s - 1 : 0]);
-                    bool lt_cur = cand_less(d2, j, bd[s], bi[s]);
-                    float nd = lt_prev ? bd[s > 0 ? s - 1 : 0] : (lt_cur ? d2 : bd[s]);
-                    int ni = lt_prev ? bi[s > 0 ? s - 1 : 0] : (lt_cur ? j : bi[s]);
-                    bd[s] = nd;
-                    bi[s] = ni;
-                }
+            for (int s = K - 1; s >= 0; --s) {
+                bool lt_prev = (s > 0) && cand_less(d2, j, bd[s > 0 ? s - 1 : 0], bi[s > 0 ? s - 1 : 0]);
+                bool lt_cur = cand_less(d2, j, bd[s], bi[s]);
+                float nd = lt_prev ? bd[s > 0 ? s - 1 : 0] : (lt_cur ? d2 : bd[s]);
+                int ni = lt_prev ? bi[s > 0 ? s - 1 : 0] : (lt_cur ? j : bi[s]);
+                bd[s] = nd;
+                bi[s] = ni;
             }
         }
+        if (bi[K - 1] != INT_MAX) lim2 = fminf(lim2, bd[K - 1]);
+    });
 #pragma unroll
     for (int s = 0; s < K; ++s) {
         bool ok = bi[s] != INT_MAX;
@@ -118,20 +117,16 @@ __global__ void __launch_bounds__(128) k_outlier(const float *__restrict__ pts, 
     float reach = fminf(r, qr);
     int cnt = 0;
     if (reach > 0.f) {
-        float rr = reach * 1.0001f + 1e-7f;
-        int x0 = cell_coord(qx - rr, g.ox, g.inv_h, g.nx), x1 = cell_coord(qx + rr, g.ox, g.inv_h, g.nx);
-        int y0 = cell_coord(qy - rr, g.oy, g.inv_h, g.ny), y1 = cell_coord(qy + rr, g.oy, g.inv_h, g.ny);
-        int z0 = cell_coord(qz - rr, g.oz, g.inv_h, g.nz), z1 = cell_coord(qz + rr, g.oz, g.inv_h, g.nz);
-        for (int cz = z0; cz <= z1 && cnt < nb; ++cz)
-            for (int cy = y0; cy <= y1 && cnt < nb; ++cy) {
-                int rowc = (cz * g.ny + cy) * g.nx;
-                int beg = __ldg(cell_start + rowc + x0), end = __ldg(cell_start + rowc + x1 + 1);
-                for (int t = beg; t < end && cnt < nb; ++t) {
-                    float4 p = __ldg(sorted + t);
-                    float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
-                    if (d2 < r2 && sqrtf(d2) < qr) ++cnt;
-                }
+        const float rr = reach * 1.0001f + 1e-7f;
+        float lim2 = rr * rr;
+        for_rows_near_first(g, cell_start, qx, qy, qz, reach, lim2, [&](int beg, int end) {
+            for (int t = beg; t < end && cnt < nb; ++t) {
+                float4 p = __ldg(sorted + t);
+                float d2 = dist2_exact(qx, qy, qz, p.x, p.y, p.z);
+                if (d2 < r2 && sqrtf(d2) < qr) ++cnt;
             }
+            if (cnt >= nb) lim2 = -1.f;       // enough neighbours found: skip every remaining row
+        });
     }
     keep[i] = cnt >= nb ? 1 : 0;
 }
