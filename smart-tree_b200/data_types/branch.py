@@ -51,3 +51,48 @@ class BranchSkeleton:
     @property
     def biggest_radius(self):
         return torch.max(self.radii)
+
+
+class PackedBranchSkeleton(BranchSkeleton):
+    """A branch whose nodes are rows [start, start+count) of one packed host array shared by the whole result
+    (nodes[R,3], radii[R]): `xyz` / `radii` are sliced out on first access instead of when the skeleton is
+    assembled (a few hundred to thousands of branches per tree; a tensor view costs ~1 us of host time each).
+    Same attributes, methods and shapes as BranchSkeleton; assigning xyz / radii replaces the view."""
+
+    def __init__(self, _id, parent_id, nodes, radii, start, count, radii_1d=False):
+        self._id = _id
+        self.parent_id = parent_id
+        self.child_id = None
+        self._flat = None
+        self._src = (nodes, radii, start, count, radii_1d)
+        self._xyz = None
+        self._radii = None
+
+    def __len__(self):
+        return self._src[3] if self._xyz is None else self._xyz.shape[0]
+
+    @property
+    def xyz(self):
+        if self._xyz is None:
+            nodes, _, s, c, _ = self._src
+            self._xyz = nodes[s:s + c]
+        return self._xyz
+
+    @xyz.setter
+    def xyz(self, v):
+        self._xyz = v
+
+    @property
+    def radii(self):
+        if self._radii is None:
+            _, rad, s, c, one_d = self._src
+            r = rad[s:s + c]
+            self._radii = r if one_d else r.unsqueeze(1)      # smoothed radii are 1-D (quirk C-17)
+        return self._radii
+
+    @radii.setter
+    def radii(self, v):
+        self._radii = v
+
+    def __repr__(self):
+        return f"BranchSkeleton(_id={self._id}, parent_id={self.parent_id}, nodes={len(self)})"

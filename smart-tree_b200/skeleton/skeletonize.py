@@ -38,7 +38,7 @@ class Skeletonizer:
         `post` = dict(prune=(min_radius, min_length) | None, repair=bool, smooth=kernel_size) or None."""
         import numpy as np
 
-        from ..data_types.branch import BranchSkeleton
+        from ..data_types.branch import BranchSkeleton, PackedBranchSkeleton
         from ..data_types.tree import NodeStore
         post = post or {}
         prune = post.get("prune")
@@ -76,15 +76,13 @@ class Skeletonizer:
             sm_row = np.repeat((flags[kept] & 4) != 0, cnt)
             packed = nodes[torch.from_numpy(rows)]
             radcol = torch.where(torch.from_numpy(sm_row), smooth[torch.from_numpy(rows)], packed[:, 3])
+            xyz_all = packed[:, :3]
+            starts = (csum - cnt).tolist()
             sizes = cnt.tolist()
-            xyz_views = packed[:, :3].split(sizes)
-            rad_views = radcol.split(sizes)
             for i in range(len(rows_l)):
-                # smoothed radii are 1-D (quirk C-17), untouched ones [N,1]
-                br = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i].unsqueeze(1))
-                if flags_l[i] & 4:
-                    br.radii = rad_views[i]
-                per_comp[comp_l[i]][bid_l[i]] = br
+                # per-branch views are cut on first access (PackedBranchSkeleton)
+                per_comp[comp_l[i]][bid_l[i]] = PackedBranchSkeleton(bid_l[i], pars_l[i], xyz_all, radcol, starts[i], sizes[i],
+                                                                      radii_1d=bool(flags_l[i] & 4))
             return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
         # plain assembly: keep the spare rows (object-level repair writes the connection points there)
         gaps = np.empty(2 * len(kept) + 1, np.int64)
