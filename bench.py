@@ -216,6 +216,8 @@ def run_b200(args):
     dev_ms, wall_ms, sk, steps_res = timed(True, args.steps)
     launches = ops.LAUNCHES - launches0
     stage_t = dict(pipe.timings)
+    for _ in range(min(args.warmup, 2)):          # the host-buffer path warms up too (fresh device buffers every step)
+        step(False)
     e2e_ms, e2e_wall_ms, sk2, steps_e2e = timed(False, args.steps)
     clk = clocks.stop() if rank == 0 else None
     # the device timeline includes host gaps (the step has host sync points), so device-event time == step time
@@ -262,8 +264,15 @@ def run_b200(args):
         top = max(table, key=lambda k: table[k]["ms_per_forward"])
         tot_ms = sum(v["ms"] for v in per.values()) / reps
         tot_b = sum(v["bytes"] for v in per.values()) / reps
+        traffic, traffic_src = None, None
+        try:          # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/README.md)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if top in tj:
+                traffic, traffic_src = tj[top]["dram_bytes_per_launch"], "profiles/ncu_conv_r1c.csv (dram__bytes_read.sum + dram__bytes_write.sum)"
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": top, "achieved": table[top]["gbps"], "peak": peak, "unit": "GB/s",
-                "frac": table[top]["gbps"] / peak, "traffic": None, "peak_source": peak_kind,
+                "frac": table[top]["gbps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                 "all_gather_convs": {"achieved": tot_b / tot_ms / 1e6, "frac": tot_b / tot_ms / 1e6 / peak, "ms_per_forward": tot_ms},
                 "per_kernel": table, "level_voxels": [lv.n for lv in levels]}
 

@@ -136,6 +136,14 @@ int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out
  * counts: cin must divide 32 or be a multiple of 32, cout a multiple of 8) and `map` is mandatory.   */
 int64_t st_conv_tc_weight_floats(int ntaps, int cin, int cout);
 int st_conv_tc_prepare(const float *w, int ntaps, int cin, int cout, float *wprep, void *stream);
+/* Fused ResBlock identity (model_blocks.py:148-156: ReLU(BN(conv(t)) + identity_1x1(x))): st_conv_tc_prepare_fused
+ * appends w2[cin2,cout] / scale as extra K stages to the prepared weights, and st_conv_gather_tc called with
+ * in2 != NULL and w2 == NULL walks them through the identity map, so the 1x1 conv runs on the tensor cores
+ * inside the same accumulation instead of as a per-thread FMA loop in the epilogue.  cin2 % 16 == 0;
+ * every scale[c] must be non-zero (the caller checks; otherwise pass w2 to keep the epilogue form).           */
+int64_t st_conv_tc_weight_floats_fused(int ntaps, int cin, int cout, int cin2);
+int st_conv_tc_prepare_fused(const float *w, int ntaps, int cin, int cout, const float *w2, int cin2,
+                             const float *scale, float *wprep, void *stream);
 int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps,
                       const float *wprep, int cin, int cout, const float *scale, const float *shift,
                       const float *residual, int res_ld, const float *in2, int in2_ld,

@@ -44,6 +44,8 @@ SIGNATURES = {
                                  _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
     "st_conv_tc_weight_floats": (_i64, [C.c_int, C.c_int, C.c_int]),
     "st_conv_tc_prepare": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "st_conv_tc_weight_floats_fused": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "st_conv_tc_prepare_fused": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p, _p]),
     "st_conv_gather_tc": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                     _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
     "st_conv_plan_bytes": (_sz, [_i64]),

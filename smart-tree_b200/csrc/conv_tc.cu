@@ -170,6 +170,7 @@ struct TcArgs {
     float *out;
     int out_ld;
     int act;
+    int nstages_main;     // stages that walk the taps; the rest (fused identity) walk the channels of in2
 };
 
 template <int CIN>
@@ -241,7 +242,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
         // 32-row quadrant -- exactly the fragment tcgen05.st.16x256b scatters into TMEM lanes.
         const int gq = lane >> 2, q4 = lane & 3;
         const int rq = 32 * (warp & 3) + gq;
+        int tile_row0 = 0;
         auto load_rows = [&](int buf, int s, float4 (&x)[4]) {
+            if (s >= a.nstages_main) {
+                // fused ResBlock identity: K continues over the channels of in2, gathered through the identity map
+                // (row i reads in2[i]); its 1x1 weights, pre-divided by the BN scale, follow the taps in wprep
+                const int c = (s - a.nstages_main) * TC_KS + 16 * half + 4 * q4;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int r = tile_row0 + rq + 8 * j;
+                    x[j] = (r < a.n_out && c < a.cin2) ? __ldg((const float4 *)(a.in2 + (size_t)r * a.in2_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                return;
+            }
             int t0, c0;
             taps_of(s, t0, c0);
             const int tap = CIN == 8 ? t0 + (q4 >> 1) : t0;
@@ -259,6 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
         map_ready();
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
             const int buf = tile_iter & 1;
+            tile_row0 = tile * TC_M;
             const int row = tile * TC_M + rloc;
             const bool row_ok = row < a.n_out;
             prefetch_map(tile + gridDim.x, buf ^ 1);
@@ -328,7 +342,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                     float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
                     v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
                 }
-                if (a.in2) {
+                if (a.in2 && a.w2) {
                     float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                     const float *xr = a.in2 + (size_t)row * a.in2_ld;
                     for (int ci = 0; ci < a.cin2; ++ci) {
@@ -423,13 +437,27 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
 
 // w [ntaps, cin, cout] -> wprep [nstages][2][npad*32]: per stage the K-major core-matrix tile of the
 // TF32 heads followed by the tile of the tails; K index kk = tap*cin + c, zero padded.
-__global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, int cout, int npad, int nstages, float *__restrict__ wprep) {
+__global__ void k_tc_prepare(const float *__restrict__ w, int ntaps, int cin, int cout, int npad, int nstages, float *__restrict__ wprep,
+                             const float *__restrict__ w2, int cin2, const float *__restrict__ scale, int nstages_main) {
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)nstages * npad * TC_KS;
     if (idx >= total) return;
     int s = (int)(idx / (npad * TC_KS));
     int rem = (int)(idx % (npad * TC_KS));
     int n = rem / TC_KS, kk = rem % TC_KS;
+    if (s >= nstages_main) {
+        // fused identity stages: logical K element = channel of in2; same fragment permutation as below
+        const int cc = kk & 15, q = (cc & 7) >> 1, m = (cc & 1) + ((cc >> 3) << 1);
+        const int c2 = (s - nstages_main) * TC_KS + (kk & 16) + 4 * q + m;
+        float v = (c2 < cin2 && n < cout) ? w2[(size_t)c2 * cout + n] / (scale ? scale[n] : 1.f) : 0.f;
+        float hi = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        float lo = v - hi;
+        size_t pos = (size_t)(n >> 3) * 256 + (size_t)(kk >> 2) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
+        float *tile = wprep + (size_t)s * 2 * npad * TC_KS;
+        tile[pos] = hi;
+        tile[(size_t)npad * TC_KS + pos] = lo;
+        return;
+    }
     // TMEM column kk of a stage holds logical K element 16*(kk/16) + 4*q + m, where the quad fragment puts
     // (q, m) at column 2q+m (m < 2) or 8+2q+(m-2) of its 16-column half (see load_rows / tmem_st_quad)
     const int cc = kk & 15, q = (cc & 7) >> 1, m = (cc & 1) + ((cc >> 3) << 1);
@@ -924,7 +952,25 @@ extern "C" int st_conv_tc_prepare(const float *w, int ntaps, int cin, int cout, 
     ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
     int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
     int64_t total = (int64_t)nst * npad * TC_KS;
-    k_tc_prepare<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, ntaps, cin, cout, npad, nst, wprep);
+    k_tc_prepare<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, ntaps, cin, cout, npad, nst, wprep, nullptr, 0, nullptr, nst);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// Weights of a conv with a FUSED ResBlock identity (out = act(scale * conv(in) + shift + w2 . in2)): the 1x1 identity
+// weights w2[cin2, cout], divided by the BN scale, are appended as extra K stages, so the tensor cores compute
+// scale * (conv(in) + (w2 / scale) . in2) + shift in one accumulation (st_conv_gather_tc with in2 != NULL, w2 == NULL).
+extern "C" int64_t st_conv_tc_weight_floats_fused(int ntaps, int cin, int cout, int cin2) {
+    if (!tc_supported(cin, cout) || cin2 <= 0 || cin2 % 16) return -1;
+    return (int64_t)(tc_nstages(ntaps, cin) + (cin2 + TC_KS - 1) / TC_KS) * 2 * tc_npad(cout) * TC_KS;
+}
+
+extern "C" int st_conv_tc_prepare_fused(const float *w, int ntaps, int cin, int cout, const float *w2, int cin2, const float *scale,
+                                        float *wprep, void *stream) {
+    ST_REQUIRE(tc_supported(cin, cout) && cin2 > 0 && cin2 % 16 == 0 && w2 != nullptr, "channel counts not supported by the fused tensor-core path");
+    int npad = tc_npad(cout), nmain = tc_nstages(ntaps, cin), nst = nmain + (cin2 + TC_KS - 1) / TC_KS;
+    int64_t total = (int64_t)nst * npad * TC_KS;
+    k_tc_prepare<<<(unsigned)cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, ntaps, cin, cout, npad, nst, wprep, w2, cin2, scale, nmain);
     ST_CHECK_LAUNCH();
     return ST_OK;
 }
@@ -940,14 +986,17 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     ST_REQUIRE(((uintptr_t)in & 15) == 0 && in_ld % 4 == 0 && ((uintptr_t)out & 15) == 0 && out_ld % 4 == 0 && ((uintptr_t)wprep & 15) == 0,
                "16-byte aligned rows required");
     ST_REQUIRE(!residual || (((uintptr_t)residual & 15) == 0 && res_ld % 4 == 0), "residual alignment");
-    ST_REQUIRE(!in2 || (w2 && ((uintptr_t)w2 & 15) == 0), "in2 needs a 16-byte aligned w2");
-    const int npad = tc_npad(cout), nst = tc_nstages(ntaps, cin);
+    ST_REQUIRE(!in2 || !w2 || ((uintptr_t)w2 & 15) == 0, "w2 must be 16-byte aligned");
+    ST_REQUIRE(!in2 || (((uintptr_t)in2 & 15) == 0 && in2_ld % 4 == 0), "in2 alignment");
+    ST_REQUIRE(!in2 || w2 || cin2 % 16 == 0, "fused identity stages need cin2 % 16 == 0");
+    const int npad = tc_npad(cout), nmain = tc_nstages(ntaps, cin);
+    const int nst = nmain + ((in2 && !w2) ? (cin2 + TC_KS - 1) / TC_KS : 0);      // w2 == NULL: identity stages are inside wprep
     // weight ring: deep enough that the bulk copies are issued ~2000 cycles ahead of their MMAs
     const int b_stage = 2 * npad * TC_KS * 4;
     int sb = (npad <= 32 ? 40 * 1024 : 128 * 1024) / b_stage;
     sb = sb > TC_MAX_BSTAGES ? TC_MAX_BSTAGES : (sb < 2 ? 2 : sb);
     if (sb > nst) sb = nst;
-    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
+    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act, nmain};
     const int smem = sb * b_stage + 1024;
     static int n_sms = 0;
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }

@@ -42,6 +42,7 @@ class ConvLayer:
     scale: Optional[torch.Tensor] = None
     shift: Optional[torch.Tensor] = None
     w_tc: Optional[torch.Tensor] = None   # tensor-core layout (ops.conv_tc_prepare), built lazily on the device
+    w_tc_fused: object = None             # same with a fused identity 1x1 conv (tc_weights_fused)
 
     def to(self, dev):
         return ConvLayer(self.w.to(dev), None if self.scale is None else self.scale.to(dev),
@@ -51,6 +52,16 @@ class ConvLayer:
         if self.w_tc is None:
             self.w_tc = ops.conv_tc_prepare(self.w)
         return self.w_tc
+
+    def tc_weights_fused(self, w2):
+        """Tensor-core weights with the ResBlock identity 1x1 conv appended as extra K stages (ops.conv_tc_prepare_fused);
+        False if unsupported (shape, or a BN scale too close to zero to divide by)."""
+        if self.w_tc_fused is None:
+            ok = self.scale is None or bool((self.scale.abs() > 1e-6).all())
+            self.w_tc_fused = (ops.conv_tc_prepare_fused(self.w, w2, self.scale) if ok else None)
+            if self.w_tc_fused is None:
+                self.w_tc_fused = False
+        return self.w_tc_fused
 
 
 @dataclass
@@ -186,8 +197,13 @@ class SmartTreeEngine:
                 impl, plan = "tp", lv.plan(which, x.shape[0])
             elif (self.conv_impl in ("tc", "tp") or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and ops.conv_tc_supported(taps, cin, cout):
                 impl = "tc"
+        wtc = layer.tc_weights() if impl != "fma" else None
+        if impl == "tc" and in2 is not None:
+            fused = layer.tc_weights_fused(w2)          # identity 1x1 conv as extra K stages on the tensor cores
+            if fused is not False:
+                wtc, w2 = fused, None
         return ops.conv_gather(x, nbr, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2,
-                               out=out, relu=relu, impl=impl, weight_tc=layer.tc_weights() if impl != "fma" else None, plan=plan)
+                               out=out, relu=relu, impl=impl, weight_tc=wtc, plan=plan)
 
     def _resblock_run(self, x, rb: ResBlockPlan, lv, out):
         n = x.shape[0]
@@ -226,7 +242,7 @@ class SmartTreeEngine:
         if not self.morton:
             return build_levels(coords, self.depth)
         perm = ops.morton_perm(coords)
-        levels = build_levels(coords[perm.long()].contiguous(), self.depth, morton=True)
+        levels = build_levels(coords.index_select(0, perm), self.depth, morton=True)      # int32 index: no widening pass
         levels[0].perm = perm
         return levels
 
@@ -243,7 +259,7 @@ class SmartTreeEngine:
             levels = self.build_levels(coords)
         perm = getattr(levels[0], "perm", None)
         if perm is not None:
-            features = features[perm.long()]
+            features = features.index_select(0, perm)
         x = self._conv(features, self.stem, None, n, relu=True)
         if trace is not None:
             trace["input_conv"] = x

@@ -206,6 +206,25 @@ def conv_tc_prepare(weight):
     return wprep
 
 
+def conv_tc_prepare_fused(weight, w2, scale):
+    """Tensor-core weights of a conv with a fused ResBlock identity: weight [ntaps, cin, cout] followed by extra K
+    stages holding w2 [cin2, cout] / scale, so that conv_gather(..., impl="tc", in2=x, w2=None, weight_tc=this)
+    computes act(scale * conv(in) + shift + w2 . in2) in one accumulation.  None if the shapes are unsupported."""
+    lib = _lib.load()
+    _req(weight, F32, "weight"); _req(w2, F32, "w2")
+    ntaps, cin, cout = weight.shape
+    cin2 = w2.shape[0]
+    nfl = lib.st_conv_tc_weight_floats_fused(ntaps, cin, cout, cin2)
+    if nfl < 0:
+        return None
+    if scale is not None:
+        _req(scale, F32, "scale")
+    wprep = torch.empty(nfl, dtype=F32, device=weight.device)
+    _lib.check(lib.st_conv_tc_prepare_fused(_ptr(weight), ntaps, cin, cout, _ptr(w2), cin2, _ptr(scale), _ptr(wprep), _stream()),
+               "st_conv_tc_prepare_fused")
+    return wprep
+
+
 def conv_tp_supported(ntaps, cin, cout):
     return bool(_lib.load().st_conv_tp_supported(ntaps, cin, cout))
 
@@ -241,7 +260,11 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
     if residual is not None:
         _req_rows(residual, "residual")
     if in2 is not None:
-        _req_rows(in2, "in2"); _req(w2, F32, "w2")
+        _req_rows(in2, "in2")
+        if w2 is not None:
+            _req(w2, F32, "w2")
+        elif impl != "tc" or weight_tc is None:
+            raise _lib.StB200Error("in2 without w2 needs impl='tc' and weights from conv_tc_prepare_fused")
     fn, wptr = lib.st_conv_gather, weight
     mptr = nbr_map
     if impl in ("tc", "tp"):
@@ -259,11 +282,11 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
     _lib.check(fn(_ptr(inp), _ld(inp), _ptr(mptr), n_out, ntaps, _ptr(wptr), cin, cout, _ptr(scale), _ptr(shift),
-                  _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (w2.shape[0] if w2 is not None else 0),
+                  _ptr(residual), _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (in2.shape[1] if in2 is not None else 0),
                   _ptr(out), _ld(out), 1 if relu else 0, _stream()), "st_conv_gather")
     if prof is not None:
         ev1.record()
-        extra = (cout if residual is not None else 0) + (w2.shape[0] if w2 is not None else 0)
+        extra = (cout if residual is not None else 0) + (in2.shape[1] if in2 is not None else 0)
         prof.append((cin, cout, ntaps, n_out, extra, ev0, ev1, impl))
     return out
 

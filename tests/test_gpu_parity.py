@@ -203,6 +203,32 @@ def test_conv_tile_plan_z_order(cin, cout, n, extent):
     assert torch.equal(out, tc)
 
 
+@pytest.mark.parametrize("cin,cout,cin2", [(16, 16, 32), (32, 32, 64), (16, 8, 16), (64, 32, 48)])
+def test_conv_tc_identity_as_k_stages(cin, cout, cin2):
+    """ResBlock tail conv with the identity 1x1 conv appended to the tensor-core K loop (weights / BN scale):
+    act(scale * conv(t) + shift + w2 . x), reading x from the concat buffer and t from a slice."""
+    ops = _ops()
+    rng = np.random.default_rng(cin + cout + cin2)
+    c = _random_coords(rng, 2500, 13)
+    n = len(c)
+    nbr = U.subm_map(c)
+    t = rng.standard_normal((n, cin)).astype(np.float32)
+    x = rng.standard_normal((n, cin2 + 8)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    w2 = (rng.standard_normal((cin2, cout)) / np.sqrt(cin2)).astype(np.float32)
+    scale = (rng.uniform(0.5, 2, cout) * rng.choice([-1, 1], cout)).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    ref = np.maximum(U.gather_conv(t.astype(np.float64), w, nbr, n) * scale + shift + x[:, :cin2].astype(np.float64) @ w2, 0)
+    wt = torch.from_numpy(w).reshape(cout, 27, cin).permute(1, 2, 0).contiguous().to(DEV)
+    fused = ops.conv_tc_prepare_fused(wt, _t(w2), _t(scale))
+    assert fused is not None
+    xd = _t(x)
+    out = ops.conv_gather(_t(t), _t(nbr, torch.int32), wt, n, _t(scale), _t(shift), in2=xd[:, :cin2], w2=None, relu=True, impl="tc", weight_tc=fused)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+    with pytest.raises(Exception):
+        ops.conv_gather(_t(t), _t(nbr, torch.int32), wt, n, in2=xd[:, :cin2], w2=None, impl="fma")
+
+
 @pytest.mark.parametrize("impl", ["fma", "tp"])
 def test_conv_slices_and_fused_identity(impl):
     """Reads from / writes into column slices of the concat buffer, fused 1x1 identity conv."""
