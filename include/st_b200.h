@@ -149,6 +149,27 @@ int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_
                       const float *residual, int res_ld, const float *in2, int in2_ld,
                       const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
 
+/* Inverse (decoder) conv on parity-sorted rows       replaces spconv SparseInverseConv3d  model_blocks.py:91-100
+ * A fine voxel p receives from coarse voxel o through tap k iff p = 2o - 1 + k: per axis the tap is fixed by the
+ * parity of p, so at most 8 of the 27 taps (3.4 on average) can be non-empty and which ones depends only on the
+ * parity class of p.  st_inverse_plan sorts the fine level's rows by parity class (stable), permutes the `up` map of
+ * st_strided_maps accordingly (up_sorted[ntaps, n]) and records per 128-row tile the taps that occur (tile_mask);
+ * st_conv_gather_tc_inv (contract of st_conv_gather_tc, no residual / second input) walks only the K stages that
+ * have work in each tile and writes launch row j to output row row_index[j].                                  */
+size_t st_inverse_plan_workspace_bytes(int64_t n);
+int st_inverse_plan(const int32_t *coords, const int32_t *up, int64_t n, int ntaps, int32_t *row_index,
+                    int32_t *up_sorted, uint32_t *tile_mask, void *workspace, size_t workspace_bytes, void *stream);
+/* st_strided_maps and st_inverse_plan in one call (the engine's path): `down` as st_strided_maps, the `up` map
+ * only in parity-sorted launch order (up_sorted / row_index / tile_mask).                                      */
+size_t st_strided_maps_inv_workspace_bytes(int64_t n);
+int st_strided_maps_inv(const int32_t *coords, int64_t n, int64_t n_out, const uint64_t *out_keys,
+                        const int32_t *out_vals, int64_t out_capacity, int32_t *down,
+                        int32_t *row_index, int32_t *up_sorted, uint32_t *tile_mask, void *workspace,
+                        size_t workspace_bytes, void *stream);
+int st_conv_gather_tc_inv(const float *in, int in_ld, const int32_t *up_sorted, const int32_t *row_index,
+                          const uint32_t *tile_mask, int64_t n_out, int ntaps, const float *wprep, int cin, int cout,
+                          const float *scale, const float *shift, float *out, int out_ld, int act, void *stream);
+
 /* Tile-plan variant of the tensor-core conv: the DISTINCT source rows of every 128-row output tile are
  * staged in shared memory once (rows are in Z-order, so a tile's 27 x 128 map entries name only ~2 x 128
  * distinct rows) and the A fragments are gathered from there instead of through the L1.  The plan is

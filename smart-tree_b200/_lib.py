@@ -48,6 +48,11 @@ SIGNATURES = {
     "st_conv_tc_prepare_fused": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, C.c_int, _p, _p, _p]),
     "st_conv_gather_tc": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                     _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
+    "st_inverse_plan_workspace_bytes": (_sz, [_i64]),
+    "st_inverse_plan": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p, _p, _p, _sz, _p]),
+    "st_strided_maps_inv_workspace_bytes": (_sz, [_i64]),
+    "st_strided_maps_inv": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "st_conv_gather_tc_inv": (C.c_int, [_p, C.c_int, _p, _p, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p]),
     "st_conv_plan_bytes": (_sz, [_i64]),
     "st_conv_plan_build": (C.c_int, [_p, _i64, C.c_int, _i64, _p, _sz, _p]),
     "st_conv_tp_supported": (C.c_int, [C.c_int, C.c_int, C.c_int]),

@@ -19,6 +19,7 @@
 // initialisation and pipeline fill are paid once.
 // Epilogue: the producer warps read their accumulator lanes with tcgen05.ld and apply the fused
 // BN affine / residual / identity 1x1 conv / ReLU, writing straight into the (possibly sliced) output.
+#include <cub/cub.cuh>
 #include <cub/block/block_radix_sort.cuh>
 #include <cub/block/block_scan.cuh>
 
@@ -171,9 +172,34 @@ struct TcArgs {
     int out_ld;
     int act;
     int nstages_main;     // stages that walk the taps; the rest (fused identity) walk the channels of in2
+    const int32_t *row_index;      // optional: launch row -> output row (parity-sorted inverse convs)
+    const uint32_t *tile_mask;     // optional: per 128-row tile, the taps that have at least one neighbour
 };
 
+// Stage s of a CIN-channel conv covers these taps (bit t = tap t).
 template <int CIN>
+__device__ __forceinline__ uint32_t stage_tap_bits(int s) {
+    if (CIN == 8) return 0xFu << (4 * s);
+    if (CIN == 16) return 0x3u << (2 * s);
+    return 1u << (s / (CIN / TC_KS));
+}
+// Bit s set = stage s has work.  tap_mask: taps through which at least one row of the tile has a neighbour
+// (inverse convs on parity-sorted rows: 1-8 of 27); the fused-identity stages beyond nmain are always active.
+template <int CIN>
+__device__ __forceinline__ unsigned long long stage_mask_of(uint32_t tap_mask, int nmain, int nstages) {
+    if (tap_mask == 0u) tap_mask = 1u;                   // an empty tile still runs one stage (the accumulator must be defined)
+    unsigned long long m = 0ull;
+    for (int s = 0; s < nmain; ++s)
+        if (tap_mask & stage_tap_bits<CIN>(s)) m |= 1ull << s;
+    for (int s = nmain; s < nstages; ++s) m |= 1ull << s;
+    return m;
+}
+__device__ __forceinline__ int next_stage(unsigned long long m, int s, int nstages) {      // smallest active stage > s
+    const unsigned long long r = s + 1 < 64 ? (m >> (s + 1)) : 0ull;
+    return r ? s + __ffsll((long long)r) : nstages;
+}
+
+template <int CIN, bool MASKED>
 __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // smem: sb x { B_hi | B_lo } (npad*128 B each).  TMEM: [0, npad) accumulator, then TC_STAGES x 64 A columns.
@@ -280,9 +306,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             // ~1000 gathers a stage consists of; the slowest one gates the whole CTA).  The three register
             // sets rotate by unrolling the stage loop three times -- no register-to-register copies.
             float4 x0[4], x1[4], x2[4];
-            auto do_stage = [&](int s, float4 (&cur)[4], float4 (&fill)[4]) {
+            auto do_stage = [&](int s_fill, float4 (&cur)[4], float4 (&fill)[4]) {       // s_fill: the stage two ahead in the walk
                 if (tid == 0) TC_TRACE(6, g);
-                if (s + 2 < a.nstages) load_rows(buf, s + 2, fill);
+                if (s_fill < a.nstages) load_rows(buf, s_fill, fill);
                 if (tid == 0) TC_TRACE(7, g);
                 if (g >= TC_STAGES) {
                     if (lane == 0) mbar_wait(&a_empty[st], pe);
@@ -314,14 +340,20 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 ++g;
                 if (++st == TC_STAGES) { st = 0; pe ^= 1; }
             };
-            load_rows(buf, 0, x0);
-            if (a.nstages > 1) load_rows(buf, 1, x1);
-            for (int s = 0; s < a.nstages; s += 3) {
-                do_stage(s, x0, x2);
-                if (s + 1 < a.nstages) do_stage(s + 1, x1, x0);
-                if (s + 2 < a.nstages) do_stage(s + 2, x2, x1);
+            // walk the ACTIVE stages only (all of them unless a tile mask is given)
+            const unsigned long long smask = MASKED ? stage_mask_of<CIN>(__ldg(a.tile_mask + tile), a.nstages_main, a.nstages) : ~0ull;
+            const int ns = a.nstages;
+            int sa = (MASKED ? next_stage(smask, -1, a.nstages) : (-1) + 1), sb = (MASKED ? next_stage(smask, sa, a.nstages) : (sa) + 1), sc = (MASKED ? next_stage(smask, sb, a.nstages) : (sb) + 1);
+            load_rows(buf, sa, x0);
+            if (sb < ns) load_rows(buf, sb, x1);
+            while (sa < ns) {
+                do_stage(sc, x0, x2);
+                sa = sb; sb = sc; sc = (MASKED ? next_stage(smask, sc, a.nstages) : (sc) + 1);
+                if (sa < ns) { do_stage(sc, x1, x0); sa = sb; sb = sc; sc = (MASKED ? next_stage(smask, sc, a.nstages) : (sc) + 1); }
+                if (sa < ns) { do_stage(sc, x2, x1); sa = sb; sb = sc; sc = (MASKED ? next_stage(smask, sc, a.nstages) : (sc) + 1); }
             }
             // ---------------- epilogue of this tile ----------------
+            const int orow = (a.row_index && row_ok) ? __ldg(a.row_index + row) : row;      // launch row -> output row
             mbar_wait(&accum_bar, tile_iter & 1);
             tc_fence_after();
             const int ncols_half = a.npad / 2;             // columns owned by this warp group
@@ -359,7 +391,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
                 }
-                float4 *op = (float4 *)(a.out + (size_t)row * a.out_ld + c);
+                float4 *op = (float4 *)(a.out + (size_t)orow * a.out_ld + c);
                 op[0] = make_float4(v[0], v[1], v[2], v[3]);
                 op[1] = make_float4(v[4], v[5], v[6], v[7]);
             }
@@ -380,7 +412,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             const uint32_t a_stage0 = tmem_base + a_col0;
             const uint32_t b_base = desc_lo(smem_u32(b_ring)), b_stage_units = (uint32_t)(b_stage_bytes >> 4), b_lo_off = (uint32_t)(b_tile_bytes >> 4);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                for (int s = 0; s < a.nstages; ++s, ++g) {
+                const unsigned long long smask = MASKED ? stage_mask_of<CIN>(__ldg(a.tile_mask + tile), a.nstages_main, a.nstages) : ~0ull;
+                const int s_first = (MASKED ? next_stage(smask, -1, a.nstages) : (-1) + 1);
+                for (int s = s_first; s < a.nstages; s = (MASKED ? next_stage(smask, s, a.nstages) : (s) + 1), ++g) {
+                    const bool s_last = (MASKED ? next_stage(smask, s, a.nstages) : (s) + 1) >= a.nstages;
                     mbar_wait(&b_full[sb], pb);
                     if (lane == 0) TC_TRACE(4, g);
                     mbar_wait(&a_full[st], pa);
@@ -392,13 +427,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
 #pragma unroll
                         for (int j = 0; j < TC_KS / 8; ++j) {
                             const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
-                            umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s | j) ? 1u : 0u);
+                            umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s != s_first || j) ? 1u : 0u);
                             umma_tf32_ts(tmem_base, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
                             umma_tf32_ts(tmem_base, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
                         }
                         umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
                         umma_commit(&b_empty[sb]);
-                        if (s == a.nstages - 1) umma_commit(&accum_bar);      // this tile's accumulator is complete
+                        if (s_last) umma_commit(&accum_bar);      // this tile's accumulator is complete
                     }
                     __syncwarp();
                     if (lane == 0) TC_TRACE(3, g);
@@ -413,15 +448,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             int g = 0, sb = 0;
             uint32_t pb = 1;              // parity of the *previous* use of the slot
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const float *src = a.wprep;
-                for (int s = 0; s < a.nstages; ++s, ++g) {
+                const unsigned long long smask = MASKED ? stage_mask_of<CIN>(__ldg(a.tile_mask + tile), a.nstages_main, a.nstages) : ~0ull;
+                for (int s = (MASKED ? next_stage(smask, -1, a.nstages) : (-1) + 1); s < a.nstages; s = (MASKED ? next_stage(smask, s, a.nstages) : (s) + 1), ++g) {
                     if (g >= SB) mbar_wait(&b_empty[sb], pb);
                     if (elect_one_sync()) {
                         mbar_arrive_expect_tx(&b_full[sb], (uint32_t)b_stage_bytes);
-                        bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, src, (uint32_t)b_stage_bytes, &b_full[sb]);
+                        bulk_copy_g2s(b_ring + (size_t)sb * b_stage_bytes, a.wprep + (size_t)s * 2 * a.npad * TC_KS, (uint32_t)b_stage_bytes, &b_full[sb]);
                     }
                     __syncwarp();
-                    src += 2 * a.npad * TC_KS;
                     if (++sb == SB) { sb = 0; pb ^= 1; }
                 }
             }
@@ -975,11 +1009,12 @@ extern "C" int st_conv_tc_prepare_fused(const float *w, int ntaps, int cin, int 
     return ST_OK;
 }
 
-extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *wprep,
-                                 int cin, int cout, const float *scale, const float *shift, const float *residual, int res_ld,
-                                 const float *in2, int in2_ld, const float *w2, int cin2, float *out, int out_ld, int act,
-                                 void *stream) {
+static int conv_gather_tc_impl(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *wprep,
+                               int cin, int cout, const float *scale, const float *shift, const float *residual, int res_ld,
+                               const float *in2, int in2_ld, const float *w2, int cin2, float *out, int out_ld, int act,
+                               const int32_t *row_index, const uint32_t *tile_mask, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    ST_REQUIRE(!tile_mask || cin <= 64, "tile masks: at most 64 stages");
     if (n_out == 0) return ST_OK;
     ST_REQUIRE(tc_supported(cin, cout), "channel counts not supported by the tensor-core path");
     ST_REQUIRE(map != nullptr, "the tensor-core path needs an explicit gather map");
@@ -996,7 +1031,7 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     int sb = (npad <= 32 ? 40 * 1024 : 128 * 1024) / b_stage;
     sb = sb > TC_MAX_BSTAGES ? TC_MAX_BSTAGES : (sb < 2 ? 2 : sb);
     if (sb > nst) sb = nst;
-    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act, nmain};
+    TcArgs a{in, in_ld, map, (int)n_out, ntaps, wprep, cin, cout, npad, nst, sb, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act, nmain, row_index, tile_mask};
     const int smem = sb * b_stage + 1024;
     static int n_sms = 0;
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
@@ -1008,10 +1043,12 @@ extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map,
     if (cin == CI) {                                                                                                \
         static int smem_set = 0;                                                                                    \
         if (smem > smem_set) {                                                                                      \
-            ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<CI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));  \
+            ST_CHECK_CUDA(cudaFuncSetAttribute(k_conv_tc<CI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));   \
             smem_set = smem;                                                                                        \
         }                                                                                                           \
-        k_conv_tc<CI><<<grid, TC_THREADS, smem, s>>>(a);                                                            \
+        if (tile_mask) k_conv_tc<CI, true><<<grid, TC_THREADS, smem, s>>>(a);                                       \
+        else k_conv_tc<CI, false><<<grid, TC_THREADS, smem, s>>>(a);                                                \
         ST_CHECK_LAUNCH();                                                                                          \
         return ST_OK;                                                                                               \
     }
@@ -1086,6 +1123,122 @@ extern "C" int st_conv_gather_tp(const float *in, int in_ld, const void *plan, i
 #undef ST_TP_CASE
     set_error("st_conv_gather_tp: cin=%d not instantiated", cin);
     return ST_ERR_UNSUPPORTED;
+}
+
+extern "C" int st_conv_gather_tc(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *wprep,
+                                 int cin, int cout, const float *scale, const float *shift, const float *residual, int res_ld,
+                                 const float *in2, int in2_ld, const float *w2, int cin2, float *out, int out_ld, int act,
+                                 void *stream) {
+    return conv_gather_tc_impl(in, in_ld, map, n_out, ntaps, wprep, cin, cout, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2,
+                               out, out_ld, act, nullptr, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------ inverse conv on parity-sorted rows
+// A fine voxel p receives from coarse voxel o through tap k iff p = 2o - 1 + k, so per axis the tap is fixed by the
+// parity of p (even: k = 1; odd: k in {0, 2}): of the 27 taps at most 8 -- 3.4 on average -- can ever be non-empty,
+// and WHICH ones depends only on the parity class of p.  st_inverse_plan sorts the rows of the fine level by parity
+// class (stable: Z-order is kept inside a class), permutes the `up` map accordingly and records per 128-row tile the
+// taps that occur; st_conv_gather_tc_inv then walks only the K stages that have work in each tile (the other
+// ~85 % multiplied zeros) and writes every result to its own row through row_index.
+__global__ void k_inv_keys(const int4 *__restrict__ coords, int n, uint32_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 c = __ldg(coords + i);
+    keys[i] = (uint32_t)(((c.y & 1) << 2) | ((c.z & 1) << 1) | (c.w & 1));
+    vals[i] = i;
+}
+__global__ void k_inv_fill(const int32_t *__restrict__ up, const int32_t *__restrict__ row_index, int n, int32_t *__restrict__ up_sorted,
+                           uint32_t *__restrict__ tile_mask) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+    int v = -1;
+    if (j < n) {
+        v = __ldg(up + (size_t)t * n + __ldg(row_index + j));
+        up_sorted[(size_t)t * n + j] = v;
+    }
+    // the 32 rows of a warp lie in one 128-row tile
+    if (__any_sync(0xffffffffu, v >= 0) && (threadIdx.x & 31) == 0) atomicOr(tile_mask + (j >> 7), 1u << t);
+}
+static size_t inv_sort_bytes(int64_t n) {
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (uint32_t *)nullptr, (uint32_t *)nullptr, (int32_t *)nullptr, (int32_t *)nullptr, (int)n, 0, 3);
+    return b;
+}
+extern "C" size_t st_inverse_plan_workspace_bytes(int64_t n) { return align_up(inv_sort_bytes(n)) + 2 * align_up(n * 4) + align_up(n * 4) + 1024; }
+
+extern "C" int st_inverse_plan(const int32_t *coords, const int32_t *up, int64_t n, int ntaps, int32_t *row_index, int32_t *up_sorted,
+                               uint32_t *tile_mask, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(n < (1ll << 31) && ntaps >= 1 && ntaps <= 32, "sizes");
+    Carver cv(workspace, workspace_bytes);
+    uint32_t *keys = cv.take<uint32_t>(n), *keys2 = cv.take<uint32_t>(n);
+    int32_t *vals = cv.take<int32_t>(n);
+    size_t sb = inv_sort_bytes(n);
+    void *sort_ws = cv.take<char>(sb);
+    if (!cv.ok()) { set_error("st_inverse_plan: workspace too small"); return ST_ERR_WORKSPACE; }
+    k_inv_keys<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, keys, vals);
+    ST_CHECK_LAUNCH();
+    ST_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sb, keys, keys2, vals, row_index, (int)n, 0, 3, s));
+    ST_CHECK_CUDA(cudaMemsetAsync(tile_mask, 0, cdiv(n, TC_M) * sizeof(uint32_t), s));
+    dim3 grid((unsigned)cdiv(n, 256), (unsigned)ntaps);
+    k_inv_fill<<<grid, 256, 0, s>>>(up, row_index, (int)n, up_sorted, tile_mask);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// One call for the strided maps AND the inverse plan of a level: `down` as st_strided_maps; the `up` map is produced
+// directly in parity-sorted launch order (up_sorted, row_index, tile_mask as st_inverse_plan), never unsorted.
+__global__ void k_strided_maps_inv(const int4 *__restrict__ coords, int n, int m, const uint64_t *__restrict__ keys,
+                                   const int32_t *__restrict__ vals, uint32_t mask, const int32_t *__restrict__ row_index,
+                                   int32_t *__restrict__ down, int32_t *__restrict__ up_sorted, uint32_t *__restrict__ tile_mask) {
+    // thread = (launch row j, tap k): rows are walked in parity-sorted order, so up_sorted is written coalesced and the
+    // 32 rows of a warp share their 128-row tile (one mask update per warp)
+    const int j = blockIdx.x * blockDim.x + threadIdx.x, k = blockIdx.y;
+    int o = -1;
+    if (j < n) {
+        const int i = __ldg(row_index + j);
+        const int4 c = __ldg(coords + i);
+        const int tz = c.y + 1 - k / 9, ty = c.z + 1 - (k / 3) % 3, tx = c.w + 1 - k % 3;
+        if (!((tz | ty | tx) & 1)) {
+            o = hash_lookup(keys, vals, mask, pack_key(c.x, tz >> 1, ty >> 1, tx >> 1));
+            if (o >= 0) down[(size_t)k * m + o] = i;
+        }
+        up_sorted[(size_t)k * n + j] = o;
+    }
+    if (__any_sync(0xffffffffu, o >= 0) && (threadIdx.x & 31) == 0) atomicOr(tile_mask + (j >> 7), 1u << k);
+}
+extern "C" size_t st_strided_maps_inv_workspace_bytes(int64_t n) { return st_inverse_plan_workspace_bytes(n); }
+
+extern "C" int st_strided_maps_inv(const int32_t *coords, int64_t n, int64_t n_out, const uint64_t *out_keys, const int32_t *out_vals,
+                                   int64_t out_capacity, int32_t *down, int32_t *row_index, int32_t *up_sorted,
+                                   uint32_t *tile_mask, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(n < (1ll << 31), "sizes");
+    Carver cv(workspace, workspace_bytes);
+    uint32_t *keys = cv.take<uint32_t>(n), *keys2 = cv.take<uint32_t>(n);
+    int32_t *vals = cv.take<int32_t>(n);
+    size_t sb = inv_sort_bytes(n);
+    void *sort_ws = cv.take<char>(sb);
+    if (!cv.ok()) { set_error("st_strided_maps_inv: workspace too small"); return ST_ERR_WORKSPACE; }
+    k_inv_keys<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, keys, vals);
+    ST_CHECK_LAUNCH();
+    ST_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sb, keys, keys2, vals, row_index, (int)n, 0, 3, s));
+    ST_CHECK_CUDA(cudaMemsetAsync(tile_mask, 0, cdiv(n, TC_M) * sizeof(uint32_t), s));
+    ST_CHECK_CUDA(cudaMemsetAsync(down, 0xFF, (size_t)27 * n_out * sizeof(int32_t), s));
+    dim3 grid((unsigned)cdiv(n, 256), 27);
+    k_strided_maps_inv<<<grid, 256, 0, s>>>((const int4 *)coords, (int)n, (int)n_out, out_keys, out_vals, (uint32_t)(out_capacity - 1), row_index,
+                                            down, up_sorted, tile_mask);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+extern "C" int st_conv_gather_tc_inv(const float *in, int in_ld, const int32_t *up_sorted, const int32_t *row_index, const uint32_t *tile_mask,
+                                     int64_t n_out, int ntaps, const float *wprep, int cin, int cout, const float *scale,
+                                     const float *shift, float *out, int out_ld, int act, void *stream) {
+    ST_REQUIRE(row_index != nullptr && tile_mask != nullptr, "plan of st_inverse_plan required");
+    return conv_gather_tc_impl(in, in_ld, up_sorted, n_out, ntaps, wprep, cin, cout, scale, shift, nullptr, 0, nullptr, 0, nullptr, 0,
+                               out, out_ld, act, row_index, tile_mask, stream);
 }
 
 // debug only (not part of include/st_b200.h)

@@ -89,24 +89,42 @@ class LevelIndex:
         self.nbr = ops.subm_map(coords, self.table)
         self.down = None
         self.up = None
+        self.child = None
         self._plans = {}
+
+    def up_map(self):
+        """The unsorted `up` map (built on demand when the level was indexed with the parity-sorted plan only)."""
+        if self.up is None and self.child is not None:
+            _, self.up = ops.strided_maps(self.coords, self.child.coords, self.child.table)
+        return self.up
+
+    def inverse_plan(self):
+        """Parity-sorted launch order of this level's inverse conv (ops.inverse_plan), built on first use."""
+        p = self._plans.get("inv")
+        if p is None:
+            p = self._plans["inv"] = ops.inverse_plan(self.coords, self.up_map())
+        return p
 
     def plan(self, name, n_in):
         """Tile plan (distinct source rows + local map per 128-row tile) of gather map `name`, built on first use
         and shared by every conv of the level that gathers through that map."""
         p = self._plans.get(name)
         if p is None:
-            p = self._plans[name] = ops.conv_plan_build(getattr(self, name), n_in)
+            p = self._plans[name] = ops.conv_plan_build(self.up_map() if name == "up" else getattr(self, name), n_in)
         return p
 
 
-def build_levels(coords: torch.Tensor, depth: int, morton: bool = False) -> List[LevelIndex]:
+def build_levels(coords: torch.Tensor, depth: int, morton: bool = False, inverse_plan: bool = False) -> List[LevelIndex]:
     levels = [LevelIndex(coords)]
     for _ in range(depth - 1):
         cur = levels[-1]
         oc = ops.strided_coords(cur.coords, morton=morton)
         nxt = LevelIndex(oc)
-        cur.down, cur.up = ops.strided_maps(cur.coords, oc, nxt.table)
+        cur.child = nxt
+        if inverse_plan:
+            cur.down, cur.up, cur._plans["inv"] = ops.strided_maps(cur.coords, oc, nxt.table, inverse_plan=True)
+        else:
+            cur.down, cur.up = ops.strided_maps(cur.coords, oc, nxt.table)
         levels.append(nxt)
     return levels
 
@@ -126,6 +144,7 @@ class SmartTreeEngine:
         self.eps = eps
         self.conv_impl = conv_impl
         self.morton = bool(int(os.environ.get("ST_MORTON", "1")))
+        self.inverse_sorted = bool(int(os.environ.get("ST_INVERSE_SORTED", "1")))
         dev = self.device
         self.stem = ConvLayer(_conv_w(sd["input_conv.sequence.0.weight"]),
                               *_fold_bn(sd, "input_conv.sequence.1", eps)).to(dev)
@@ -194,10 +213,18 @@ class SmartTreeEngine:
         impl, plan = "fma", None
         if taps > 1:
             if self.conv_impl == "tp" and lv is not None and ops.conv_tp_supported(taps, cin, cout):
+                if which == "up" and nbr is None:
+                    nbr = lv.up_map()
                 impl, plan = "tp", lv.plan(which, x.shape[0])
             elif (self.conv_impl in ("tc", "tp") or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and ops.conv_tc_supported(taps, cin, cout):
                 impl = "tc"
         wtc = layer.tc_weights() if impl != "fma" else None
+        if which == "up" and nbr is None:
+            if not (impl == "tc" and self.inverse_sorted and residual is None and in2 is None and cin <= 64):
+                nbr = lv.up_map()
+        if impl == "tc" and which == "up" and self.inverse_sorted and residual is None and in2 is None and cin <= 64:
+            # decoder: only the <= 8 taps a fine voxel's parity class allows have work (parity-sorted rows, stage skipping)
+            return ops.conv_gather_tc_inv(x, lv.inverse_plan(), wtc, taps, cin, cout, n_out, layer.scale, layer.shift, out=out, relu=relu)
         if impl == "tc" and in2 is not None:
             fused = layer.tc_weights_fused(w2)          # identity 1x1 conv as extra K stages on the tensor cores
             if fused is not False:
@@ -239,10 +266,11 @@ class SmartTreeEngine:
         (batch, Z-order): level 0 through a permutation of the caller's rows (undone by the heads
         kernel), deeper levels by construction."""
         coords = coords.contiguous().int()
+        inv = self.inverse_sorted and self.conv_impl in ("auto", "tc")      # (the tile-plan path wants the unsorted up map)
         if not self.morton:
-            return build_levels(coords, self.depth)
+            return build_levels(coords, self.depth, inverse_plan=inv)
         perm = ops.morton_perm(coords)
-        levels = build_levels(coords.index_select(0, perm), self.depth, morton=True)      # int32 index: no widening pass
+        levels = build_levels(coords.index_select(0, perm), self.depth, morton=True, inverse_plan=inv)      # int32 index: no widening pass
         levels[0].perm = perm
         return levels
 

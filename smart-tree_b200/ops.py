@@ -16,7 +16,7 @@ LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1}
+                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3}
 
 
 def _count(op):
@@ -166,10 +166,21 @@ def strided_coords(coords, morton=False):
     return out[:m.value].clone() if m.value * 4 < out.shape[0] else out[:m.value]
 
 
-def strided_maps(coords, out_coords, out_table: CoordTable):
+def strided_maps(coords, out_coords, out_table: CoordTable, inverse_plan=False):
+    """down [27, m], up [27, n]; with inverse_plan the `up` map is produced only in parity-sorted launch order:
+    returns (down, None, (row_index, up_sorted, tile_mask)) as ops.inverse_plan would (st_strided_maps_inv)."""
     lib = _lib.load()
     n, m = coords.shape[0], out_coords.shape[0]
     down = torch.empty((27, m), dtype=I32, device=coords.device)
+    if inverse_plan and n:
+        buf = torch.empty(27 * n + n + (n + 127) // 128, dtype=I32, device=coords.device)
+        up_sorted, row_index, tile_mask = buf[:27 * n].view(27, n), buf[27 * n:28 * n], buf[28 * n:]
+        ws = _ws(lib.st_strided_maps_inv_workspace_bytes(n), coords.device)
+        _count("strided_maps"); _count("inverse_plan")
+        _lib.check(lib.st_strided_maps_inv(_ptr(coords), n, m, _ptr(out_table.keys), _ptr(out_table.vals), out_table.capacity,
+                                           _ptr(down), _ptr(row_index), _ptr(up_sorted), _ptr(tile_mask), _ptr(ws), ws.numel(),
+                                           _stream()), "st_strided_maps_inv")
+        return down, None, (row_index, up_sorted, tile_mask)
     up = torch.empty((27, n), dtype=I32, device=coords.device)
     _count("strided_maps")
     _lib.check(lib.st_strided_maps(_ptr(coords), n, m, _ptr(out_table.keys), _ptr(out_table.vals), out_table.capacity,
@@ -223,6 +234,46 @@ def conv_tc_prepare_fused(weight, w2, scale):
     _lib.check(lib.st_conv_tc_prepare_fused(_ptr(weight), ntaps, cin, cout, _ptr(w2), cin2, _ptr(scale), _ptr(wprep), _stream()),
                "st_conv_tc_prepare_fused")
     return wprep
+
+
+def inverse_plan(coords, up):
+    """Parity-sorted launch order of an inverse conv (st_inverse_plan): coords [n,4] of the fine level, up [ntaps, n].
+    Returns (row_index [n] i32, up_sorted [ntaps, n] i32, tile_mask [ceil(n/128)] as int32 bit masks)."""
+    lib = _lib.load()
+    _req(coords, I32, "coords"); _req(up, I32, "up")
+    ntaps, n = up.shape
+    dev = up.device
+    row_index = torch.empty(n, dtype=I32, device=dev)
+    up_sorted = torch.empty_like(up)
+    tile_mask = torch.empty(max((n + 127) // 128, 1), dtype=I32, device=dev)
+    ws = _ws(lib.st_inverse_plan_workspace_bytes(n), dev)
+    _count("inverse_plan")
+    _lib.check(lib.st_inverse_plan(_ptr(coords), _ptr(up), n, ntaps, _ptr(row_index), _ptr(up_sorted), _ptr(tile_mask), _ptr(ws),
+                                   ws.numel(), _stream()), "st_inverse_plan")
+    return row_index, up_sorted, tile_mask
+
+
+def conv_gather_tc_inv(inp, plan, weight_tc, ntaps, cin, cout, n_out, scale=None, shift=None, out=None, relu=False):
+    """Inverse conv through the tensor-core kernel on parity-sorted rows; plan = inverse_plan(coords, up)."""
+    lib = _lib.load()
+    _req_rows(inp, "inp")
+    row_index, up_sorted, tile_mask = plan
+    if out is None:
+        out = torch.empty((n_out, cout), dtype=F32, device=inp.device)
+    _req_rows(out, "out")
+    assert out.shape == (n_out, cout) and inp.shape[1] == cin and up_sorted.shape == (ntaps, n_out)
+    _count("conv")
+    prof = _conv_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.check(lib.st_conv_gather_tc_inv(_ptr(inp), _ld(inp), _ptr(up_sorted), _ptr(row_index), _ptr(tile_mask), n_out, ntaps, _ptr(weight_tc),
+                                         cin, cout, _ptr(scale), _ptr(shift), _ptr(out), _ld(out), 1 if relu else 0, _stream()),
+               "st_conv_gather_tc_inv")
+    if prof is not None:
+        ev1.record()
+        prof.append((cin, cout, ntaps, n_out, 0, ev0, ev1, "tcinv"))
+    return out
 
 
 def conv_tp_supported(ntaps, cin, cout):

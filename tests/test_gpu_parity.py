@@ -229,6 +229,53 @@ def test_conv_tc_identity_as_k_stages(cin, cout, cin2):
         ops.conv_gather(_t(t), _t(nbr, torch.int32), wt, n, in2=xd[:, :cin2], w2=None, impl="fma")
 
 
+@pytest.mark.parametrize("cin,cout", [(16, 8), (32, 16), (64, 32)])
+@pytest.mark.parametrize("n,extent", [(30000, 40), (200, 30), (129, 5)])
+def test_inverse_conv_parity_sorted(cin, cout, n, extent):
+    """Decoder conv through the parity-sorted plan (stage skipping + output row indirection) == the oracle's inverse
+    conv == the plain tensor-core kernel on the unsorted `up` map; the plan's tile masks name only taps the parity
+    rule allows; output written into a column slice."""
+    ops = _ops()
+    rng = np.random.default_rng(n + cin)
+    c = _random_coords(rng, n, extent)
+    perm = ops.morton_perm(_t(c, torch.int32)).cpu().numpy()
+    c = c[perm]
+    n = len(c)
+    oc, down, up = U.strided_maps(c)
+    m = len(oc)
+    y = rng.standard_normal((m, cin)).astype(np.float32)
+    w = (rng.standard_normal((cout, 3, 3, 3, cin)) / np.sqrt(4 * cin)).astype(np.float32)
+    scale = rng.uniform(0.5, 2, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    ref = np.maximum(U.gather_conv(y.astype(np.float64), w, up, n) * scale + shift, 0)
+    wt = torch.from_numpy(w).reshape(cout, 27, cin).permute(1, 2, 0).contiguous().to(DEV)
+    wtc = ops.conv_tc_prepare(wt)
+    up_d = _t(up, torch.int32)
+    plan = ops.inverse_plan(_t(c, torch.int32), up_d)
+    row_index, up_sorted, tile_mask = plan
+    ri = row_index.cpu().numpy()
+    assert np.array_equal(np.sort(ri), np.arange(n))
+    cls = ((c[:, 1] & 1) << 2) | ((c[:, 2] & 1) << 1) | (c[:, 3] & 1)
+    assert np.all(np.diff(cls[ri]) >= 0) and np.array_equal(up_sorted.cpu().numpy(), up[:, ri])
+    buf = torch.zeros((n, cout + 8), device=DEV)
+    ops.conv_gather_tc_inv(_t(y), plan, wtc, 27, cin, cout, n, _t(scale), _t(shift), out=buf[:, 8:], relu=True)
+    np.testing.assert_allclose(buf[:, 8:].cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+    assert torch.all(buf[:, :8] == 0)
+    plain = ops.conv_gather(_t(y), up_d, wt, n, _t(scale), _t(shift), relu=True, impl="tc", weight_tc=wtc)
+    np.testing.assert_allclose(buf[:, 8:].cpu().numpy(), plain.cpu().numpy(), rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    # the fused builder (strided maps + plan in one call) gives the same maps and plan
+    oc_d = _t(oc, torch.int32)
+    dn2, up2, plan2 = ops.strided_maps(_t(c, torch.int32), oc_d, ops.CoordTable(oc_d), inverse_plan=True)
+    assert np.array_equal(dn2.cpu().numpy(), down) and up2 is None
+    for a_, b_ in zip(plan, plan2):
+        assert torch.equal(a_, b_)
+    # pure tiles of the all-even class use exactly one tap (the centre tap 13)
+    tm = tile_mask.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+    n_even = int((cls == 0).sum())
+    if n_even >= 128:
+        assert np.all(tm[: n_even // 128] == 1 << 13)
+
+
 @pytest.mark.parametrize("impl", ["fma", "tp"])
 def test_conv_slices_and_fused_identity(impl):
     """Reads from / writes into column slices of the concat buffer, fused 1x1 identity conv."""
