@@ -207,20 +207,23 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
     const int b_stage_bytes = 2 * b_tile_bytes;
     uint8_t *const b_ring = smem_raw;
     const int SB = a.b_stages;
-    __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar;
+    __shared__ uint64_t a_full[TC_STAGES], a_empty[TC_STAGES], b_full[TC_MAX_BSTAGES], b_empty[TC_MAX_BSTAGES], accum_bar[2];
     __shared__ uint32_t tmem_base_sh;
     __shared__ int smap[2][TC_MAXTAPS][TC_M];     // gather-map entries of the current / next tile (28 KB)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t tmem_need = (uint32_t)a.npad + TC_STAGES * TC_A_COLS;
+    // MASKED (parity-sorted inverse conv: 1-4 stages per tile, so the tile switch dominates): two accumulators, the
+    // epilogue of tile i runs after the stages of tile i+1 have been produced and overlaps with their MMAs
+    constexpr uint32_t NACC = MASKED ? 2u : 1u;
+    const uint32_t tmem_need = NACC * (uint32_t)a.npad + TC_STAGES * TC_A_COLS;
     const uint32_t tmem_cols = tmem_need <= 256 ? 256u : 512u;
-    const uint32_t a_col0 = (uint32_t)a.npad;
+    const uint32_t a_col0 = NACC * (uint32_t)a.npad;
     const int ntiles = (a.n_out + TC_M - 1) / TC_M;
 
     if (tid == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&a_full[s], TC_PRODUCERS / 32); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < TC_MAX_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        mbar_init(&accum_bar, 1);
+        mbar_init(&accum_bar[0], 1); mbar_init(&accum_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) tmem_alloc(&tmem_base_sh, tmem_cols);
@@ -247,8 +250,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
         auto prefetch_map = [&](int tile, int buf) {
             if (tile < ntiles) {
                 const int row = tile * TC_M + rloc;
+                // MASKED: only the taps that occur in the tile are fetched (1-8 of 27); the others read as absent
+                const uint32_t tm = MASKED ? __ldg(a.tile_mask + tile) : 0xFFFFFFFFu;
                 for (int t = half; t < TC_MAXTAPS; t += 2) {
-                    if (row < a.n_out && t < a.ntaps) {
+                    if (row < a.n_out && t < a.ntaps && ((tm >> t) & 1u)) {
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&smap[buf][t][rloc])),
                                      "l"(a.map + (size_t)t * a.n_out + row) : "memory");
                     } else {
@@ -291,6 +296,55 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 x[j] = src >= 0 ? __ldg((const float4 *)(a.in + (size_t)src * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
+        // epilogue of one tile: e_row = launch row (residual / second input are indexed by it), e_orow = output row
+        auto epilogue = [&](int e_row, bool e_ok, int e_orow, int e_iter) {
+            mbar_wait(&accum_bar[MASKED ? (e_iter & 1) : 0], (uint32_t)((MASKED ? (e_iter >> 1) : e_iter) & 1));
+            tc_fence_after();
+            const int ncols_half = a.npad / 2;             // columns owned by this warp group
+            const int col0 = half * ncols_half;
+            for (int cb = 0; cb < ncols_half; cb += 8) {
+                const int c = col0 + cb;
+                float v[8];
+                tmem_ld8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((MASKED ? (e_iter & 1) * a.npad : 0) + c), v);
+                if (!e_ok || c >= a.cout) continue;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float sc = a.scale ? __ldg(a.scale + c + i) : 1.f;
+                    float sh = a.shift ? __ldg(a.shift + c + i) : 0.f;
+                    v[i] = fmaf(v[i], sc, sh);
+                }
+                if (a.res) {
+                    const float4 *rp = (const float4 *)(a.res + (size_t)e_row * a.res_ld + c);
+                    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+                }
+                if (a.in2 && a.w2) {
+                    float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    const float *xr = a.in2 + (size_t)e_row * a.in2_ld;
+                    for (int ci = 0; ci < a.cin2; ++ci) {
+                        const float xv = __ldg(xr + ci);
+                        const float4 *wp = (const float4 *)(a.w2 + (size_t)ci * a.cout + c);
+                        float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
+                        e[0] = fmaf(xv, w0.x, e[0]); e[1] = fmaf(xv, w0.y, e[1]); e[2] = fmaf(xv, w0.z, e[2]); e[3] = fmaf(xv, w0.w, e[3]);
+                        e[4] = fmaf(xv, w1.x, e[4]); e[5] = fmaf(xv, w1.y, e[5]); e[6] = fmaf(xv, w1.z, e[6]); e[7] = fmaf(xv, w1.w, e[7]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += e[i];
+                }
+                if (a.act & ST_ACT_RELU) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                float4 *op = (float4 *)(a.out + (size_t)e_orow * a.out_ld + c);
+                op[0] = make_float4(v[0], v[1], v[2], v[3]);
+                op[1] = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            // the accumulator has been read: order those TMEM loads before this thread's next arrivals,
+            // which in turn gate the next tile's first (overwriting) MMA
+            tc_fence_before();
+        };
+        bool pend = false, p_ok = false;
+        int p_row = 0, p_orow = 0, p_iter = 0;
         int g = 0, st = 0;                            // global stage counter, ring position
         uint32_t pe = 1;                              // parity of the previous use of A stage `st`
         int tile_iter = 0;
@@ -352,54 +406,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 if (sa < ns) { do_stage(sc, x1, x0); sa = sb; sb = sc; sc = (MASKED ? next_stage(smask, sc, a.nstages) : (sc) + 1); }
                 if (sa < ns) { do_stage(sc, x2, x1); sa = sb; sb = sc; sc = (MASKED ? next_stage(smask, sc, a.nstages) : (sc) + 1); }
             }
-            // ---------------- epilogue of this tile ----------------
-            const int orow = (a.row_index && row_ok) ? __ldg(a.row_index + row) : row;      // launch row -> output row
-            mbar_wait(&accum_bar, tile_iter & 1);
-            tc_fence_after();
-            const int ncols_half = a.npad / 2;             // columns owned by this warp group
-            const int col0 = half * ncols_half;
-            for (int cb = 0; cb < ncols_half; cb += 8) {
-                const int c = col0 + cb;
-                float v[8];
-                tmem_ld8(tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c, v);
-                if (!row_ok || c >= a.cout) continue;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float sc = a.scale ? __ldg(a.scale + c + i) : 1.f;
-                    float sh = a.shift ? __ldg(a.shift + c + i) : 0.f;
-                    v[i] = fmaf(v[i], sc, sh);
-                }
-                if (a.res) {
-                    const float4 *rp = (const float4 *)(a.res + (size_t)row * a.res_ld + c);
-                    float4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-                    v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-                }
-                if (a.in2 && a.w2) {
-                    float e[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    const float *xr = a.in2 + (size_t)row * a.in2_ld;
-                    for (int ci = 0; ci < a.cin2; ++ci) {
-                        const float xv = __ldg(xr + ci);
-                        const float4 *wp = (const float4 *)(a.w2 + (size_t)ci * a.cout + c);
-                        float4 w0 = __ldg(wp), w1 = __ldg(wp + 1);
-                        e[0] = fmaf(xv, w0.x, e[0]); e[1] = fmaf(xv, w0.y, e[1]); e[2] = fmaf(xv, w0.z, e[2]); e[3] = fmaf(xv, w0.w, e[3]);
-                        e[4] = fmaf(xv, w1.x, e[4]); e[5] = fmaf(xv, w1.y, e[5]); e[6] = fmaf(xv, w1.z, e[6]); e[7] = fmaf(xv, w1.w, e[7]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += e[i];
-                }
-                if (a.act & ST_ACT_RELU) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                float4 *op = (float4 *)(a.out + (size_t)orow * a.out_ld + c);
-                op[0] = make_float4(v[0], v[1], v[2], v[3]);
-                op[1] = make_float4(v[4], v[5], v[6], v[7]);
+            // ---------------- epilogue: of this tile, or (MASKED) of the previous one ----------------
+            if (!MASKED) {
+                epilogue(row, row_ok, row, tile_iter);
+            } else {
+                if (pend) epilogue(p_row, p_ok, p_orow, p_iter);
+                pend = true; p_row = row; p_ok = row_ok; p_iter = tile_iter;
+                p_orow = row_ok ? __ldg(a.row_index + row) : row;
             }
-            // the accumulator has been read: order those TMEM loads before this thread's next arrivals,
-            // which in turn gate the next tile's first (overwriting) MMA
-            tc_fence_before();
             map_ready();                   // next tile's gather map has landed; this tile's buffer may be refilled
         }
+        if (MASKED && pend) epilogue(p_row, p_ok, p_orow, p_iter);
     } else if (warp == 8) {
         // ================= MMA issuer (one elected lane) =================
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.npad >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -411,8 +428,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             uint32_t pa = 0, pb = 0;
             const uint32_t a_stage0 = tmem_base + a_col0;
             const uint32_t b_base = desc_lo(smem_u32(b_ring)), b_stage_units = (uint32_t)(b_stage_bytes >> 4), b_lo_off = (uint32_t)(b_tile_bytes >> 4);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            int tile_iter = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tile_iter) {
                 const unsigned long long smask = MASKED ? stage_mask_of<CIN>(__ldg(a.tile_mask + tile), a.nstages_main, a.nstages) : ~0ull;
+                const uint32_t tmem_d = tmem_base + (MASKED ? (uint32_t)((tile_iter & 1) * a.npad) : 0u);
                 const int s_first = (MASKED ? next_stage(smask, -1, a.nstages) : (-1) + 1);
                 for (int s = s_first; s < a.nstages; s = (MASKED ? next_stage(smask, s, a.nstages) : (s) + 1), ++g) {
                     const bool s_last = (MASKED ? next_stage(smask, s, a.nstages) : (s) + 1) >= a.nstages;
@@ -427,13 +446,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
 #pragma unroll
                         for (int j = 0; j < TC_KS / 8; ++j) {
                             const uint32_t ko = (uint32_t)j * 16;        // B: 256 bytes per k-step; A: 8 TMEM columns
-                            umma_tf32_ts(tmem_base, ah + j * 8, bh + ko, DESC_HI, idesc, (s != s_first || j) ? 1u : 0u);
-                            umma_tf32_ts(tmem_base, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
-                            umma_tf32_ts(tmem_base, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
+                            umma_tf32_ts(tmem_d, ah + j * 8, bh + ko, DESC_HI, idesc, (s != s_first || j) ? 1u : 0u);
+                            umma_tf32_ts(tmem_d, al + j * 8, bh + ko, DESC_HI, idesc, 1u);
+                            umma_tf32_ts(tmem_d, ah + j * 8, bl + ko, DESC_HI, idesc, 1u);
                         }
                         umma_commit(&a_empty[st]);    // both ring slots are reusable once these MMAs have read them
                         umma_commit(&b_empty[sb]);
-                        if (s_last) umma_commit(&accum_bar);      // this tile's accumulator is complete
+                        if (s_last) umma_commit(&accum_bar[MASKED ? (tile_iter & 1) : 0]);      // this tile's accumulator is complete
                     }
                     __syncwarp();
                     if (lane == 0) TC_TRACE(3, g);
@@ -1037,7 +1056,7 @@ static int conv_gather_tc_impl(const float *in, int in_ld, const int32_t *map, i
     if (!n_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev); }
     const int64_t ntiles = cdiv(n_out, TC_M);
     // two CTAs per SM when both fit: 256 TMEM columns each (accumulator + 3 A stages) and ~75 KB of smem
-    const int ctas_per_sm = (npad + TC_STAGES * TC_A_COLS <= 256 && smem <= 80 * 1024) ? 2 : 1;
+    const int ctas_per_sm = ((tile_mask ? 2 : 1) * npad + TC_STAGES * TC_A_COLS <= 256 && smem <= 80 * 1024) ? 2 : 1;
     const unsigned grid = (unsigned)(ntiles < (int64_t)n_sms * ctas_per_sm ? ntiles : (int64_t)n_sms * ctas_per_sm);   // persistent CTAs
 #define ST_TC_CASE(CI)                                                                                              \
     if (cin == CI) {                                                                                                \
