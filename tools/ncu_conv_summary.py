@@ -33,7 +33,7 @@ def main():
     for r in rows:
         name = r[idx["Kernel Name"]]
         m = re.search(r"k_[a-z0-9_]+(<[^>]*>)?", name)
-        short = m.group(0).replace(" ", "") if m else name[:40]
+        short = m.group(0).replace(" ", "").replace(",", "x") if m else name[:40].replace(",", ";")
         vals = []
         for n, metric in COLS:
             if metric not in idx or r[idx[metric]] in ("", "n/a"):
