@@ -114,6 +114,17 @@ int st_strided_maps(const int32_t *coords, int64_t n, int64_t n_out, const uint6
                     const int32_t *out_vals, int64_t out_capacity, int32_t *down, int32_t *up,
                     void *stream);
 
+/* Devoxelise: per-voxel predictions back to every input point.  The reference's voxeliser
+ * returns pc_voxel_id and drops it (smart_tree/dataset/dataset.py:214); this is the gather it omits.  Pair t is
+ * (point pair_point[t], block pair_block[t]) with voxel row pair_voxel[t] (-1 = dropped) as st_block_emit /
+ * st_voxelize produce them; a point takes the prediction of the block whose inner half-open cube
+ * [centre - size/2, centre + size/2) contains it (util/maths.py:135-155).  Outputs are initialised here:
+ * point_medial[n,3] = 0, point_class[n] = -1, point_voxel[n] = -1 for points without a prediction.          */
+int st_devoxelize(const float *xyz, int64_t n_points, const int64_t *pair_point, const int32_t *pair_block,
+                  const int32_t *pair_voxel, int64_t n_pairs, const float *block_centres, float block_size,
+                  const float *voxel_medial, const int32_t *voxel_class, float *point_medial,
+                  int32_t *point_class, int32_t *point_voxel, void *stream);
+
 /* ------------------------------------------------------------------ K4/K5/K6 gather convolution, fused epilogue
  * replaces spconv Fsp.indice_subm_conv / indice_conv / indice_inverse_conv (ConvAlgo.Native)
  * followed by nn.BatchNorm1d(eval), the residual add, nn.ReLU and torch.cat

@@ -102,6 +102,34 @@ def infer(params, xyz, rgb, voxel_size=0.01, block_size=4, buffer_size=0.4, eps=
     return res
 
 
+def infer_points(params, xyz, rgb, voxel_size=0.01, block_size=4, buffer_size=0.4, eps=1e-4, dtype=np.float32):
+    """Devoxelised inference: every input point takes the prediction of its voxel
+    (pc_voxel_id of voxelize_block, which the reference computes in dataset.py:214 and drops) from the block whose
+    inner half-open cube contains the point; class -1 / zero vector where no block covers it."""
+    centres, members = compute_blocks(xyz, block_size, buffer_size)
+    medial = np.zeros((len(xyz), 3), F32)
+    cls = np.full(len(xyz), -1, np.int64)
+    feats, coords, ids = [], [], []
+    off = 0
+    for b, (c, m) in enumerate(zip(centres, members)):
+        vox, zyx, pcid, _ = voxelize_block(np.concatenate([xyz[m], rgb[m]], 1), voxel_size)
+        feats.append(vox)
+        coords.append(np.concatenate([np.full((len(zyx), 1), b, np.int32), zyx], 1))
+        inner = cube_mask(xyz[m], c, block_size) & (pcid >= 0)
+        ids.append((np.asarray(m)[inner], pcid[inner] + off))
+        off += len(vox)
+    if not feats:
+        return dict(medial_vector=medial, class_l=cls)
+    feats, coords = np.concatenate(feats), np.concatenate(coords)
+    out = U.forward(params, feats[:, :3], coords, eps=eps, dtype=dtype)
+    vmed = (np.exp(out["radius"]) * out["direction"]).astype(F32)
+    vcls = out["class_l"].argmax(1)
+    for pts, rows in ids:
+        medial[pts] = vmed[rows]
+        cls[pts] = vcls[rows]
+    return dict(medial_vector=medial, class_l=cls)
+
+
 # ----------------------------------------------------------------------------- post-processing
 def branch_length(xyz):
     d = xyz[1:] - xyz[:-1]

@@ -373,3 +373,49 @@ extern "C" int st_voxelize(const float *points, int64_t n, int ld, const int32_t
     *n_voxels_host = (int64_t)last_rank + last_flag;
     return ST_OK;
 }
+
+// ------------------------------------------------------------------------------------ devoxelise
+// Per-voxel predictions broadcast back to EVERY input point (the reference computes
+// pc_voxel_id in dataset.py:214 and then drops it).  A point can sit in several blocks (buffers overlap); it takes
+// the prediction of the block whose inner half-open cube contains it (util/maths.py:135-155), which is unique.
+// Points of dropped blocks / dropped by the voxeliser keep class -1, voxel -1 and a zero vector.
+__global__ void k_devoxelize(const float *__restrict__ xyz, const int64_t *__restrict__ pair_point, const int32_t *__restrict__ pair_block,
+                             const int32_t *__restrict__ pair_voxel, int64_t n_pairs, const float *__restrict__ centres, float half,
+                             const float *__restrict__ vmedial, const int32_t *__restrict__ vclass, float *__restrict__ pmedial,
+                             int32_t *__restrict__ pclass, int32_t *__restrict__ pvoxel) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pairs) return;
+    const int v = __ldg(pair_voxel + t);
+    if (v < 0) return;
+    const int64_t p = __ldg(pair_point + t);
+    const int b = __ldg(pair_block + t);
+    bool inside = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float c = __ldg(centres + 3 * (size_t)b + a), x = __ldg(xyz + 3 * p + a);
+        inside = inside && x >= __fsub_rn(c, half) && x < __fadd_rn(c, half);
+    }
+    if (!inside) return;
+    pmedial[3 * p] = __ldg(vmedial + 3 * (size_t)v);
+    pmedial[3 * p + 1] = __ldg(vmedial + 3 * (size_t)v + 1);
+    pmedial[3 * p + 2] = __ldg(vmedial + 3 * (size_t)v + 2);
+    pclass[p] = __ldg(vclass + v);
+    pvoxel[p] = v;
+}
+
+extern "C" int st_devoxelize(const float *xyz, int64_t n_points, const int64_t *pair_point, const int32_t *pair_block,
+                             const int32_t *pair_voxel, int64_t n_pairs, const float *block_centres, float block_size,
+                             const float *voxel_medial, const int32_t *voxel_class, float *point_medial, int32_t *point_class,
+                             int32_t *point_voxel, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_points == 0) return ST_OK;
+    ST_CHECK_CUDA(cudaMemsetAsync(point_medial, 0, (size_t)n_points * 3 * sizeof(float), s));
+    ST_CHECK_CUDA(cudaMemsetAsync(point_class, 0xFF, (size_t)n_points * sizeof(int32_t), s));
+    ST_CHECK_CUDA(cudaMemsetAsync(point_voxel, 0xFF, (size_t)n_points * sizeof(int32_t), s));
+    if (n_pairs == 0) return ST_OK;
+    k_devoxelize<<<(unsigned)cdiv(n_pairs, 256), 256, 0, s>>>(xyz, pair_point, pair_block, pair_voxel, n_pairs, block_centres,
+                                                              (float)(block_size / 2), voxel_medial, voxel_class, point_medial,
+                                                              point_class, point_voxel);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

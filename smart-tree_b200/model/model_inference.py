@@ -4,6 +4,8 @@ from pathlib import Path
 
 import torch
 
+from .. import ops
+
 from ..data_types.cloud import Cloud
 from ..dataset.dataset import load_dataloader
 from ..engine import SmartTreeEngine
@@ -62,6 +64,31 @@ class ModelInference:
             return clouds[0]
         return Cloud(xyz=torch.cat([c.xyz for c in clouds]), rgb=torch.cat([c.rgb for c in clouds]),
                      medial_vector=torch.cat([c.medial_vector for c in clouds]), class_l=torch.cat([c.class_l for c in clouds]))
+
+    @torch.no_grad()
+    def forward_points(self, cloud: Cloud) -> Cloud:
+        """Devoxelised inference (not in the reference, which keeps one labelled point per voxel and discards
+        pc_voxel_id, dataset.py:214): EVERY input point gets the medial vector and class of its voxel, taken from
+        the block whose inner cube contains the point.  class_l = -1 (zero vector) where there is no prediction
+        (blocks of <= 20 points).  Same order and length as `cloud`."""
+        if cloud.xyz.device.type != "cuda":
+            cloud = cloud.to_device(self.device)
+        xyz = cloud.xyz.contiguous().float()
+        n, dev = xyz.shape[0], xyz.device
+        ds = load_dataloader(cloud, self.voxel_size, self.block_size, self.buffer_size, self.num_workers, self.batch_size)
+        medial = torch.zeros((n, 3), dtype=torch.float32, device=dev)
+        cls = torch.full((n,), -1, dtype=torch.int32, device=dev)
+        for bb in ds.voxelize_chunks():
+            if bb.feats.shape[0] == 0:
+                continue
+            preds = self.model.forward(bb.feats[:, :3], bb.coords, fused_outputs=True)
+            pm, pc, _ = ops.devoxelize(xyz, bb.point_index.contiguous(), bb.point_block.contiguous(), bb.pc_voxel_id.contiguous(),
+                                       bb.block_centres.contiguous().float(), self.block_size,
+                                       preds["medial_vector"].contiguous(), preds["class_idx"].int().contiguous())
+            hit = pc >= 0
+            medial = torch.where(hit.unsqueeze(1), pm, medial)
+            cls = torch.where(hit, pc, cls)
+        return Cloud(xyz=cloud.xyz, rgb=cloud.rgb, medial_vector=medial, class_l=cls.long().unsqueeze(1))
 
     @staticmethod
     def from_cfg(cfg):

@@ -16,7 +16,7 @@ LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3}
+                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3, "devoxelize": 1}
 
 
 def _count(op):
@@ -113,6 +113,23 @@ def voxelize(points, point_block, block_lo, block_grid, vsize):
                                block_lo.shape[0], float(vsize), _ptr(pc), _ptr(rep), _ptr(coords), C.byref(m),
                                _ptr(ws), ws.numel(), _stream()), "st_voxelize")
     return pc, rep[:m.value], coords[:m.value]
+
+
+def devoxelize(xyz, pair_point, pair_block, pair_voxel, block_centres, block_size, voxel_medial, voxel_class):
+    """Per-voxel predictions back to every input point (st_devoxelize).  Returns point_medial [n,3] f32,
+    point_class [n] i32 (-1 = no prediction), point_voxel [n] i32 (-1 = none)."""
+    lib = _lib.load()
+    _req(xyz, F32, "xyz"); _req(pair_point, I64, "pair_point"); _req(pair_block, I32, "pair_block"); _req(pair_voxel, I32, "pair_voxel")
+    _req(block_centres, F32, "block_centres"); _req(voxel_medial, F32, "voxel_medial"); _req(voxel_class, I32, "voxel_class")
+    n, dev = xyz.shape[0], xyz.device
+    pm = torch.empty((n, 3), dtype=F32, device=dev)
+    pc = torch.empty(n, dtype=I32, device=dev)
+    pv = torch.empty(n, dtype=I32, device=dev)
+    _count("devoxelize")
+    _lib.check(lib.st_devoxelize(_ptr(xyz), n, _ptr(pair_point), _ptr(pair_block), _ptr(pair_voxel), pair_point.shape[0], _ptr(block_centres),
+                                 float(block_size), _ptr(voxel_medial), _ptr(voxel_class), _ptr(pm), _ptr(pc), _ptr(pv), _stream()),
+               "st_devoxelize")
+    return pm, pc, pv
 
 
 # ------------------------------------------------------------------ coordinate table / maps

@@ -593,6 +593,39 @@ def test_inference_other_configs_match_oracle(weights, voxel, block, chunk):
     assert (lc.class_l.cpu().numpy().reshape(-1) == lab["class_l"]).mean() > 0.999
 
 
+@pytest.mark.parametrize("block,chunk", [(4, None), (0.64, 5)])
+def test_devoxelised_inference_matches_oracle(block, chunk):
+    """every input point gets its voxel's prediction from the block whose inner cube holds it; which
+    voxel a point maps to is exact (integer work), the values within the network tolerance; points of dropped blocks
+    keep class -1."""
+    from smart_tree_b200.data_types.cloud import Cloud
+    from smart_tree_b200.dataset import dataset as ds_mod
+    from smart_tree_b200.model.model_inference import ModelInference
+    tr = _synth(4, 12000)
+    xyz = P.centre_cloud(tr.xyz)
+    if block != 4:
+        xyz = xyz[xyz[:, 1] < 1.4]
+    xyz = np.concatenate([xyz, xyz[:3] + np.float32(40.0)])           # three far-away points: a block of <= 20 points
+    old = ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH
+    try:
+        if chunk:
+            ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH = chunk
+        mi = ModelInference(None, os.path.join(WEIGHTS, "noble-elevator-58_model_weights.pt"), 0.02, block, 0.4, device=torch.device(DEV))
+        pc = mi.forward_points(Cloud(xyz=_t(xyz), rgb=torch.zeros(len(xyz), 3, device=DEV)))
+    finally:
+        ds_mod.SingleTreeInference.MAX_BLOCKS_PER_LAUNCH = old
+    ref = P.infer_points(U.to_numpy_params(_load("noble-elevator-58")), xyz, np.zeros_like(xyz), 0.02, block, 0.4)
+    assert len(pc) == len(xyz) and np.array_equal(pc.xyz.cpu().numpy(), xyz)
+    cls = pc.class_l.cpu().numpy().reshape(-1)
+    assert np.array_equal(cls < 0, ref["class_l"] < 0) and np.all(cls[-3:] == -1)
+    mv = pc.medial_vector.cpu().numpy()
+    assert np.all(mv[cls < 0] == 0)
+    assert np.abs(mv - ref["medial_vector"]).max() <= 1e-3 * np.abs(ref["medial_vector"]).max()
+    assert (cls == ref["class_l"]).mean() > 0.999
+    # points of one voxel share one prediction: as many distinct vectors as the oracle has
+    assert len(np.unique(mv, axis=0)) == len(np.unique(ref["medial_vector"], axis=0))
+
+
 # ------------------------------------------------------------------ end to end through the reference-shaped API
 def test_pipeline_end_to_end_matches_oracle():
     from smart_tree_b200.config import instantiate, load_config

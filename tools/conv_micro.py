@@ -23,7 +23,7 @@ MORTON = bool(int(os.environ.get("ST_MORTON", "1")))
 coords = bb.coords.contiguous()
 if MORTON:
     coords = coords[ops.morton_perm(coords).long()].contiguous()
-levels = build_levels(coords, 4, morton=MORTON)
+levels = build_levels(coords, 4, morton=MORTON, inverse_plan=(impl == "tcinv"))
 print("levels", [l.n for l in levels], "z-order" if MORTON else "input order")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 cases = [(8, 8, 0), (16, 8, 0), (16, 16, 1), (32, 16, 1), (32, 32, 2), (64, 32, 2), (64, 64, 3)]
@@ -32,8 +32,29 @@ if only:
 if os.environ.get("ST_TC_DBG"):
     from smart_tree_b200 import _lib as _l
     _l.load().st_debug_tc_set(int(os.environ["ST_TC_DBG"]))
+if impl == "tcinv":
+    cases = [c for c in [(16, 8, 0), (32, 16, 1), (64, 32, 2)] if only is None or c == only]
 for cin, cout, li in cases:
     lv = levels[li]
+    if impl == "tcinv":
+        x = torch.randn(levels[li + 1].n, cin, device=dev)
+        w = torch.randn(27, cin, cout, device=dev) / (4 * cin) ** 0.5
+        wtc = ops.conv_tc_prepare(w)
+        out = torch.empty(lv.n, cout, device=dev)
+        run = lambda: ops.conv_gather_tc_inv(x, lv.inverse_plan(), wtc, 27, cin, cout, lv.n, out=out, relu=True)
+        for _ in range(3):
+            run()
+        ts = []
+        for _ in range(10):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); run(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        us = float(np.median(ts))
+        byt = 4 * (lv.n * cout + levels[li + 1].n * cin)
+        print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s")
+        continue
     x = torch.randn(lv.n, cin, device=dev)
     w = torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5
     wtc = ops.conv_tc_prepare(w) if impl in ("tc", "tp") else None
@@ -59,6 +80,20 @@ for cin, cout, li in cases:
     byt = 4 * lv.n * (cin + cout)
     print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s  ({byt / us / 1e3 / 6525.2 * 100:5.2f}% of measured HBM peak)")
 
+if only and impl == "tcinv":
+    import ctypes as C
+    from smart_tree_b200 import _lib
+    lib = _lib.load()
+    buf = (C.c_longlong * 1024)()
+    lib.st_debug_tc_trace.argtypes = [C.c_void_p]
+    lib.st_debug_tc_trace(buf)
+    t = np.array(buf[:]).reshape(8, 128)
+    t0 = t[5, 0]
+    nt = int((t[5] > 0).sum())
+    print("tile starts (cycles):", (t[5, :nt] - t0).tolist())
+    names = {6: "P.start", 7: "P.loads", 0: "P.slot_ok", 1: "P.arrived", 4: "M.b_full", 2: "M.a_full", 3: "M.commit"}
+    for g in range(0, 24):
+        print(g, "  ".join(f"{names[k]}={t[k, g] - t0:6d}" for k in (6, 7, 0, 1, 4, 2, 3)))
 if only and impl in ("tc", "tp"):
     import ctypes as C
     from smart_tree_b200 import _lib
