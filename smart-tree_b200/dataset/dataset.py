@@ -50,6 +50,22 @@ class SingleTreeInference:
         self.point_index, self.point_block = pidx, pblk
         self.block_lo, self.block_hi = lo, hi
 
+    def keep_shard(self, rank: int, world: int):
+        """Multi-GPU plots: keep blocks rank, rank+world, ... of the (deterministic) block list.
+        Blocks are independent forward passes (eval-mode BatchNorm), so every rank labels its own blocks and the
+        labelled voxels are exchanged afterwards (dist.gather_labelled).  `block_global` = index in the full list."""
+        nb = int(self.block_centres.shape[0])
+        dev = self.point_block.device
+        self.block_global = torch.arange(rank, nb, world, device=dev)
+        if world == 1:
+            return self
+        sel = (self.point_block % world) == rank
+        self.point_index = self.point_index[sel].contiguous()
+        self.point_block = torch.div(self.point_block[sel], world, rounding_mode="floor").to(self.point_block.dtype).contiguous()
+        self.block_ids, self.block_centres = self.block_ids[rank::world], self.block_centres[rank::world]
+        self.block_lo, self.block_hi = self.block_lo[rank::world].contiguous(), self.block_hi[rank::world].contiguous()
+        return self
+
     MAX_BLOCKS_PER_LAUNCH = 16384      # the batch index has 15 bits in the packed voxel key
 
     def voxelize_chunks(self):

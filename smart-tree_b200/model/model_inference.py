@@ -34,7 +34,7 @@ class ModelInference:
         self.last_batch = None
 
     @torch.no_grad()
-    def forward(self, cloud: Cloud, return_masked=True) -> Cloud:
+    def forward(self, cloud: Cloud, return_masked=True, shard=None) -> Cloud:
         """Tiles the cloud into blocks, voxelises, runs the network on all blocks as one batch
         (eval-mode BatchNorm makes the result independent of how blocks are batched) and returns the
         labelled voxel cloud (on the device; the reference returns it on the CPU and the pipeline
@@ -43,10 +43,14 @@ class ModelInference:
             cloud = cloud.to_device(self.device)
         with section("infer.blocks"):
             ds = load_dataloader(cloud, self.voxel_size, self.block_size, self.buffer_size, self.num_workers, self.batch_size)
-        clouds, all_preds = [], []
+            if shard is not None:          # (rank, world): this rank's blocks only; self.last_voxel_block = their global ids
+                ds.keep_shard(*shard)
+        clouds, all_preds, vblocks = [], [], []
+        chunk0 = 0
         for bb in ds.voxelize_chunks():
             self.last_batch = bb
             if bb.feats.shape[0] == 0:
+                chunk0 += ds.MAX_BLOCKS_PER_LAUNCH
                 continue
             with section("infer.levels"):
                 levels = self.model.build_levels(bb.coords)
@@ -57,6 +61,11 @@ class ModelInference:
                            class_l=preds["class_idx"].long().unsqueeze(1))
                 self.last_preds = preds
                 clouds.append(lc.filter(bb.mask) if return_masked else lc)
+                if shard is not None:
+                    vb = ds.block_global[(bb.coords[:, 0].long() + chunk0)]
+                    vblocks.append(vb[bb.mask] if return_masked else vb)
+            chunk0 += ds.MAX_BLOCKS_PER_LAUNCH
+        self.last_voxel_block = torch.cat(vblocks) if vblocks else torch.zeros(0, dtype=torch.int64, device=cloud.xyz.device)
         if not clouds:
             z = torch.zeros(0, 3, device=cloud.xyz.device)
             return Cloud(xyz=z, rgb=z.clone(), medial_vector=z.clone(), class_l=torch.zeros(0, 1, dtype=torch.int64, device=z.device))

@@ -66,6 +66,35 @@ class Pipeline:
                 save_skeleton(s, f"{self.save_path}/skeleton_{s._id}.npz")
         return skeleton
 
+    def process_plot_sharded(self, cloud: Cloud, rank: int, world: int, exchange=None):
+        """Multi-GPU plot (BASELINE config C5): every rank holds the plot, labels blocks
+        rank, rank+world, ... and all-gathers the labelled voxels (dist.gather_labelled, restored to block order so the
+        merged cloud is identical to the single-GPU one); every rank then builds the same neighbour graph and
+        components and skeletonises components rank, rank+world, ... of the size-ordered list.  Returns this rank's
+        DisjointTreeSkeleton (skeleton ids = global component indices); gather them with dist.gather_skeletons.
+        `exchange(parts) -> list of all ranks' parts` replaces the collective (tests run the ranks in one process)."""
+        from . import dist as stdist
+        cloud = self.preprocessing(cloud.to_device(self.device))
+        lc = self.model_inference.forward(cloud, shard=(rank, world)).to_device(self.device)
+        part = stdist.labelled_part(lc, self.model_inference.last_voxel_block)
+        parts = exchange(part) if exchange is not None else stdist.gather_labelled(part, device=self.device)
+        lc = stdist.merge_labelled(parts, self.device)
+        self.labelled_cloud = lc
+        branch_cloud = lc.filter_by_class(self.branch_classes)
+        skeleton = self.skeletonizer.forward(branch_cloud, post=self._fused_post(), shard=(rank, world))
+        done = getattr(skeleton, "post_applied", None) or {}
+        if not done:
+            # object-level post-processing: only the globally first skeleton is pruned (quirk C-18)
+            if self.prune_skeletons and skeleton.skeletons and skeleton.skeletons[0]._id == 0:
+                skeleton.prune(min_length=self.min_skeleton_length, min_radius=self.min_skeleton_radius)
+            if self.repair_skeletons:
+                skeleton.repair(device=self.device)
+            if self.smooth_skeletons:
+                skeleton.smooth(self.smooth_kernel_size)
+        elif self.smooth_skeletons and "smooth" not in done:
+            skeleton.smooth(self.smooth_kernel_size)
+        return skeleton
+
     def _fused_post(self):
         """The part of post_process (pipeline.py:76-88) the skeletoniser can run on the device in its branch
         assembly launch.  Steps are order-dependent (prune -> repair -> smooth), so fusing stops at the first

@@ -97,7 +97,7 @@ class Skeletonizer:
                                                            _flat=(store, rows_l[i], lens_l[i], False))
         return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
 
-    def forward(self, cloud: Cloud, post: dict = None) -> DisjointTreeSkeleton:
+    def forward(self, cloud: Cloud, post: dict = None, shard=None) -> DisjointTreeSkeleton:
         """`post` (optional, not in the reference signature): post-processing to fuse into the device-side branch
         assembly -- see _emit.  The returned skeleton records it in `.post_applied` so that Pipeline.post_process
         does not repeat it."""
@@ -120,6 +120,13 @@ class Skeletonizer:
         # skeletonize.py:43-45
         with section("skel.components"):
             label, roots, sizes = graph.ranked_components(self.minimum_graph_vertices)
+        self.component_ids = list(range(int(roots.shape[0])))
+        if shard is not None:
+            # multi-GPU plots: every rank builds the same graph and components (cheap, redundant) and then
+            # extracts the skeletons of components rank, rank+world, ... of the size-ordered list only
+            rank, world = shard
+            self.component_ids = self.component_ids[rank::world]
+            roots, sizes = roots[rank::world], sizes[rank::world]
         ncomp = int(roots.shape[0])
         if ncomp == 0:
             self.last = dict(keep=keep, n_components=0)
@@ -167,8 +174,13 @@ class Skeletonizer:
         # skeletonize.py:87-93
         with section("skel.sample_tree"):
             path, blen, bpar, cnb, cnp = ops.sample_tree(sub_medial, sub_radius, pred_local, tdist, off32, _cell_size(sub_radius))
+        if shard is not None and post and (not self.component_ids or self.component_ids[0] != 0):
+            post = {k: v for k, v in post.items() if k != "prune"}        # only the globally first skeleton is pruned (quirk C-18)
         with section("skel.emit"):
             skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post)
+            if shard is not None:
+                for sk_, gid in zip(skeletons, self.component_ids):
+                    sk_._id = gid                                            # global (size-ordered) component index
         self.last = dict(keep=keep, order=order, comp_off=comp_off, pred=pred_local, dist=dist, tree_dist=tdist, roots=src,
                          path=path, branch_len=blen, branch_parent=bpar, comp_n_branches=cnb, comp_n_path=cnp,
                          n_components=ncomp, edges=graph.edges, edge_weights=graph.edge_weights)

@@ -78,3 +78,46 @@ def test_shard_covers_all_units():
     units = list(range(11))
     parts = [stdist.shard(units, r, 4) for r in range(4)]
     assert sorted(sum(parts, [])) == units
+
+
+# ---------------------------------------------------------------- block-sharded plots: labelled-voxel exchange
+def _fake_labelled(nblocks, seed=0):
+    """A labelled voxel cloud in block order, as ModelInference.forward returns it, with its per-voxel block ids."""
+    from smart_tree_b200.data_types.cloud import Cloud
+    g = torch.Generator().manual_seed(seed)
+    per = [int(v) for v in torch.randint(0, 7, (nblocks,), generator=g)]           # some blocks contribute nothing
+    blk = torch.repeat_interleave(torch.arange(nblocks), torch.tensor(per))
+    n = int(blk.shape[0])
+    lc = Cloud(xyz=torch.randn(n, 3, generator=g), rgb=torch.rand(n, 3, generator=g), medial_vector=torch.randn(n, 3, generator=g),
+               class_l=torch.randint(0, 2, (n, 1), generator=g))
+    return lc, blk
+
+
+def _labelled_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    stdist.init_from_env(backend="gloo")
+    lc, blk = _fake_labelled(11)
+    mine = (blk % world) == rank                                    # this rank labelled blocks rank, rank+world, ...
+    part = stdist.labelled_part(lc.filter(mine), blk[mine])
+    merged = stdist.merge_labelled(stdist.gather_labelled(part, device=torch.device("cpu")))
+    out[rank] = (merged.xyz.numpy().tobytes(), merged.rgb.numpy().tobytes(), merged.medial_vector.numpy().tobytes(),
+                 merged.class_l.numpy().tobytes())
+    dist.destroy_process_group()
+
+
+def test_labelled_voxel_exchange_world2_restores_block_order():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_labelled_worker, args=(2, port, out), nprocs=2, join=True)
+    lc, _ = _fake_labelled(11)
+    expect = (lc.xyz.numpy().tobytes(), lc.rgb.numpy().tobytes(), lc.medial_vector.numpy().tobytes(), lc.class_l.numpy().tobytes())
+    assert out[0] == expect and out[1] == expect                    # bit-identical to the unsharded cloud on every rank
+
+
+def test_merge_labelled_any_world_single_process():
+    lc, blk = _fake_labelled(23, seed=3)
+    for world in (1, 3, 8):
+        parts = [stdist.labelled_part(lc.filter((blk % world) == r), blk[(blk % world) == r]) for r in range(world)]
+        m = stdist.merge_labelled(parts)
+        assert torch.equal(m.xyz, lc.xyz) and torch.equal(m.medial_vector, lc.medial_vector) and torch.equal(m.class_l, lc.class_l)

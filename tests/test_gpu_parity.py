@@ -626,6 +626,56 @@ def test_devoxelised_inference_matches_oracle(block, chunk):
     assert len(np.unique(mv, axis=0)) == len(np.unique(ref["medial_vector"], axis=0))
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_block_and_component_sharded_plot_equals_single_gpu(world):
+    """SURVEY 8(e) / config C5 at oracle scale: a plot of three trees, blocks dealt round-robin to `world` ranks, the
+    labelled voxels exchanged and restored to block order, components dealt round-robin for skeletonisation.  The
+    ranks run one after the other in this process (the collective itself is covered by the gloo tests); the union
+    of their skeletons must be bit-identical to Pipeline.process_cloud on one GPU."""
+    from smart_tree_b200 import dist as stdist
+    from smart_tree_b200.data_types.cloud import Cloud
+    from smart_tree_b200.dataset.augmentations import AugmentationPipeline, CentreCloud
+    from smart_tree_b200.model.model_inference import ModelInference
+    from smart_tree_b200.pipeline import Pipeline
+    from smart_tree_b200.skeleton.skeletonize import Skeletonizer
+    dev = torch.device(DEV)
+    xyz = np.concatenate([_synth(s, 7000).xyz + np.float32([4.0 * s, 0, 0]) for s in range(3)])
+    mi = ModelInference(None, os.path.join(WEIGHTS, "noble-elevator-58_model_weights.pt"), 0.02, 1.28, 0.4, device=dev)
+
+    def make_pipe():
+        return Pipeline(AugmentationPipeline([CentreCloud()]), mi, Skeletonizer(16, 0.02, 32, device=dev), repair_skeletons=True,
+                        smooth_skeletons=True, smooth_kernel_size=11, prune_skeletons=True, min_skeleton_radius=0.01,
+                        min_skeleton_length=0.02, device=dev)
+
+    cloud = Cloud(xyz=_t(xyz), rgb=torch.zeros(len(xyz), 3, device=DEV))
+    single = make_pipe().process_cloud(cloud=cloud)
+    assert len(single.skeletons) >= 2
+    pipe = make_pipe()
+    pre = pipe.preprocessing(cloud)
+    parts = []
+    for r in range(world):
+        lc = mi.forward(pre, shard=(r, world))
+        parts.append(stdist.labelled_part(lc, mi.last_voxel_block))
+    assert sum(p[0].shape[0] for p in parts) == pipe_labelled_count(make_pipe(), cloud)
+    got = {}
+    for r in range(world):
+        sk = pipe.process_plot_sharded(cloud, r, world, exchange=lambda part: parts)
+        for s in sk.skeletons:
+            assert s._id % world == r and s._id not in got
+            got[s._id] = s
+    assert sorted(got) == list(range(len(single.skeletons)))
+    for i, ref in enumerate(single.skeletons):
+        assert sorted(got[i].branches) == sorted(ref.branches)
+        for bid, b in ref.branches.items():
+            g = got[i].branches[bid]
+            assert g.parent_id == b.parent_id and torch.equal(g.xyz, b.xyz) and torch.equal(g.radii.reshape(-1), b.radii.reshape(-1))
+
+
+def pipe_labelled_count(pipe, cloud):
+    pipe.process_cloud(cloud=cloud)
+    return int(pipe.labelled_cloud.xyz.shape[0])
+
+
 # ------------------------------------------------------------------ end to end through the reference-shaped API
 def test_pipeline_end_to_end_matches_oracle():
     from smart_tree_b200.config import instantiate, load_config
