@@ -332,6 +332,88 @@ __global__ void __launch_bounds__(256) k_sssp_big(const int32_t *__restrict__ ro
     }
 }
 
+// Near-far relaxation (as k_sssp) for graphs too large for register-resident ownership: a warp strides over
+// arbitrarily many groups of 32 vertices and keeps their poll state (last seen change counter, parked candidate)
+// in global memory -- only the owning warp ever touches it.  The flag variant above improved every vertex dozens
+// of times on a 1.3 M-vertex graph (77 ms); the distance-ordered schedule is what keeps the work near-linear.
+__global__ void __launch_bounds__(256) k_sssp_nf_big(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                                     const float *__restrict__ w, int n, float *dist, int *dirty, int *seen_g, float *pend_g,
+                                                     SsspCtl *ctl, float delta, int npass) {
+    unsigned phase = 0;
+    const int lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int w0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int ngroups = (n + 31) >> 5;
+    float T = delta;
+    for (unsigned chunk = 0;; ++chunk) {
+        bool consumed = false;
+        float pmin = ST_INF;
+        for (int pass = 0; pass < npass; ++pass) {
+            const bool last = pass == npass - 1;
+            for (int g = w0; g < ngroups; g += nwarps) {
+                const int v = (g << 5) + lane;
+                const bool in = v < n;
+                const int sn = in ? seen_g[v] : 0;
+                const int cnt = in ? __ldcg(dirty + v) : sn;
+                float pd = in ? pend_g[v] : ST_INF;
+                const bool woke = cnt != sn || pd <= T;
+                unsigned mask = __ballot_sync(0xffffffffu, woke);
+                if (!mask) { if (last) pmin = fminf(pmin, pd); continue; }
+                if (in && cnt != sn) seen_g[v] = cnt;
+                __threadfence();          // counter observed -> the distance that caused it is visible
+                if (woke) pd = ST_INF;
+                while (mask) {            // woken vertices one after the other, each relaxed by the whole warp
+                    const int l = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int vv = (g << 5) + l;
+                    const int b = __ldg(row_ptr + vv), e = __ldg(row_ptr + vv + 1);
+                    const float cur = __ldcg(dist + vv);
+                    float best = cur;
+                    int u0 = -1, u1 = -1;
+                    float c0 = ST_INF, c1 = ST_INF, d0 = 0.f, d1 = 0.f, ww0 = 0.f, ww1 = 0.f;
+                    if (b + lane < e) { u0 = __ldg(col + b + lane); ww0 = __ldg(w + b + lane); d0 = __ldcg(dist + u0); c0 = __fadd_rn(d0, ww0); }
+                    if (b + 32 + lane < e) { u1 = __ldg(col + b + 32 + lane); ww1 = __ldg(w + b + 32 + lane); d1 = __ldcg(dist + u1); c1 = __fadd_rn(d1, ww1); }
+                    best = fminf(best, fminf(c0, c1));
+                    for (int a = b + 64 + lane; a < e; a += 32)
+                        best = fminf(best, __fadd_rn(__ldcg(dist + __ldg(col + a)), __ldg(w + a)));
+                    for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                    if (best < cur) {
+                        if (best <= T) {
+                            consumed = true;
+                            if (lane == 0) { __stcg(dist + vv, best); __threadfence(); }
+                            __syncwarp();
+                            if (u0 >= 0 && __fadd_rn(best, ww0) < d0) atomicAdd(dirty + u0, 1);
+                            if (u1 >= 0 && __fadd_rn(best, ww1) < d1) atomicAdd(dirty + u1, 1);
+                            for (int a = b + 64 + lane; a < e; a += 32) {
+                                const int u = __ldg(col + a);
+                                if (__fadd_rn(best, __ldg(w + a)) < __ldcg(dist + u)) atomicAdd(dirty + u, 1);
+                            }
+                        } else if (lane == l) {
+                            pd = best;        // parked until the threshold reaches it (or a neighbour wakes it again)
+                        }
+                    }
+                }
+                if (in && woke) pend_g[v] = pd;
+                if (last) pmin = fminf(pmin, pd);
+            }
+        }
+        for (int o = 16; o; o >>= 1) pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        if (lane == 0 && pmin < ST_INF) atomicMin(&ctl->min_pend[chunk % 3], __float_as_uint(pmin));
+        if (__syncthreads_or(consumed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->changed[(chunk + 1) % 3] = 0; ctl->min_pend[(chunk + 1) % 3] = 0x7F800000u; }
+        grid_barrier(&ctl->barrier, phase);
+        const unsigned any = *(volatile unsigned *)&ctl->changed[chunk % 3];
+        const unsigned mp = *(volatile unsigned *)&ctl->min_pend[chunk % 3];
+        if (!any) {
+            if (mp == 0x7F800000u) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) ctl->chunks = chunk + 1;
+                break;
+            }
+            T = fmaxf(T, __uint_as_float(mp)) + delta;
+        }
+    }
+}
+
 __global__ void k_sssp_seed(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int *dirty,
                             const int32_t *__restrict__ sources, int ns) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -391,7 +473,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     cudaStream_t s = (cudaStream_t)stream;
     if (sweeps_host) *sweeps_host = 0;
     if (n == 0) return ST_OK;
-    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 4n bytes) required");
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 12n bytes) required");
     int device = 0;
     ST_CHECK_CUDA(cudaGetDevice(&device));
     SsspCtl *ctl = (SsspCtl *)ctl_workspace;
@@ -419,9 +501,27 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     int npass = SSSP_NF_PASSES;
     if (const char *e = getenv("ST_SSSP_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 1024) npass = v; }
     void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta, (void *)&npass};
-    // near-far counter variant when every resident warp can own its vertices in registers, flag variant otherwise
-    const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n;
-    ST_CHECK_CUDA(cudaLaunchCooperativeKernel(small ? (const void *)k_sssp : (const void *)k_sssp_big, dim3(blocks), dim3(256), args, 0, s));
+    // near-far counter variant: poll state in registers when every resident warp can own its vertices there, in global
+    // memory otherwise (ctl_workspace holds dirty[n], seen[n], pend[n]); ST_SSSP_FLAGS=1 forces the old flag variant
+    const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n && !getenv("ST_SSSP_FORCE_BIG");      // (env: tests exercise the large-graph kernel)
+    if (small) {
+        ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
+    } else if (getenv("ST_SSSP_FLAGS")) {
+        ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_big, dim3(blocks), dim3(256), args, 0, s));
+    } else {
+        int *seen_g = dirty + n;
+        float *pend_g = (float *)(dirty + 2 * n);
+        ST_CHECK_CUDA(cudaMemsetAsync(seen_g, 0, n * sizeof(int), s));
+        k_sssp_init<<<g, 256, 0, s>>>(pend_g, (int)n);
+        ST_CHECK_LAUNCH();
+        int blocks2 = 0;
+        rc = coop_grid((const void *)k_sssp_nf_big, 256, device, blocks2);
+        if (rc) return rc;
+        if (blocks2 > (int)g) blocks2 = (int)g;
+        void *args2[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&seen_g, (void *)&pend_g,
+                         (void *)&ctl, (void *)&delta, (void *)&npass};
+        ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_nf_big, dim3(blocks2), dim3(256), args2, 0, s));
+    }
     k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
     ST_CHECK_LAUNCH();
     k_sssp_finish<<<g, 256, 0, s>>>(dist, (int)n);

@@ -455,7 +455,7 @@ def sssp(row_ptr, col, w, n, sources, want_sweeps=False, delta=0.0):
     dev = row_ptr.device
     dist = torch.empty(n, dtype=F32, device=dev)
     pred = torch.empty(n, dtype=I32, device=dev)
-    ctl = torch.empty(64 + n, dtype=I32, device=dev)
+    ctl = torch.empty(64 + 3 * n, dtype=I32, device=dev)      # control block + dirty[n] (+ seen[n], pend[n] for large graphs)
     sweeps = C.c_int32(0)
     _count("sssp")
     _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], float(delta), _ptr(dist), _ptr(pred),

@@ -478,7 +478,14 @@ def test_connected_components_exact():
     assert sum(len(c) for c in comps) == len(med)
 
 
-def test_sssp_and_tree_distances_exact():
+@pytest.mark.parametrize("variant", ["registers", "large-graph", "large-graph-flags"])
+def test_sssp_and_tree_distances_exact(variant, monkeypatch):
+    """The three relaxation schedules (poll state in registers / in global memory for graphs beyond the resident
+    capacity / the older flag variant) all reach the same fp32 fixed point and predecessors."""
+    if variant != "registers":
+        monkeypatch.setenv("ST_SSSP_FORCE_BIG", "1")
+    if variant == "large-graph-flags":
+        monkeypatch.setenv("ST_SSSP_FLAGS", "1")
     ops = _ops()
     xyz, med, rad, e, w = _graph_case()
     comp = S.connected_components(len(med), e, 32)[0]
