@@ -189,10 +189,13 @@ template <int CIN>
 __device__ __forceinline__ unsigned long long stage_mask_of(uint32_t tap_mask, int nmain, int nstages) {
     if (tap_mask == 0u) tap_mask = 1u;                   // an empty tile still runs one stage (the accumulator must be defined)
     unsigned long long m = 0ull;
-    for (int s = 0; s < nmain; ++s)
-        if (tap_mask & stage_tap_bits<CIN>(s)) m |= 1ull << s;
-    for (int s = nmain; s < nstages; ++s) m |= 1ull << s;
-    return m;
+    for (uint32_t r = tap_mask; r; r &= r - 1) {         // the 1-8 taps that occur: stages [t*CIN/32, ((t+1)*CIN-1)/32]
+        const int t = __ffs((int)r) - 1;
+        const int s0 = t * CIN / TC_KS, s1 = ((t + 1) * CIN - 1) / TC_KS;
+        m |= ((2ull << s1) - 1ull) & ~((1ull << s0) - 1ull);
+    }
+    if (nstages > nmain) m |= ((nstages < 64 ? (1ull << nstages) : 0ull) - 1ull) & ~((1ull << nmain) - 1ull);
+    return m & ((nstages < 64 ? (1ull << nstages) : 0ull) - 1ull);
 }
 __device__ __forceinline__ int next_stage(unsigned long long m, int s, int nstages) {      // smallest active stage > s
     const unsigned long long r = s + 1 < 64 ? (m >> (s + 1)) : 0ull;
@@ -250,10 +253,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
         auto prefetch_map = [&](int tile, int buf) {
             if (tile < ntiles) {
                 const int row = tile * TC_M + rloc;
-                // MASKED: only the taps that occur in the tile are fetched (1-8 of 27); the others read as absent
-                const uint32_t tm = MASKED ? __ldg(a.tile_mask + tile) : 0xFFFFFFFFu;
+                if (MASKED) {
+                    // only the taps that occur in the tile are fetched (1-8 of 27); load_rows treats the others as absent
+                    int q = 0;
+                    for (uint32_t r = __ldg(a.tile_mask + tile); r; r &= r - 1, ++q) {
+                        if ((q & 1) != half) continue;              // the two producer halves alternate
+                        const int t = __ffs((int)r) - 1;
+                        if (row < a.n_out) {
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&smap[buf][t][rloc])),
+                                         "l"(a.map + (size_t)t * a.n_out + row) : "memory");
+                        } else {
+                            smap[buf][t][rloc] = -1;
+                        }
+                    }
+                } else
                 for (int t = half; t < TC_MAXTAPS; t += 2) {
-                    if (row < a.n_out && t < a.ntaps && ((tm >> t) & 1u)) {
+                    if (row < a.n_out && t < a.ntaps) {
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&smap[buf][t][rloc])),
                                      "l"(a.map + (size_t)t * a.n_out + row) : "memory");
                     } else {
@@ -274,6 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
         const int gq = lane >> 2, q4 = lane & 3;
         const int rq = 32 * (warp & 3) + gq;
         int tile_row0 = 0;
+        uint32_t cur_tmask = 0xFFFFFFFFu;             // MASKED: taps of the current tile that were prefetched
         auto load_rows = [&](int buf, int s, float4 (&x)[4]) {
             if (s >= a.nstages_main) {
                 // fused ResBlock identity: K continues over the channels of in2, gathered through the identity map
@@ -292,7 +308,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
             const int c = CIN == 8 ? (q4 & 1) * 4 : c0 + q4 * 4;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int src = tap < TC_MAXTAPS ? smap[buf][tap][rq + 8 * j] : -1;
+                const int src = (tap < TC_MAXTAPS && (!MASKED || ((cur_tmask >> tap) & 1u))) ? smap[buf][tap][rq + 8 * j] : -1;
                 x[j] = src >= 0 ? __ldg((const float4 *)(a.in + (size_t)src * a.in_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
@@ -395,7 +411,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) k_conv_tc(TcArgs a) {
                 if (++st == TC_STAGES) { st = 0; pe ^= 1; }
             };
             // walk the ACTIVE stages only (all of them unless a tile mask is given)
-            const unsigned long long smask = MASKED ? stage_mask_of<CIN>(__ldg(a.tile_mask + tile), a.nstages_main, a.nstages) : ~0ull;
+            if (MASKED) cur_tmask = __ldg(a.tile_mask + tile);
+            const unsigned long long smask = MASKED ? stage_mask_of<CIN>(cur_tmask, a.nstages_main, a.nstages) : ~0ull;
             const int ns = a.nstages;
             int sa = (MASKED ? next_stage(smask, -1, a.nstages) : (-1) + 1), sb = (MASKED ? next_stage(smask, sa, a.nstages) : (sa) + 1), sc = (MASKED ? next_stage(smask, sb, a.nstages) : (sb) + 1);
             load_rows(buf, sa, x0);
