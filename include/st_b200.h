@@ -114,6 +114,11 @@ int st_strided_maps(const int32_t *coords, int64_t n, int64_t n_out, const uint6
                     const int32_t *out_vals, int64_t out_capacity, int32_t *down, int32_t *up,
                     void *stream);
 
+/* Row gather dst[r,:] = src[idx[r],:] (rows of row_bytes bytes, a multiple of 4; int32 indices): the row
+ * permutations of the path (Z-order rows of the network, voxel representatives; torch indexing in the reference:
+ * smart_tree/dataset/dataset.py:218-226, model/sparse.py:40-61).                                          */
+int st_gather_rows(const void *src, const int32_t *idx, int64_t n, int row_bytes, void *dst, void *stream);
+
 /* Devoxelise: per-voxel predictions back to every input point.  The reference's voxeliser
  * returns pc_voxel_id and drops it (smart_tree/dataset/dataset.py:214); this is the gather it omits.  Pair t is
  * (point pair_point[t], block pair_block[t]) with voxel row pair_voxel[t] (-1 = dropped) as st_block_emit /

@@ -32,6 +32,7 @@ SIGNATURES = {
     "st_block_list": (C.c_int, [_p, _i64, _f, C.c_int, _p, _p, _i32, _pi64, _p, _sz, _p]),
     "st_block_count": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _f, C.c_int, _p, _pi64, _p, _sz, _p]),
     "st_block_emit": (C.c_int, [_p, _i64, _p, _i32, _f, _f, _f, C.c_int, _p, _i64, _p, _p, _p, _p, _p, _sz, _p]),
+    "st_gather_rows": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p]),
     "st_devoxelize": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p]),
     "st_hash_capacity": (_i64, [_i64]),
     "st_hash_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),

@@ -419,3 +419,31 @@ extern "C" int st_devoxelize(const float *xyz, int64_t n_points, const int64_t *
     ST_CHECK_LAUNCH();
     return ST_OK;
 }
+
+// ------------------------------------------------------------------------------------ row gather
+// dst[r, :] = src[idx[r], :] for rows of `words` 32-bit words (int32 index): the permutations of the path (Z-order
+// rows, voxel representatives) -- torch's 16-byte vectorised gather took 259 us for 495 k rows.
+__global__ void k_gather_rows(const uint32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int words, uint32_t *__restrict__ dst) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * words) return;
+    const int64_t r = t / words;
+    const int w = (int)(t - r * words);
+    dst[t] = __ldg(src + (int64_t)__ldg(idx + r) * words + w);
+}
+__global__ void k_gather_rows16(const int4 *__restrict__ src, const int32_t *__restrict__ idx, int64_t n, int4 *__restrict__ dst) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) dst[r] = __ldg(src + __ldg(idx + r));
+}
+extern "C" int st_gather_rows(const void *src, const int32_t *idx, int64_t n, int row_bytes, void *dst, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(row_bytes > 0 && row_bytes % 4 == 0, "rows must be a whole number of 32-bit words");
+    if (row_bytes == 16 && ((uintptr_t)src & 15) == 0 && ((uintptr_t)dst & 15) == 0) {
+        k_gather_rows16<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)src, idx, n, (int4 *)dst);
+    } else {
+        const int words = row_bytes / 4;
+        k_gather_rows<<<(unsigned)cdiv(n * words, 256), 256, 0, s>>>((const uint32_t *)src, idx, n, words, (uint32_t *)dst);
+    }
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}

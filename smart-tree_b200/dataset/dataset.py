@@ -106,7 +106,7 @@ class SingleTreeInference:
         vs = torch.tensor(self.voxel_size, dtype=torch.float32, device=dev)
         grid = _round_half_away((hi - lo) / vs).int().contiguous()                     # spconv calc_meta_data
         pc, rep, coords = ops.voxelize(pts, self.point_block.contiguous(), lo.contiguous(), grid, float(self.voxel_size))
-        feats = pts.index_select(0, rep)
+        feats = ops.gather_rows(pts, rep)
         mask = cube_filter(feats[:, :3], self.block_centres[coords[:, 0].long()], self.block_size)   # dataset.py:224
         return BlockBatch(feats, coords, mask, self.block_centres, pc, self.point_index, self.point_block)
 

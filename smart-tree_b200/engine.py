@@ -270,7 +270,7 @@ class SmartTreeEngine:
         if not self.morton:
             return build_levels(coords, self.depth, inverse_plan=inv)
         perm = ops.morton_perm(coords)
-        levels = build_levels(coords.index_select(0, perm), self.depth, morton=True, inverse_plan=inv)      # int32 index: no widening pass
+        levels = build_levels(ops.gather_rows(coords, perm), self.depth, morton=True, inverse_plan=inv)      # int32 index: no widening pass
         levels[0].perm = perm
         return levels
 
@@ -287,7 +287,7 @@ class SmartTreeEngine:
             levels = self.build_levels(coords)
         perm = getattr(levels[0], "perm", None)
         if perm is not None:
-            features = features.index_select(0, perm)
+            features = ops.gather_rows(features, perm)
         x = self._conv(features, self.stem, None, n, relu=True)
         if trace is not None:
             trace["input_conv"] = x

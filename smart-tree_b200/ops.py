@@ -16,7 +16,7 @@ LAST_SSSP_CTL = None
 _conv_profile = None
 _KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
-                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3, "devoxelize": 1}
+                     "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3, "devoxelize": 1, "gather_rows": 1}
 
 
 def _count(op):
@@ -113,6 +113,17 @@ def voxelize(points, point_block, block_lo, block_grid, vsize):
                                block_lo.shape[0], float(vsize), _ptr(pc), _ptr(rep), _ptr(coords), C.byref(m),
                                _ptr(ws), ws.numel(), _stream()), "st_voxelize")
     return pc, rep[:m.value], coords[:m.value]
+
+
+def gather_rows(src, idx):
+    """src[idx] for a 2-D contiguous tensor of 4-byte elements and an int32 index vector (st_gather_rows)."""
+    lib = _lib.load()
+    if idx.dtype != I32 or src.dim() != 2 or not src.is_contiguous() or src.element_size() != 4 or not src.is_cuda:
+        return src.index_select(0, idx)
+    out = torch.empty((idx.shape[0], src.shape[1]), dtype=src.dtype, device=src.device)
+    _count("gather_rows")
+    _lib.check(lib.st_gather_rows(_ptr(src), _ptr(idx), idx.shape[0], src.shape[1] * 4, _ptr(out), _stream()), "st_gather_rows")
+    return out
 
 
 def devoxelize(xyz, pair_point, pair_block, pair_voxel, block_centres, block_size, voxel_medial, voxel_class):
