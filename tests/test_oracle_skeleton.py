@@ -155,3 +155,35 @@ def test_sample_tree_matches_literal_restatement(seed):
     assert len(got) == len(ref) and len(got) >= 2
     for g, r in zip(got, ref):
         assert (g.id, g.parent_id) == (r[0], r[1]) and g.path.tolist() == r[2]
+
+
+def test_devoxelised_inference_restates_its_definition():
+    """oracle.pipeline_ref.infer_points against a direct per-point definition: the point's block is the
+    one whose inner half-open cube holds it, its voxel the one the block's voxeliser assigned it to, its label the
+    network's output for that voxel (taken from oracle.infer's raw per-voxel predictions)."""
+    import os
+    import torch
+    from oracle import pipeline_ref as P
+    from oracle import unet_ref as U
+    from smart_tree_b200 import synth
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sd = torch.load(os.path.join(root, "smart-tree_b200", "model", "weights", "noble-elevator-58_model_weights.pt"), map_location="cpu", weights_only=True)
+    params = U.to_numpy_params(sd)
+    xyz = P.centre_cloud(synth.make_tree(2, 2500).xyz)
+    xyz = np.concatenate([xyz, xyz[:2] + np.float32(30)])               # two points in a block that is dropped (<= 20 points)
+    rgb = np.zeros_like(xyz)
+    got = P.infer_points(params, xyz, rgb, 0.02, 1.0, 0.4)
+    raw = P.infer(params, xyz, rgb, 0.02, 1.0, 0.4, return_raw=True)["raw"]
+    vmed = (np.exp(raw["preds"]["radius"]) * raw["preds"]["direction"]).astype(np.float32)
+    centres, members = P.compute_blocks(xyz, 1.0, 0.4)
+    first = np.concatenate([[0], np.cumsum([int((raw["coords"][:, 0] == b).sum()) for b in range(len(centres))])])
+    seen = np.zeros(len(xyz), bool)
+    for b, (c, m) in enumerate(zip(centres, members)):
+        m = np.asarray(m)
+        _, _, pcid, _ = P.voxelize_block(np.concatenate([xyz[m], rgb[m]], 1), 0.02)
+        for j, p in enumerate(m):
+            if P.cube_mask(xyz[p:p + 1], c, 1.0)[0] and pcid[j] >= 0:
+                assert not seen[p]                                       # exactly one block's inner cube holds a point
+                seen[p] = True
+                assert np.array_equal(got["medial_vector"][p], vmed[first[b] + pcid[j]])
+    assert np.array_equal(seen, got["class_l"] >= 0) and not seen[-2:].any() and seen[:-2].mean() > 0.9     # (sparse 1 m blocks of <= 20 points are dropped, dataset.py:178)

@@ -101,3 +101,25 @@ def test_point_to_voxel_first_point_wins():
         assert pid[i] == seen[key]
     assert np.array_equal(vox, p[order])
     assert np.array_equal(idx[:, ::-1], np.floor((p[order, :3] - lo32) / vs).astype(np.int32))
+
+
+def test_inverse_conv_taps_are_fixed_by_parity_class():
+    """What the parity-sorted decoder conv (st_inverse_plan / k_conv_tc<.., MASKED>) relies on: a fine voxel p receives
+    from a coarse voxel through tap k only if p = 2o - 1 + k, so per axis k = 1 for even p and k in {0, 2} for odd p.
+    Hence at most 8 of the 27 taps of the oracle's `up` map are non-empty for any voxel, they depend on the parity class
+    only, and the all-even class uses the centre tap alone."""
+    rng = np.random.default_rng(5)
+    c, _ = _random_sparse(rng, 3000, 20)
+    _, _, up = U.strided_maps(c)
+    assert (up >= 0).any(axis=0).all()                                   # every fine voxel has at least one parent
+    cls = ((c[:, 1] & 1) << 2) | ((c[:, 2] & 1) << 1) | (c[:, 3] & 1)
+    allowed = np.zeros((8, 27), bool)
+    for m in range(8):
+        for k in range(27):
+            kz, ky, kx = k // 9, (k // 3) % 3, k % 3
+            ok = all((kk == 1) if not (m >> sh) & 1 else (kk in (0, 2)) for kk, sh in ((kz, 2), (ky, 1), (kx, 0)))
+            allowed[m, k] = ok
+    assert allowed.sum(1).tolist() == [1, 2, 2, 4, 2, 4, 4, 8] and allowed[0, 13]
+    used = up >= 0
+    assert not (used & ~allowed[cls].T).any()
+    assert used.sum(0).max() <= 8 and abs(allowed.sum() / 8 - 27 / 8) < 1e-12
