@@ -72,6 +72,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Samples before this call (nvidia-smi start-up, warm-up steps) are not part of the reported clocks."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -80,6 +84,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        self.rows = self.rows[getattr(self, "first", 0):]
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -207,11 +212,16 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), sk, per_step
 
-    for _ in range(args.warmup):
-        step(True)
+    # the sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation) stalled one timed step in five
+    # by ~10 ms when it was launched right at the start of the timed region; only samples taken after mark() count
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step(True)
+    import gc
+    gc.collect()
+    clocks.mark()
     launches0 = ops.LAUNCHES
     dev_ms, wall_ms, sk, steps_res = timed(True, args.steps)
     launches = ops.LAUNCHES - launches0

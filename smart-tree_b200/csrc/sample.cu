@@ -509,7 +509,9 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     if (!cv.ok()) { set_error("st_sample_tree: workspace too small"); return ST_ERR_WORKSPACE; }
     k_st_init<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(pred, tree_dist, (int)n, distw, alloc, branch_id, best, comp_off, n_comp, keys, vals);
     ST_CHECK_LAUNCH();
-    ST_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sb, keys, keys2, vals, order, (int)n, 0, 64, s));
+    int key_bits = 33;                                   // 32 distance bits + the component index above them
+    while (key_bits < 64 && (1ll << (key_bits - 32)) < (long long)n_comp) ++key_bits;
+    ST_CHECK_CUDA(cub::DeviceRadixSort::SortPairs(sort_ws, sb, keys, keys2, vals, order, (int)n, 0, key_bits, s));
     GridBuild gb;
     int rc = build_grid(medial_pts, n, cell_size, cv, gb, s);
     if (rc) return rc;
