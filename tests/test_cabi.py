@@ -66,3 +66,20 @@ def test_host_modules_mirror_reference_names():
     assert compat.install() is not None
     import spconv.pytorch as sp  # noqa: F401  (the stand-in, registered by compat.install)
     assert hasattr(sp, "SubMConv3d") and hasattr(sp, "SparseConvTensor")
+
+
+def test_packed_branch_skeleton_is_a_lazy_branch_skeleton():
+    """Host logic of the skeleton emit path: branches cut lazily from one packed array behave like BranchSkeleton."""
+    import torch
+    from smart_tree_b200.data_types.branch import BranchSkeleton, PackedBranchSkeleton
+    nodes, rad = torch.randn(12, 3), torch.rand(12)
+    b = PackedBranchSkeleton(4, 1, nodes, rad, 3, 5)
+    assert isinstance(b, BranchSkeleton) and len(b) == 5 and (b._id, b.parent_id, b.child_id) == (4, 1, None)
+    assert torch.equal(b.xyz, nodes[3:8]) and b.radii.shape == (5, 1) and torch.equal(b.radii[:, 0], rad[3:8])
+    assert torch.equal(b.length, (nodes[4:8] - nodes[3:7]).norm(dim=1).sum()) and len(b.to_tubes()) == 4
+    s = PackedBranchSkeleton(5, 4, nodes, rad, 0, 3, radii_1d=True)      # smoothed radii are 1-D (reference quirk)
+    assert s.radii.shape == (3,)
+    f = b.filter(torch.tensor([True, False, True, True, False]))
+    assert type(f) is BranchSkeleton and len(f) == 3
+    b.xyz, b.radii = nodes[:2], rad[:2].unsqueeze(1)                      # object-level post-processing may replace them
+    assert len(b) == 2 and b.radii.shape == (2, 1)
