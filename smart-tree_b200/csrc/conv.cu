@@ -55,7 +55,7 @@ struct ConvCfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(256) k_conv_fma(ConvArgs a) {
+__global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_fma(ConvArgs a) {
     using C = ConvCfg<CIN, COUT>;
     extern __shared__ __align__(16) float smem[];
     const int tid = threadIdx.x;
@@ -88,15 +88,58 @@ __global__ void __launch_bounds__(256) k_conv_fma(ConvArgs a) {
         const float *ws = smem + (s & 1) * C::STAGE_FLOATS;
         const int t0 = s * C::TPS;
         const int nt = min(C::TPS, a.ntaps - t0);
-        for (int t = 0; t < nt; ++t) {
-            const int k = t0 + t;
-            int j[C::RT];
-            bool any = false;
+        // Narrow layers (CIN <= 16: the 8 -> 8 convs of level 0) are bound by the dependent load chain of a tap
+        // (gather-map entry, cold from HBM -> feature row -> FMAs) rather than by the FMAs: the map entries run two taps
+        // ahead and the feature rows one tap ahead of the arithmetic, in registers.
+        constexpr bool PIPE = CIN <= 16;
+        constexpr int XV = CIN / 4;
+        auto map_at = [&](int k, int (&j)[C::RT]) {
 #pragma unroll
             for (int r = 0; r < C::RT; ++r) {
                 j[r] = -1;
-                if (rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
-                any |= j[r] >= 0;
+                if (k < t0 + nt && rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+            }
+        };
+        auto rows_at = [&](const int (&j)[C::RT], float4 (&x)[C::RT][PIPE ? XV : 1]) {
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r)
+#pragma unroll
+                for (int q = 0; q < (PIPE ? XV : 1); ++q)
+                    x[r][q] = j[r] >= 0 ? __ldg((const float4 *)(a.in + (size_t)j[r] * a.in_ld) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        int jn1[C::RT], jn2[C::RT];
+        float4 xn[C::RT][PIPE ? XV : 1];
+        if (PIPE) {
+            int j0[C::RT];
+            map_at(t0, j0);
+            map_at(t0 + 1, jn1);
+            rows_at(j0, xn);
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) jn2[r] = j0[r];          // jn2 = entries of the tap whose rows sit in xn
+        }
+        for (int t = 0; t < nt; ++t) {
+            const int k = t0 + t;
+            int j[C::RT];
+            float4 xc[C::RT][PIPE ? XV : 1];
+            bool any = false;
+            if (PIPE) {
+#pragma unroll
+                for (int r = 0; r < C::RT; ++r) {
+                    j[r] = jn2[r];
+                    any |= j[r] >= 0;
+#pragma unroll
+                    for (int q = 0; q < XV; ++q) xc[r][q] = xn[r][q];
+                    jn2[r] = jn1[r];
+                }
+                rows_at(jn1, xn);                     // rows of tap k+1 (its entries were loaded a tap ago)
+                map_at(k + 2, jn1);                   // entries of tap k+2
+            } else {
+#pragma unroll
+                for (int r = 0; r < C::RT; ++r) {
+                    j[r] = -1;
+                    if (rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+                    any |= j[r] >= 0;
+                }
             }
             if (!__any_sync(0xffffffffu, any)) continue;
             const float *wt = ws + t * C::TAP_FLOATS + cg * C::CT;
@@ -104,8 +147,10 @@ __global__ void __launch_bounds__(256) k_conv_fma(ConvArgs a) {
             for (int ci4 = 0; ci4 < CIN / 4; ++ci4) {
                 float4 x[C::RT];
 #pragma unroll
-                for (int r = 0; r < C::RT; ++r)
-                    x[r] = j[r] >= 0 ? __ldg((const float4 *)(a.in + (size_t)j[r] * a.in_ld) + ci4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int r = 0; r < C::RT; ++r) {
+                    if (PIPE) x[r] = xc[r][ci4];
+                    else x[r] = j[r] >= 0 ? __ldg((const float4 *)(a.in + (size_t)j[r] * a.in_ld) + ci4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
 #pragma unroll
