@@ -210,6 +210,8 @@ def strided_maps(coords, out_coords, out_table: CoordTable, inverse_plan=False):
                                            _stream()), "st_strided_maps_inv")
         return down, None, (row_index, up_sorted, tile_mask)
     up = torch.empty((27, n), dtype=I32, device=coords.device)
+    if inverse_plan:          # (empty level: nothing to plan)
+        return down, up, None
     _count("strided_maps")
     _lib.check(lib.st_strided_maps(_ptr(coords), n, m, _ptr(out_table.keys), _ptr(out_table.vals), out_table.capacity,
                                    _ptr(down), _ptr(up), _stream()), "st_strided_maps")
