@@ -13,7 +13,7 @@
  *     return a count through an *_host pointer synchronise that stream before returning
  *   - return value: 0 = ok, negative = error; st_last_error() gives the thread-local text
  *   - features are fp32 row-major; coordinates int32 (batch, z, y, x) with
- *     0 <= z,y,x < 65534 and 0 <= batch < 32768; graph indices int32
+ *     0 <= z,y,x <= 65533 and 0 <= batch < 32768 (checked by st_hash_build); graph indices int32
  */
 #ifndef ST_B200_H
 #define ST_B200_H
@@ -84,13 +84,19 @@ int st_block_emit(const float *xyz, int64_t n, const uint64_t *kept_keys, int32_
  * replaces spconv ops.get_indice_pairs(subm=True) reached from every SubMConv3d.forward
  *                                      smart_tree/model/model_blocks.py:24-32,123-144,258-282
  * Hash table: `capacity` slots (power of two >= 2n, see st_hash_capacity), keys u64, vals i32.
+ * `status` (optional, device int32): set to 1 if any coordinate lies outside the range the 64-bit keys can hold
+ * (0 <= z,y,x <= 65533, 0 <= batch < 32768); such rows are left out of the table -- the caller must treat it as an error.
  * nbr[27, n]: row of the active voxel at coords[i] + (kz-1,ky-1,kx-1), k=(kz*3+ky)*3+kx, or -1.
- * Coordinates are unbounded: no spatial_shape clipping.           */
+ * spatial_shape (optional, device int32[3] = (z,y,x)): the reference declares spatial_shape = max(coords), not max+1
+ * (smart_tree/model/sparse.py:15-19), and spconv bound-checks neighbour LOCATIONS against it, so voxels on the max
+ * faces are invisible as neighbours.  NULL = unbounded grid (the default of this library);
+ * non-NULL reproduces the clip: a neighbour with any coordinate >= spatial_shape is reported absent (the centre tap
+ * is never clipped).  Only the clip is modelled, not the index aliasing of the out-of-range voxels.             */
 int64_t st_hash_capacity(int64_t n);
 int st_hash_build(const int32_t *coords, int64_t n, uint64_t *keys, int32_t *vals,
-                  int64_t capacity, void *stream);
+                  int64_t capacity, int32_t *status, void *stream);
 int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *keys, const int32_t *vals,
-                int64_t capacity, int32_t *nbr, void *stream);
+                int64_t capacity, const int32_t *spatial_shape, int32_t *nbr, void *stream);
 
 /* ------------------------------------------------------------------ K3 strided / inverse conv maps
  * replaces spconv generate_conv_inds for SparseConv3d(k=3,s=2,p=1,indice_key) and the reuse of
@@ -99,9 +105,12 @@ int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *keys, const in
  *         out_coords must hold 8n rows).  Step 2 (after the caller built the hash of
  *         out_coords): down[27,M] = input row feeding output o through tap k (p = 2o-1+k),
  *         up[27,n] = output row fed by input p through tap k; -1 where absent.           */
+/* out_shape (optional, device int32[3]): strict_spconv_bounds as above -- outputs with any coordinate >= out_shape
+ * (= (spatial_shape - 1) / 2 + 1 of the input level, the shape spconv hands to the next level) are not created.    */
 size_t st_strided_coords_workspace_bytes(int64_t n);
-int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, int32_t *out_coords,
-                      int64_t *n_out_host, void *workspace, size_t workspace_bytes, void *stream);
+int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, const int32_t *out_shape,
+                      int32_t *out_coords, int64_t *n_out_host, void *workspace, size_t workspace_bytes,
+                      void *stream);
 /* Row order is free inside the network (every encoder is undone by its inverse conv), so the engine
  * keeps each level in (batch, Z-order): morton_order=1 above sorts the new level that way, and
  * st_morton_perm gives the permutation that does the same for the caller's level-0 rows
@@ -145,6 +154,21 @@ int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out
                    const float *w, int cin, int cout, const float *scale, const float *shift,
                    const float *residual, int res_ld, const float *in2, int in2_ld,
                    const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
+
+/* Stem: the 1x1 input conv + BN + ReLU (smart_tree/model/model.py:31-38, SubMConv3d k=1 fast path) fused with the
+ * row permutation that puts the network's rows into Z-order: out[i,:] = act(scale * (W . in[row_index[i], :cin]) + shift).
+ * w[cin, cout]; cin <= 8, cout in {8, 16}; `in` may be a column slice of a wider array (in_ld floats per row);
+ * row_index may be NULL (identity).  ST_ERR_UNSUPPORTED for other shapes (use st_conv_gather with ntaps = 1).       */
+int st_stem_conv(const float *in, int in_ld, const int32_t *row_index, int64_t n, const float *w, int cin,
+                 int cout, const float *scale, const float *shift, float *out, int out_ld, int act, void *stream);
+
+/* Inverse (decoder) conv on parity-sorted rows, fp32 FMA kernel: same plan (st_inverse_plan / st_strided_maps_inv) and
+ * result as st_conv_gather_tc_inv below; w[ntaps, cin, cout] plain.  For the narrow decoder of level 0 (16 -> 8), where a
+ * fine voxel has 3.4 of 27 taps on average, the CTA reads only the map rows of the taps its tiles' masks name.
+ *                                      replaces spconv SparseInverseConv3d  smart_tree/model/model_blocks.py:91-100 */
+int st_conv_gather_inv(const float *in, int in_ld, const int32_t *up_sorted, const int32_t *row_index,
+                       const uint32_t *tile_mask, int64_t n_out, int ntaps, const float *w, int cin, int cout,
+                       const float *scale, const float *shift, float *out, int out_ld, int act, void *stream);
 
 /* Tensor-core variant (tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM).  Same
  * contract as st_conv_gather except that `wprep` is the weight tensor pre-arranged by
@@ -269,7 +293,7 @@ int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t 
  * tree_dist[v] = tree_dist[pred[v]] + ||p_v - p_pred(v)||, 0 at roots (pred<0 & reachable
  * flag), FLT_MAX where unreachable[v] != 0.                                              */
 int st_tree_distances(const float *points, const int32_t *pred, const uint8_t *is_root,
-                      int64_t n, float *tree_dist, void *ctl_workspace /* 256 B, device */,
+                      int64_t n, float *tree_dist, void *ctl_workspace /* 256 + 8n B, device */,
                       void *stream);
 
 /* ------------------------------------------------------------------ K10 greedy branch extraction

@@ -67,9 +67,18 @@ def point_to_voxel(points: np.ndarray, vsize: float, lo: np.ndarray, hi: np.ndar
 
 
 # ----------------------------------------------------------------------------- B2-B4
-def subm_map(coords: np.ndarray) -> np.ndarray:
+def declared_spatial_shape(coords: np.ndarray) -> np.ndarray:
+    """spatial_shape as the reference declares it: max(coords) per axis, NOT max + 1
+    (/root/reference/smart_tree/model/sparse.py:15-19)."""
+    return coords[:, 1:].max(0).astype(np.int64) if len(coords) else np.zeros(3, np.int64)
+
+
+def subm_map(coords: np.ndarray, spatial_shape=None) -> np.ndarray:
     """nbr[27,N]: row of the active voxel at coords[i] + OFFSETS[k], or -1.
-    Coordinates are unbounded (no spatial_shape clipping)."""
+    spatial_shape = None: unbounded grid (the default).  Otherwise (strict_spconv_bounds) a
+    neighbour LOCATION with any coordinate >= spatial_shape is not queried, as spconv bound-checks it -- voxels on
+    the max faces are invisible as neighbours; the centre tap is never clipped.  Only the clip is modelled, not the
+    index aliasing spconv would suffer for those voxels (implementation detail, unverifiable here)."""
     keys = pack_keys(coords)
     order = np.argsort(keys, kind="stable")
     sk = keys[order]
@@ -80,15 +89,19 @@ def subm_map(coords: np.ndarray) -> np.ndarray:
         q[:, 2] += dy
         q[:, 3] += dx
         out[k] = _lookup(sk, order, pack_keys(q))
+        if spatial_shape is not None and k != 13:
+            out[k][np.any(q[:, 1:] >= np.asarray(spatial_shape, np.int64), axis=1)] = -1
     return out
 
 
-def strided_maps(coords: np.ndarray):
+def strided_maps(coords: np.ndarray, out_shape=None):
     """SparseConv3d(k=3,s=2,p=1) index generation.
 
     Returns out_coords [M,4] sorted by (b,z,y,x), down[27,M] (input row feeding output
     row o through tap k, p = 2o-1+k) and up[27,N] (output row fed by input row p through
-    tap k, o = (p+1-k)/2) -- the latter is what SparseInverseConv3d gathers from (B4)."""
+    tap k, o = (p+1-k)/2) -- the latter is what SparseInverseConv3d gathers from (B4).
+    out_shape (strict_spconv_bounds): outputs with any coordinate >= out_shape = (in_shape - 1) // 2 + 1 are not
+    created (B3: 0 <= o < out_shape)."""
     c = coords.astype(np.int64)
     n = len(c)
     cand = []
@@ -97,6 +110,8 @@ def strided_maps(coords: np.ndarray):
     for k, (dz, dy, dx) in enumerate(OFFSETS):  # tap index per axis = d+1
         t = c[:, 1:] + 1 - (np.array([dz, dy, dx]) + 1)
         ok = np.all((t % 2) == 0, axis=1)
+        if out_shape is not None:
+            ok &= np.all(t // 2 < np.asarray(out_shape, np.int64), axis=1)
         o = np.concatenate([c[:, :1], t // 2], axis=1)
         up_o[k], up_ok[k] = o, ok
         cand.append(o[ok])
@@ -158,19 +173,24 @@ def unet_depth(params) -> int:
 class LevelMaps:
     """Index structures of one UNet level, built once and shared by all its convs."""
 
-    def __init__(self, coords):
+    def __init__(self, coords, spatial_shape=None):
         self.coords = coords
-        self.nbr = subm_map(coords)
+        self.spatial_shape = spatial_shape
+        self.nbr = subm_map(coords, spatial_shape)
         self.down = self.up = None
         self.child = None
 
 
-def build_levels(coords: np.ndarray, depth: int):
-    levels = [LevelMaps(coords)]
+def build_levels(coords: np.ndarray, depth: int, spatial_shape=None):
+    """spatial_shape = declared_spatial_shape(coords) reproduces spconv's bound checks (strict_spconv_bounds); each level
+    hands out_shape = (shape - 1) // 2 + 1 to the next, as spconv does.  None = unbounded."""
+    levels = [LevelMaps(coords, spatial_shape)]
     for _ in range(depth - 1):
-        oc, down, up = strided_maps(levels[-1].coords)
-        levels[-1].down, levels[-1].up = down, up
-        levels.append(LevelMaps(oc))
+        cur = levels[-1]
+        out_shape = None if cur.spatial_shape is None else (np.asarray(cur.spatial_shape, np.int64) - 1) // 2 + 1
+        oc, down, up = strided_maps(cur.coords, out_shape)
+        cur.down, cur.up = down, up
+        levels.append(LevelMaps(oc, out_shape))
     return levels
 
 

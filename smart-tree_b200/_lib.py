@@ -35,15 +35,17 @@ SIGNATURES = {
     "st_gather_rows": (C.c_int, [_p, _p, _i64, C.c_int, _p, _p]),
     "st_devoxelize": (C.c_int, [_p, _i64, _p, _p, _p, _i64, _p, _f, _p, _p, _p, _p, _p, _p]),
     "st_hash_capacity": (_i64, [_i64]),
-    "st_hash_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p]),
-    "st_subm_map": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "st_hash_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p]),
+    "st_subm_map": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _p, _p]),
     "st_strided_coords_workspace_bytes": (_sz, [_i64]),
-    "st_strided_coords": (C.c_int, [_p, _i64, C.c_int, _p, _pi64, _p, _sz, _p]),
+    "st_strided_coords": (C.c_int, [_p, _i64, C.c_int, _p, _p, _pi64, _p, _sz, _p]),
     "st_morton_workspace_bytes": (_sz, [_i64]),
     "st_morton_perm": (C.c_int, [_p, _i64, _p, _p, _sz, _p]),
     "st_strided_maps": (C.c_int, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _p]),
     "st_conv_gather": (C.c_int, [_p, C.c_int, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int,
                                  _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
+    "st_stem_conv": (C.c_int, [_p, C.c_int, _p, _i64, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p]),
+    "st_conv_gather_inv": (C.c_int, [_p, C.c_int, _p, _p, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p]),
     "st_conv_tc_weight_floats": (_i64, [C.c_int, C.c_int, C.c_int]),
     "st_conv_tc_prepare": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "st_conv_tc_weight_floats_fused": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -1,5 +1,6 @@
-"""Opt-in stage timers (ST_TIMING=1 or timing.enable()): synchronising wall-clock sections used by
-tools/stage_stats.py and bench.py's stage table.  Disabled = zero overhead, no synchronisation."""
+"""Stage sections: an NVTX range per pipeline stage (always, for profilers) and opt-in stage timers (ST_TIMING=1 or
+timing.enable()): synchronising wall-clock sections used by tools/stage_stats.py and bench.py's stage table.
+Timers disabled = no synchronisation."""
 import os
 import time
 from contextlib import contextmanager
@@ -18,15 +19,25 @@ def enable(on=True):
     SAMPLES.clear()
 
 
+NVTX = bool(int(os.environ.get("ST_NVTX", "1")))      # NVTX ranges around every pipeline stage (profilers; ~1 us each)
+
+
 @contextmanager
 def section(name):
-    if not ENABLED:
+    nvtx = NVTX and torch.cuda.is_available()
+    if nvtx:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        if not ENABLED:
+            yield
+            return
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         yield
-        return
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    yield
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) * 1e3
-    RECORDS[name] = RECORDS.get(name, 0.0) + dt
-    SAMPLES.setdefault(name, []).append(dt)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) * 1e3
+        RECORDS[name] = RECORDS.get(name, 0.0) + dt
+        SAMPLES.setdefault(name, []).append(dt)
+    finally:
+        if nvtx:
+            torch.cuda.nvtx.range_pop()

@@ -54,11 +54,15 @@ struct Carver {
 };
 
 // ---- 64-bit packed voxel key: b<<48 | (z+1)<<32 | (y+1)<<16 | (x+1); sorts as (b,z,y,x)
+// Fields are masked to their width; the legal range (checked once per coordinate set by st_hash_build) is
+// 0 <= z,y,x <= ST_MAX_COORD (so that the -1 / +1 neighbours of a voxel still fit) and 0 <= b < ST_MAX_BATCH.
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr unsigned ST_MAX_COORD = 65533u;
+constexpr unsigned ST_MAX_BATCH = 32768u;
 
 __host__ __device__ __forceinline__ uint64_t pack_key(int b, int z, int y, int x) {
-    return ((uint64_t)(uint32_t)b << 48) | ((uint64_t)(uint32_t)(z + 1) << 32) |
-           ((uint64_t)(uint32_t)(y + 1) << 16) | (uint64_t)(uint32_t)(x + 1);
+    return ((uint64_t)((uint32_t)b & 0xFFFFu) << 48) | ((uint64_t)((uint32_t)(z + 1) & 0xFFFFu) << 32) |
+           ((uint64_t)((uint32_t)(y + 1) & 0xFFFFu) << 16) | (uint64_t)((uint32_t)(x + 1) & 0xFFFFu);
 }
 __host__ __device__ __forceinline__ void unpack_key(uint64_t k, int &b, int &z, int &y, int &x) {
     b = (int)(k >> 48);

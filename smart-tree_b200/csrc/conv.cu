@@ -30,6 +30,8 @@ struct ConvArgs {
     float *out;
     int out_ld;
     int act;
+    const int32_t *out_index;     // optional: launch row i is output row out_index[i] (parity-sorted inverse conv)
+    const uint32_t *tile_mask;    // optional: per 128 launch rows, bit k set iff tap k occurs in the tile
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -38,6 +40,23 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// FFMA2 (fma.rn.f32x2, sm_100): two fp32 FMAs per lane and issue slot; each component rounds exactly like fmaf.
+// Written as PTX on 64-bit register pairs: the compiler otherwise splits most __ffma2_rn calls back into scalar FFMAs
+// when one operand is a broadcast.
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 
 template <int CIN, int COUT>
 struct ConvCfg {
@@ -66,11 +85,31 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
 #pragma unroll
     for (int r = 0; r < C::RT; ++r) rows[r] = row0 + r * C::ROW_SLOTS;
 
-    float acc[C::RT][C::CT];
+    // accumulators as channel pairs (FFMA2)
+    unsigned long long acc[C::RT][C::CT / 2];
 #pragma unroll
     for (int r = 0; r < C::RT; ++r)
 #pragma unroll
-        for (int c = 0; c < C::CT; ++c) acc[r][c] = 0.f;
+        for (int c = 0; c < C::CT / 2; ++c) acc[r][c] = 0ull;
+
+    // taps this CTA has to visit: all of them, or (inverse conv on parity-sorted rows) the <= 8 of 27 that occur in its
+    // 128-row tiles -- the other taps' map entries are never read
+    __shared__ int s_taps[32];
+    __shared__ int s_ntaps;
+    if (tid < 32) {
+        unsigned m = a.ntaps >= 32 ? 0xffffffffu : ((1u << a.ntaps) - 1u);
+        if (a.tile_mask) {
+            unsigned mm = 0;
+            const int tile0 = blockIdx.x * (C::ROWS / 128), ntile = (a.n_out + 127) / 128;
+            for (int t = 0; t < C::ROWS / 128; ++t)
+                if (tile0 + t < ntile) mm |= __ldg(a.tile_mask + tile0 + t);
+            m &= mm;
+        }
+        if (m & (1u << tid)) s_taps[__popc(m & ((1u << tid) - 1u))] = tid;
+        if (tid == 0) s_ntaps = __popc(m);
+    }
+    __syncthreads();
+    const int nlist = s_ntaps;
 
     const int nstages = (a.ntaps + C::TPS - 1) / C::TPS;
     auto issue = [&](int s) {
@@ -82,22 +121,26 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
         cp_async_commit();
     };
     issue(0);
+    int li = 0;                     // position in the tap list (ascending taps: stages consume it in order)
     for (int s = 0; s < nstages; ++s) {
         if (s + 1 < nstages) { issue(s + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
         __syncthreads();
         const float *ws = smem + (s & 1) * C::STAGE_FLOATS;
         const int t0 = s * C::TPS;
         const int nt = min(C::TPS, a.ntaps - t0);
+        int lend = li;
+        while (lend < nlist && s_taps[lend] < t0 + nt) ++lend;      // list entries [li, lend) belong to this stage
         // Narrow layers (CIN <= 16: the 8 -> 8 convs of level 0) are bound by the dependent load chain of a tap
         // (gather-map entry, cold from HBM -> feature row -> FMAs) rather than by the FMAs: the map entries run two taps
-        // ahead and the feature rows one tap ahead of the arithmetic, in registers.
+        // and the feature rows one tap ahead of the arithmetic, in registers.
         constexpr bool PIPE = CIN <= 16;
         constexpr int XV = CIN / 4;
-        auto map_at = [&](int k, int (&j)[C::RT]) {
+        auto map_at = [&](int i, int (&j)[C::RT]) {
+            const int k = i < lend ? s_taps[i] : -1;
 #pragma unroll
             for (int r = 0; r < C::RT; ++r) {
                 j[r] = -1;
-                if (k < t0 + nt && rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+                if (k >= 0 && rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
             }
         };
         auto rows_at = [&](const int (&j)[C::RT], float4 (&x)[C::RT][PIPE ? XV : 1]) {
@@ -111,14 +154,14 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
         float4 xn[C::RT][PIPE ? XV : 1];
         if (PIPE) {
             int j0[C::RT];
-            map_at(t0, j0);
-            map_at(t0 + 1, jn1);
+            map_at(li, j0);
+            map_at(li + 1, jn1);
             rows_at(j0, xn);
 #pragma unroll
             for (int r = 0; r < C::RT; ++r) jn2[r] = j0[r];          // jn2 = entries of the tap whose rows sit in xn
         }
-        for (int t = 0; t < nt; ++t) {
-            const int k = t0 + t;
+        for (int i = li; i < lend; ++i) {
+            const int k = s_taps[i];
             int j[C::RT];
             float4 xc[C::RT][PIPE ? XV : 1];
             bool any = false;
@@ -131,8 +174,8 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
                     for (int q = 0; q < XV; ++q) xc[r][q] = xn[r][q];
                     jn2[r] = jn1[r];
                 }
-                rows_at(jn1, xn);                     // rows of tap k+1 (its entries were loaded a tap ago)
-                map_at(k + 2, jn1);                   // entries of tap k+2
+                rows_at(jn1, xn);                     // rows of the next listed tap (its entries were loaded a tap ago)
+                map_at(i + 2, jn1);                   // entries of the tap after that
             } else {
 #pragma unroll
                 for (int r = 0; r < C::RT; ++r) {
@@ -142,7 +185,7 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
                 }
             }
             if (!__any_sync(0xffffffffu, any)) continue;
-            const float *wt = ws + t * C::TAP_FLOATS + cg * C::CT;
+            const float *wt = ws + (k - t0) * C::TAP_FLOATS + cg * C::CT;
 #pragma unroll
             for (int ci4 = 0; ci4 < CIN / 4; ++ci4) {
                 float4 x[C::RT];
@@ -156,18 +199,19 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
 #pragma unroll
                     for (int co4 = 0; co4 < C::CT / 4; ++co4) {
                         float4 w4 = *(const float4 *)(wt + (ci4 * 4 + c) * COUT + co4 * 4);
+                        const unsigned long long w01 = f2_pack(w4.x, w4.y), w23 = f2_pack(w4.z, w4.w);
 #pragma unroll
                         for (int r = 0; r < C::RT; ++r) {
-                            float xv = c == 0 ? x[r].x : c == 1 ? x[r].y : c == 2 ? x[r].z : x[r].w;
-                            acc[r][co4 * 4 + 0] = fmaf(xv, w4.x, acc[r][co4 * 4 + 0]);
-                            acc[r][co4 * 4 + 1] = fmaf(xv, w4.y, acc[r][co4 * 4 + 1]);
-                            acc[r][co4 * 4 + 2] = fmaf(xv, w4.z, acc[r][co4 * 4 + 2]);
-                            acc[r][co4 * 4 + 3] = fmaf(xv, w4.w, acc[r][co4 * 4 + 3]);
+                            const float xv = c == 0 ? x[r].x : c == 1 ? x[r].y : c == 2 ? x[r].z : x[r].w;
+                            const unsigned long long xx = f2_pack(xv, xv);
+                            acc[r][co4 * 2 + 0] = ffma2(xx, w01, acc[r][co4 * 2 + 0]);
+                            acc[r][co4 * 2 + 1] = ffma2(xx, w23, acc[r][co4 * 2 + 1]);
                         }
                     }
                 }
             }
         }
+        li = lend;
         __syncthreads();
     }
 
@@ -175,14 +219,16 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
     const int co0 = cg * C::CT;
 #pragma unroll
     for (int r = 0; r < C::RT; ++r) {
-        const int row = rows[r];
-        if (row >= a.n_out) continue;
+        if (rows[r] >= a.n_out) continue;
+        const int row = a.out_index ? __ldg(a.out_index + rows[r]) : rows[r];      // output row (residual / in2 follow it)
         float v[C::CT];
+#pragma unroll
+        for (int c = 0; c < C::CT / 2; ++c) f2_unpack(acc[r][c], v[2 * c], v[2 * c + 1]);
 #pragma unroll
         for (int c = 0; c < C::CT; ++c) {
             float sc = a.scale ? __ldg(a.scale + co0 + c) : 1.f;
             float sh = a.shift ? __ldg(a.shift + co0 + c) : 0.f;
-            v[c] = fmaf(acc[r][c], sc, sh);
+            v[c] = fmaf(v[c], sc, sh);
         }
         if (a.res) {
 #pragma unroll
@@ -242,7 +288,7 @@ __global__ void k_conv_generic(ConvArgs a) {
         v += e;
     }
     if (a.act & ST_ACT_RELU) v = fmaxf(v, 0.f);
-    a.out[(size_t)row * a.out_ld + co] = v;
+    a.out[(size_t)(a.out_index ? a.out_index[row] : row) * a.out_ld + co] = v;
 }
 
 template <int CIN, int COUT>
@@ -260,6 +306,7 @@ static int launch_fma(const ConvArgs &a, cudaStream_t s) {
 }
 
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
+static int conv_dispatch(const ConvArgs &a, cudaStream_t s);
 
 extern "C" int st_conv_gather(const float *in, int in_ld, const int32_t *map, int64_t n_out, int ntaps, const float *w,
                               int cin, int cout, const float *scale, const float *shift, const float *residual,
@@ -270,7 +317,17 @@ extern "C" int st_conv_gather(const float *in, int in_ld, const int32_t *map, in
     ST_REQUIRE(n_out < (1ll << 31), "n_out");
     ST_REQUIRE(ntaps >= 1 && (map != nullptr || ntaps == 1), "identity map requires ntaps == 1");
     ST_REQUIRE(!in2 || w2, "in2 needs w2");
-    ConvArgs a{in, in_ld, map, (int)n_out, ntaps, w, cin, cout, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act};
+    ST_REQUIRE(ntaps <= 32, "at most 32 taps");
+    ConvArgs a{in, in_ld, map, (int)n_out, ntaps, w, cin, cout, scale, shift, residual, res_ld, in2, in2_ld, w2, cin2, out, out_ld, act,
+               nullptr, nullptr};
+    return conv_dispatch(a, s);
+}
+
+static int conv_dispatch(const ConvArgs &a, cudaStream_t s) {
+    const float *in = a.in, *w = a.w, *residual = a.res, *w2 = a.w2;
+    float *out = a.out;
+    const int in_ld = a.in_ld, out_ld = a.out_ld, res_ld = a.res_ld, cin = a.cin, cout = a.cout;
+    const int64_t n_out = a.n_out;
     bool fast = aligned16(in) && aligned16(out) && aligned16(w) && (in_ld % 4 == 0) && (out_ld % 4 == 0) &&
                 (!residual || (aligned16(residual) && res_ld % 4 == 0)) && (!w2 || aligned16(w2));
     if (fast) {
@@ -283,6 +340,71 @@ extern "C" int st_conv_gather(const float *in, int in_ld, const int32_t *map, in
     k_conv_generic<<<(unsigned)cdiv(total, 256), 256, 0, s>>>(a);
     ST_CHECK_LAUNCH();
     return ST_OK;
+}
+
+// Stem: the 1x1 input conv (3 -> 8 in the shipped checkpoints) + BN + ReLU, fused with the row permutation that puts the
+// network's rows into Z-order: out[i,:] = act(scale * (W . in[row_index[i], :cin]) + shift).  One thread per row, weights in
+// registers via shared memory, two 16-byte stores; `in` may be a column slice of a wider array (in_ld).
+template <int COUT>
+__global__ void __launch_bounds__(256) k_stem(const float *__restrict__ in, int in_ld, const int32_t *__restrict__ row_index, int n,
+                                              const float *__restrict__ w, int cin, const float *__restrict__ scale,
+                                              const float *__restrict__ shift, float *__restrict__ out, int out_ld, int act) {
+    __shared__ float sw[8 * COUT + 2 * COUT];
+    for (int i = threadIdx.x; i < cin * COUT; i += blockDim.x) sw[i] = w[i];
+    for (int i = threadIdx.x; i < COUT; i += blockDim.x) {
+        sw[8 * COUT + i] = scale ? scale[i] : 1.f;
+        sw[9 * COUT + i] = shift ? shift[i] : 0.f;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *x = in + (size_t)(row_index ? __ldg(row_index + i) : i) * in_ld;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int ci = 0; ci < cin; ++ci) {
+        const float xv = __ldg(x + ci);
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, sw[ci * COUT + c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) {
+        acc[c] = fmaf(acc[c], sw[8 * COUT + c], sw[9 * COUT + c]);
+        if (act & ST_ACT_RELU) acc[c] = fmaxf(acc[c], 0.f);
+    }
+    float4 *o = (float4 *)(out + (size_t)i * out_ld);
+#pragma unroll
+    for (int c4 = 0; c4 < COUT / 4; ++c4) o[c4] = make_float4(acc[c4 * 4], acc[c4 * 4 + 1], acc[c4 * 4 + 2], acc[c4 * 4 + 3]);
+}
+
+extern "C" int st_stem_conv(const float *in, int in_ld, const int32_t *row_index, int64_t n, const float *w, int cin, int cout,
+                            const float *scale, const float *shift, float *out, int out_ld, int act, void *stream) {
+    if (n == 0) return ST_OK;
+    ST_REQUIRE(n < (1ll << 31), "n");
+    if (!(cin >= 1 && cin <= 8 && (cout == 8 || cout == 16) && aligned16(out) && out_ld % 4 == 0)) {
+        set_error("st_stem_conv: supports cin <= 8, cout in {8, 16}, 16-byte aligned output rows");
+        return ST_ERR_UNSUPPORTED;
+    }
+    const unsigned g = (unsigned)cdiv(n, 256);
+    if (cout == 8) k_stem<8><<<g, 256, 0, (cudaStream_t)stream>>>(in, in_ld, row_index, (int)n, w, cin, scale, shift, out, out_ld, act);
+    else k_stem<16><<<g, 256, 0, (cudaStream_t)stream>>>(in, in_ld, row_index, (int)n, w, cin, scale, shift, out, out_ld, act);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
+// Inverse (decoder) conv on parity-sorted rows through the FMA kernel: FMA counterpart of st_conv_gather_tc_inv for the
+// narrow layers (16 -> 8 at level 0), where a fine voxel has 3.4 of 27 taps on average and the tensor-core tile switch
+// costs more than the arithmetic.  The CTA visits only the taps its tiles' masks name.
+extern "C" int st_conv_gather_inv(const float *in, int in_ld, const int32_t *up_sorted, const int32_t *row_index,
+                                  const uint32_t *tile_mask, int64_t n_out, int ntaps, const float *w, int cin, int cout,
+                                  const float *scale, const float *shift, float *out, int out_ld, int act, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_out == 0) return ST_OK;
+    ST_REQUIRE(n_out < (1ll << 31), "n_out");
+    ST_REQUIRE(ntaps >= 1 && ntaps <= 32 && up_sorted && row_index, "inverse conv needs up_sorted / row_index and at most 32 taps");
+    ConvArgs a{in, in_ld, up_sorted, (int)n_out, ntaps, w, cin, cout, scale, shift, nullptr, 0, nullptr, 0, nullptr, 0, out, out_ld, act,
+               row_index, tile_mask};
+    return conv_dispatch(a, s);
 }
 
 // ------------------------------------------------------------------------------------ fused heads

@@ -186,13 +186,15 @@ struct SsspCtl {
 };
 
 __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta, int npass) {
+                                              const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta, int npass, int adv) {
     // Distance-ordered ("near-far") discipline on top of the asynchronous relaxation: an improvement is only
     // accepted -- written and propagated -- while it lies below the current threshold T; larger candidates
     // stay parked in a register of the owning lane until T reaches them.  Vertices are therefore settled in
     // roughly increasing distance and each one is improved a few times instead of dozens (plain chaotic
     // relaxation improved every vertex ~35 times on the bench graph).  T only moves at the grid barriers:
-    // when a chunk accepted nothing, T jumps to (smallest parked candidate) + delta.
+    // to (smallest parked candidate) + delta -- as soon as anything is parked (adv != 0: the fastest part of the
+    // wave has reached T; slower regions simply keep relaxing below it), or only once a whole chunk accepted
+    // nothing (adv == 0, the round-1 schedule: one idle chunk per threshold step).
     unsigned phase = 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -276,6 +278,8 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
                 break;
             }
             T = fmaxf(T, __uint_as_float(mp)) + delta;      // every thread derives the same new threshold
+        } else if (adv && mp != 0x7F800000u) {
+            T = fmaxf(T, __uint_as_float(mp) + delta);
         }
     }
 }
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(256) k_sssp_big(const int32_t *__restrict__ ro
 // of times on a 1.3 M-vertex graph (77 ms); the distance-ordered schedule is what keeps the work near-linear.
 __global__ void __launch_bounds__(256) k_sssp_nf_big(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
                                                      const float *__restrict__ w, int n, float *dist, int *dirty, int *seen_g, float *pend_g,
-                                                     SsspCtl *ctl, float delta, int npass) {
+                                                     SsspCtl *ctl, float delta, int npass, int adv) {
     unsigned phase = 0;
     const int lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -410,6 +414,8 @@ __global__ void __launch_bounds__(256) k_sssp_nf_big(const int32_t *__restrict__
                 break;
             }
             T = fmaxf(T, __uint_as_float(mp)) + delta;
+        } else if (adv && mp != 0x7F800000u) {
+            T = fmaxf(T, __uint_as_float(mp) + delta);
         }
     }
 }
@@ -500,7 +506,9 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     if (!(delta > 0.f)) delta = 0.05f;
     int npass = SSSP_NF_PASSES;
     if (const char *e = getenv("ST_SSSP_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 1024) npass = v; }
-    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta, (void *)&npass};
+    int adv = 1;                           // threshold schedule (see k_sssp); any value gives the same result
+    if (const char *e = getenv("ST_SSSP_ADVANCE")) adv = atoi(e) != 0;
+    void *args[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta, (void *)&npass, (void *)&adv};
     // near-far counter variant: poll state in registers when every resident warp can own its vertices there, in global
     // memory otherwise (ctl_workspace holds dirty[n], seen[n], pend[n]); ST_SSSP_FLAGS=1 forces the old flag variant
     const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n && !getenv("ST_SSSP_FORCE_BIG");      // (env: tests exercise the large-graph kernel)
@@ -519,7 +527,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
         if (rc) return rc;
         if (blocks2 > (int)g) blocks2 = (int)g;
         void *args2[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&seen_g, (void *)&pend_g,
-                         (void *)&ctl, (void *)&delta, (void *)&npass};
+                         (void *)&ctl, (void *)&delta, (void *)&npass, (void *)&adv};
         ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_nf_big, dim3(blocks2), dim3(256), args2, 0, s));
     }
     k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
@@ -570,6 +578,69 @@ __global__ void __launch_bounds__(256) k_tree_dist(const float *__restrict__ pts
     }
 }
 
+// Chain-walking variant: edge lengths are computed once (k_tree_edges), then every unfinished vertex walks up to
+// TD_H predecessors looking for an ancestor whose length is final and adds the collected edge lengths back down in
+// root -> leaf order -- bit for bit the sum the hop-by-hop kernel above forms, but the wave of finished vertices
+// advances TD_H hops per L2 round trip instead of one (tree depth 368 on the bench graph: 0.7 ms -> ~0.05 ms).
+// Finished values are final, so reading one "early" is harmless; passes are non-blocking (a thread that owns several
+// vertices never waits inside one of them), so the resident grid always makes progress.
+constexpr int TD_H = 32;
+
+__global__ void k_tree_edges(const float *__restrict__ pts, const int32_t *__restrict__ pred, const uint8_t *__restrict__ is_root, int n,
+                             int2 *__restrict__ pe, float *__restrict__ td) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int p = pred[v];
+    float e = 0.f;
+    if (p >= 0)
+        e = sqrtf(dist2_exact(pts[3 * (size_t)v], pts[3 * (size_t)v + 1], pts[3 * (size_t)v + 2],
+                              pts[3 * (size_t)p], pts[3 * (size_t)p + 1], pts[3 * (size_t)p + 2]));
+    pe[v] = make_int2(p, __float_as_int(e));
+    td[v] = is_root[v] ? 0.f : -1.f;
+}
+
+__global__ void __launch_bounds__(256) k_tree_dist_walk(const int2 *__restrict__ pe, int n, float *td) {
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    bool pending = true;
+    while (pending) {
+        pending = false;
+        for (int v = t0; v < n; v += stride) {
+            if (__ldcg(td + v) >= 0.f) continue;
+            float e[TD_H];
+            int cnt = 0, cur = v;
+            float t = -1.f;
+            bool dead = false;
+#pragma unroll
+            for (int h = 0; h < TD_H; ++h) {
+                if (t < 0.f && !dead) {
+                    const int2 x = __ldg(pe + cur);
+                    if (x.x < 0) {
+                        dead = true;                       // a non-root without predecessor: nothing below it is reachable
+                    } else {
+                        e[h] = __int_as_float(x.y);
+                        cnt = h + 1;
+                        cur = x.x;
+                        t = __ldcg(td + cur);
+                    }
+                }
+            }
+            if (dead) { __stcg(td + v, FLT_MAX); continue; }
+            if (t >= 0.f) {
+                float s = t;
+                if (t != FLT_MAX) {
+#pragma unroll
+                    for (int h = TD_H - 1; h >= 0; --h)
+                        if (h < cnt) s = __fadd_rn(s, e[h]);
+                }
+                __stcg(td + v, s);
+            } else {
+                pending = true;
+            }
+        }
+    }
+}
+
 __global__ void k_tree_dist_init(const int32_t *__restrict__ pred, const uint8_t *__restrict__ is_root, int n, float *td) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -585,12 +656,26 @@ extern "C" int st_tree_distances(const float *points, const int32_t *pred, const
                                  void *ctl_workspace, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (n == 0) return ST_OK;
-    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 bytes) required");
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 8n bytes) required");
     int device = 0;
     ST_CHECK_CUDA(cudaGetDevice(&device));
     SsspCtl *ctl = (SsspCtl *)ctl_workspace;
     ST_CHECK_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SsspCtl), s));
     unsigned g = (unsigned)cdiv(n, 256);
+    if (!getenv("ST_TREE_DIST_HOPWISE")) {
+        int2 *pe = (int2 *)((char *)ctl_workspace + 256);
+        k_tree_edges<<<g, 256, 0, s>>>(points, pred, is_root, (int)n, pe, tree_dist);
+        ST_CHECK_LAUNCH();
+        int blocks = 0;
+        int rc = coop_grid((const void *)k_tree_dist_walk, 256, device, blocks);
+        if (rc) return rc;
+        if (blocks > (int)g) blocks = (int)g;
+        int nn = (int)n;
+        const int2 *pe_c = pe;
+        void *args[] = {(void *)&pe_c, (void *)&nn, (void *)&tree_dist};
+        ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_tree_dist_walk, dim3(blocks), dim3(256), args, 0, s));
+        return ST_OK;
+    }
     k_tree_dist_init<<<g, 256, 0, s>>>(pred, is_root, (int)n, tree_dist);
     ST_CHECK_LAUNCH();
     int blocks = 0;

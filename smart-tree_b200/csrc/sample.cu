@@ -124,6 +124,42 @@ __device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s
     }
 }
 
+// Collecting variant for the speculative batches (k_sample_tree_b): nothing is committed; a settled point is appended to
+// the member's touched list and stamped with (epoch, member) so that later members of the batch can tell they were
+// touched by an earlier one.  Called by whole warps (the append is warp-aggregated).
+struct Collect {
+    int32_t *tlist;       // this member's touched list
+    int *s_tcnt;          // its length (shared memory)
+    int32_t *stamp;       // per vertex: max over touchers of epoch * 16 + (15 - member)
+    int sval;
+};
+
+__device__ __forceinline__ void claim_drain_collect(const SampleArgs &a, const float4 *s_path, int len, const int2 *queue, int first,
+                                                    int count, int lane, const Collect &co) {
+    bool hit = false;
+    int gi = -1;
+    if (lane < count) {
+        const int2 e = queue[first + lane];
+        const float4 q = __ldg(a.sorted + e.x);
+        const float4 p = s_path[e.y];
+        const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - e.y);
+        bool own = true;
+        for (int j2 = 0; j2 < len; ++j2) own = own && !(claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key);
+        hit = own && sqrtf(d2) < p.w;
+        gi = __float_as_int(q.w);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (!m) return;
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(co.s_tcnt, __popc(m));
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if (hit) {
+        co.tlist[pos + __popc(m & ((1u << lane) - 1u))] = gi;
+        atomicMax(co.stamp + gi, co.sval);
+    }
+}
+
 // Range [beg, end) of the cell-sorted point array covered by grid row `row` (numbered 0 .. RW*RW-1 around the
 // cell of path vertex p) within the search sphere of radius rr: the chord of the sphere along that row.
 __device__ __forceinline__ void row_range(const SampleArgs &a, float4 p, int row, int R, float rr, int &beg, int &end) {
@@ -180,10 +216,11 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &tot
 // along the branch axes, so a few rows hold most of the candidates and a warp per row leaves the cluster
 // waiting for one warp.  Per round every thread looks up the range of ONE task (a single round trip for
 // 1024 tasks), a block scan lays the ranges end to end, and the 1024 threads walk the concatenated points.
-template <bool SHORT>
+template <int MODE>
 __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc, const float4 *s_path, int len, int nflat, int R2, int R,
                                            float r, float r2, int bid, int32_t *touch_cnt, int2 *queue, int *s_off, int *s_beg,
-                                           int *s_jj, int *s_warp, unsigned cr, unsigned CL) {
+                                           int *s_jj, int *s_warp, unsigned cr, unsigned CL, const Collect *co = nullptr) {
+    constexpr bool SHORT = MODE != 0;
     const int tid = threadIdx.x, lane = tid & 31;
     const float rr = r * 1.0001f + 1e-7f;
     const int lim = len < PATH_SMEM ? len : PATH_SMEM;
@@ -240,7 +277,8 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
                 __syncwarp();
                 if (qn >= 32) {
                     qn -= 32;
-                    claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
+                    if (MODE == 2) claim_drain_collect(a, s_path, len, queue, qn, 32, lane, *co);
+                    else claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
                     __syncwarp();
                 }
             } else if (cand) {
@@ -252,7 +290,8 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
     }
     if (SHORT) {
         __syncwarp();
-        claim_drain(a, s_path, len, queue, 0, qn, lane, bid);
+        if (MODE == 2) claim_drain_collect(a, s_path, len, queue, 0, qn, lane, *co);
+        else claim_drain(a, s_path, len, queue, 0, qn, lane, bid);
     }
 }
 
@@ -401,11 +440,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
         if (len <= SCAN_PATH) {
             // ---- 4s. short route (the common case): claim and resolve in one pass, no atomics (path.py:37-39)
             if (r > 0.f)
-                claim_flat<true>(a, base, nc, s_path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, s_queue[warp], s_off, s_beg, s_jj, s_scan, cr, CL);
+                claim_flat<1>(a, base, nc, s_path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, s_queue[warp], s_off, s_beg, s_jj, s_scan, cr, CL);
         } else {
             // ---- 4. claim: every point within r of the path records its nearest path vertex
             if (r > 0.f) {
-                claim_flat<false>(a, base, nc, s_path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, s_off, s_beg, s_jj, s_scan, cr, CL);
+                claim_flat<0>(a, base, nc, s_path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, s_off, s_beg, s_jj, s_scan, cr, CL);
                 for (long long t = (long long)nflat + gwarp; t < ntask; t += nwarp) {      // vertices beyond the staged part of the path
                     const int jj = (int)(t / R2);
                     const int v = base + path[jj];
@@ -472,6 +511,297 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
     cluster_sync_all();   // no CTA of the cluster may exit while others still expect it at a barrier
 }
 
+
+// ------------------------------------------------------------------------------------ speculative batches
+// The greedy loop above is strictly sequential: 634 iterations of ~9 us on the bench tree, most of them twigs of a few
+// vertices whose cost is a handful of dependent L2 round trips and two cluster barriers.  Successive farthest vertices
+// are usually far apart (tips of different twigs), so this kernel runs up to CL of them AT ONCE, one per CTA of the
+// cluster, and then keeps the longest prefix that provably equals the sequential result:
+//   * the next CL live entries of the sorted list are the candidates f_0 .. f_{B-1}; CTA j traces f_j to its first
+//     allocated ancestor and collects (without committing) the points its path would claim -- claims do not depend on
+//     the allocation state (path.py:30-46 searches all points), the route only through where it stops
+//   * every vertex a member touches (path + claimed points) is stamped with the smallest member index that touched it
+//   * member j is exactly what the sequential loop would do iff no earlier member touched its start vertex, any vertex
+//     of its route, or the vertex whose label becomes its parent id.  A member whose start vertex was claimed by an
+//     accepted earlier member is skipped (the sequential loop would never pick it); the first member that fails the
+//     test ends the batch -- it and everything after it is retried in the next round.  Member 0 is always valid.
+//   * accepted members commit together; labels go through atomicMax (branch ids grow with the member index, so "the
+//     latest writer wins" of path.py:135-138 is the maximum)
+// Routes of 64 or more vertices are not batched: if candidate 0's is that long, the whole cluster runs the iteration
+// of k_sample_tree on it; a long route further back ends the batch before it.
+constexpr int BATCH_PATH = 64;
+constexpr int ST_ACCEPT = 1, ST_SKIP = 2, ST_CUT = 0;
+
+__global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
+                                                           int32_t *tlist_all, int32_t *binfo) {
+    const unsigned CL = cluster_size(), cr = cluster_rank();
+    const int c = blockIdx.x / CL;
+    const int base = a.comp_off[c];
+    const int nc = a.comp_off[c + 1] - base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = cr * 32 + warp, nwarp = CL * 32;
+    const int gtid = cr * 1024 + tid, nthr = CL * 1024;
+    const int B = (int)min(CL, 16u);
+    __shared__ int s_first, s_first2, s_term, s_rbits, s_tcnt, s_mf, s_mp, s_stop, s_newbid, s_newpcur;
+    __shared__ int s_cand[16], s_status[16], s_bid[16], s_pcur[16];
+    __shared__ int s_pv[BATCH_PATH];
+    __shared__ float4 s_path[PATH_SMEM];
+    __shared__ int2 s_queue[32][QUEUE_LEN];
+    __shared__ int s_off[1024], s_beg[1024], s_jj[1024], s_scan[32];
+    int32_t *const tlist = tlist_all + (size_t)cr * n_total + base;
+    int32_t *const info = binfo + (size_t)c * 64;
+    int cursor = 0, bid = 0, pcur = 0, iter = 0, epoch = 1;
+    while (true) {
+        // ---- A. the next B live entries of the (distance desc, index asc) list, same in every CTA
+        int ncand = 0;
+        for (int sp = cursor; ncand < B && sp < nc; sp += 1024) {
+            const int pos = sp + tid;
+            int live = 0;
+            if (pos < nc) live = __ldcg(a.distw + __ldg(a.order + base + pos)) > 0.f;
+            int total;
+            const int rank = block_excl_scan_1024(live, s_scan, total);
+            if (live && ncand + rank < B) s_cand[ncand + rank] = pos;
+            ncand = min(B, ncand + total);
+            __syncthreads();
+        }
+        if (ncand == 0) break;
+        const bool member = (int)cr < ncand;
+        const int f0 = __ldg(a.order + base + s_cand[0]) - base;
+        const int fm = member ? __ldg(a.order + base + s_cand[cr]) - base : -1;
+        // ---- B. probe: ancestors 0..63 of candidate 0 (threads 0..63: is its route long?) and of this CTA's candidate
+        //         (threads 64..127); ancestor h < 64 = two octal digits = at most two dependent loads
+        if (tid == 0) { s_first = 1024; s_first2 = 1024; s_rbits = 0; s_tcnt = 0; s_mf = 16; s_mp = 16; s_term = -1; }
+        __syncthreads();
+        int x = -1;
+        const int h = tid & 63;
+        if (tid < 128) {
+            const int src = tid < 64 ? f0 : fm;
+            if (src >= 0) {
+                x = src;
+#pragma unroll
+                for (int L = 0; L < 2; ++L) {
+                    const int d = (h >> (3 * L)) & 7;
+                    if (d && x >= 0) x = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + x);
+                }
+                const bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
+                if (stop) atomicMin(tid < 64 ? &s_first : &s_first2, h);
+            }
+        }
+        __syncthreads();
+        if (s_first == 1024) {
+            // =========================== long route: one iteration of k_sample_tree on candidate 0, whole cluster
+            const int f = f0;
+            int len = 0, cur = f, term = -1;
+            float rl = 0.f;
+            int *out = a.path_out + base + pcur;
+            __syncthreads();
+            while (true) {
+                if (tid == 0) s_first = 1024;
+                __syncthreads();
+                int y = cur;
+#pragma unroll
+                for (int L = 0; L < JUMP_L; ++L) {
+                    const int d = (tid >> (3 * L)) & 7;
+                    if (d && y >= 0) y = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + y);
+                }
+                const bool stop = y < 0 || __ldcg(a.alloc + base + y) != 0;
+                if (stop) atomicMin(&s_first, tid);
+                __syncthreads();
+                const int first = s_first;
+                if (tid == first) s_term = y;
+                const int cnt = min(first, max(nc - pcur - len, 0));
+                if (tid < cnt) {
+                    out[len + tid] = y;
+                    const int v = base + y;
+                    const float rv = a.radii[v];
+                    if (len + tid < PATH_SMEM) s_path[len + tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                    rl = fmaxf(rl, rv);
+                }
+                __syncthreads();
+                len += cnt;
+                if (first < 1024) { term = s_term; break; }
+                if (cnt < 1024) { term = -1; break; }
+                cur = __ldg(jump + (size_t)(7 * 3 + 1) * n_total + base + cur);
+                __syncthreads();
+            }
+            const int parent = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));
+            const int *path = out;
+            for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+            if (lane == 0 && rl > 0.f) atomicMax(&s_rbits, __float_as_int(rl));
+            __syncthreads();
+            const float r = __int_as_float(s_rbits);
+            const float r2 = __fmul_rn(r, r);
+            const bool emit = len >= 2;
+            int32_t *const cnt_cur = a.touch_cnt + 2 * c + (iter & 1);
+            if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;
+            const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;
+            const int R2 = (2 * R + 1) * (2 * R + 1);
+            const long long ntask = (long long)len * R2;
+            const int nflat = (int)min((long long)min(len, PATH_SMEM) * R2, (long long)INT_MAX);
+            if (len <= SCAN_PATH) {
+                if (r > 0.f)
+                    claim_flat<1>(a, base, nc, s_path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, s_queue[warp], s_off, s_beg, s_jj, s_scan, cr, CL);
+            } else {
+                if (r > 0.f) {
+                    claim_flat<0>(a, base, nc, s_path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, s_off, s_beg, s_jj, s_scan, cr, CL);
+                    for (long long t = (long long)nflat + gwarp; t < ntask; t += nwarp) {
+                        const int jj = (int)(t / R2);
+                        const int v = base + path[jj];
+                        claim_task(a, base, nc, a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], (unsigned)(len - 1 - jj),
+                                   (int)(t % R2), R, r, r2, lane, cnt_cur);
+                    }
+                }
+                cluster_sync_all();
+                const int ntouch = __ldcg(cnt_cur);
+                for (int k = gtid; k < ntouch; k += nthr) {
+                    const int gi = __ldcg(a.touched + base + k);
+                    const unsigned long long bkey = __ldcg(a.best + gi);
+                    const int jj = len - 1 - (int)(unsigned)(bkey & 0xFFFFFFFFull);
+                    const float d2 = __uint_as_float((unsigned)(bkey >> 32));
+                    const float vr = jj < PATH_SMEM ? s_path[jj].w : a.radii[base + path[jj]];
+                    if (sqrtf(d2) < vr) {
+                        a.distw[gi] = -1.f;
+                        a.alloc[gi] = 1;
+                        if (emit) a.branch_id[gi] = bid;
+                    }
+                    __stcg(a.best + gi, BEST_NONE);
+                }
+            }
+            for (int jj = gtid; jj < len; jj += nthr) {
+                const int v = base + path[jj];
+                a.distw[v] = -1.f;
+                a.alloc[v] = 1;
+                if (emit) a.branch_id[v] = bid;
+            }
+            cluster_sync_all();
+            if (emit) {
+                if (cr == 0) {
+                    for (int jj = tid; jj < len / 2; jj += blockDim.x) {
+                        const int t = out[jj];
+                        out[jj] = out[len - 1 - jj];
+                        out[len - 1 - jj] = t;
+                    }
+                    if (tid == 0) {
+                        a.branch_len[base + bid] = len;
+                        a.branch_parent[base + bid] = parent;
+                    }
+                }
+                ++bid;
+                pcur += len;
+            }
+            ++iter;
+            cursor = s_cand[0] + 1;
+            __syncthreads();
+            continue;
+        }
+        // =========================== batch: CTA j works on candidate j
+        const int first2 = s_first2;
+        const bool active = member && first2 < 1024;      // (a member whose route is long ends the batch: see the resolution)
+        const int len = active ? first2 : 0;
+        float rl = 0.f;
+        if (active && tid >= 64 && tid < 128) {
+            if (h < len) {
+                s_pv[h] = x;
+                const int v = base + x;
+                const float rv = a.radii[v];
+                s_path[h] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                rl = rv;
+            } else if (h == len) {
+                s_term = x;
+            }
+        }
+        if (tid >= 64 && tid < 128) {
+            for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+            if (lane == 0 && rl > 0.f) atomicMax(&s_rbits, __float_as_int(rl));
+        }
+        __syncthreads();
+        const int term = s_term;
+        int parent = -1;
+        if (active) parent = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));      // state before this batch (nobody has committed yet)
+        const float r = __int_as_float(s_rbits);
+        const float r2 = __fmul_rn(r, r);
+        const int sval = epoch * 16 + (15 - (int)cr);
+        if (active) {
+            if (r > 0.f) {
+                const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;
+                const int R2 = (2 * R + 1) * (2 * R + 1);
+                const Collect co{tlist, &s_tcnt, stamp, sval};
+                claim_flat<2>(a, base, nc, s_path, len, len * R2, R2, R, r, r2, -1, nullptr, s_queue[warp], s_off, s_beg, s_jj, s_scan, 0u, 1u, &co);
+            }
+            if (tid < len) atomicMax(stamp + base + s_pv[tid], sval);
+        }
+        cluster_sync_all();                                  // 1: every member's stamps are in place
+        if (active) {
+            if (tid <= len) {
+                const int v = tid < len ? s_pv[tid] : (term >= 0 ? term : nc - 1);
+                const int sv = __ldcg(stamp + base + v);
+                const int who = (sv >> 4) == epoch ? 15 - (sv & 15) : 16;      // smallest member index that touched v in this batch
+                if (tid == 0) s_mf = who; else atomicMin(&s_mp, who);
+            }
+        }
+        __syncthreads();
+        if (member && tid == 0) {
+            __stcg(info + 4 * cr + 0, s_mf);
+            __stcg(info + 4 * cr + 1, s_mp);
+            __stcg(info + 4 * cr + 2, len);
+            __stcg(info + 4 * cr + 3, active ? 1 : 0);
+        }
+        cluster_sync_all();                                  // 2: every member's verdict inputs are published
+        if (tid == 0) {
+            int b = bid, p = pcur, stop = ncand;
+            for (int j = 0; j < ncand; ++j) {
+                const int mf = __ldcg(info + 4 * j), mp = __ldcg(info + 4 * j + 1), lj = __ldcg(info + 4 * j + 2), act = __ldcg(info + 4 * j + 3);
+                if (!act) { stop = j; break; }
+                if (mf < j) {
+                    if (s_status[mf] == ST_ACCEPT) { s_status[j] = ST_SKIP; continue; }      // claimed by an accepted earlier member: never picked
+                    stop = j;
+                    break;
+                }
+                if (mp < j) { stop = j; break; }
+                s_status[j] = ST_ACCEPT;
+                s_bid[j] = b;
+                s_pcur[j] = p;
+                if (lj >= 2) { ++b; p += lj; }
+            }
+            for (int j = stop; j < 16; ++j) s_status[j] = ST_CUT;
+            s_stop = stop; s_newbid = b; s_newpcur = p;
+        }
+        __syncthreads();
+        if (active && s_status[cr] == ST_ACCEPT) {
+            const bool emit = len >= 2;
+            const int mybid = s_bid[cr], mypcur = s_pcur[cr];
+            const int ntouch = s_tcnt;
+            for (int k = tid; k < ntouch; k += 1024) {
+                const int gi = tlist[k];
+                a.distw[gi] = -1.f;
+                a.alloc[gi] = 1;
+                if (emit) atomicMax(a.branch_id + gi, mybid);
+            }
+            if (tid < len) {
+                const int v = base + s_pv[tid];
+                a.distw[v] = -1.f;
+                a.alloc[v] = 1;
+                if (emit) {
+                    atomicMax(a.branch_id + v, mybid);
+                    a.path_out[base + mypcur + (len - 1 - tid)] = s_pv[tid];      // root side first
+                }
+            }
+            if (emit && tid == 0) {
+                a.branch_len[base + mybid] = len;
+                a.branch_parent[base + mybid] = parent;
+            }
+        }
+        const int stop = s_stop;
+        bid = s_newbid;
+        pcur = s_newpcur;
+        cursor = stop < ncand ? s_cand[stop] : s_cand[ncand - 1] + 1;
+        ++epoch;
+        cluster_sync_all();                                  // 3: commits visible before the next round reads the state
+    }
+    if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
+    cluster_sync_all();
+}
+
 static size_t sort_bytes(int64_t n) {
     size_t b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr,
@@ -481,7 +811,8 @@ static size_t sort_bytes(int64_t n) {
 
 extern "C" size_t st_sample_tree_workspace_bytes(int64_t n, int32_t n_comp) {
     return grid_ws_bytes(n) + align_up(sort_bytes(n)) + 2 * align_up(n * 8) + 2 * align_up(n * 4) + align_up(n * 4) + align_up(n) +
-           align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + 2 * align_up(n * 4) + align_up((2 * (size_t)n_comp + 2) * 4) + 8192;
+           align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + 2 * align_up(n * 4) + align_up((2 * (size_t)n_comp + 2) * 4) +
+           align_up(n * 4) + align_up((size_t)16 * n * 4) + align_up((size_t)n_comp * 64 * 4) + 8192;      // batches: stamps, touched lists, verdicts
 }
 
 extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const int32_t *pred, const float *tree_dist,
@@ -504,9 +835,14 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     int32_t *touch_cnt = cv.take<int32_t>(2 * (size_t)n_comp + 2);
     int32_t *jump = cv.take<int32_t>((size_t)JUMP_LEVELS * n);
     int32_t *vbase = cv.take<int32_t>(n);
+    int32_t *stamp = cv.take<int32_t>(n);
+    int32_t *tlist_all = cv.take<int32_t>((size_t)16 * n);
+    int32_t *binfo = cv.take<int32_t>((size_t)n_comp * 64);
     size_t sb = sort_bytes(n);
     void *sort_ws = cv.take<char>(sb);
     if (!cv.ok()) { set_error("st_sample_tree: workspace too small"); return ST_ERR_WORKSPACE; }
+    const bool batched = !getenv("ST_SAMPLE_SEQUENTIAL");      // speculative batches (k_sample_tree_b); same result either way
+    if (batched) ST_CHECK_CUDA(cudaMemsetAsync(stamp, 0, n * sizeof(int32_t), s));
     k_st_init<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(pred, tree_dist, (int)n, distw, alloc, branch_id, best, comp_off, n_comp, keys, vals);
     ST_CHECK_LAUNCH();
     int key_bits = 33;                                   // 32 distance bits + the component index above them
@@ -532,6 +868,7 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     int CL = cluster_cached;
     if (CL == 0) {
         cudaFuncSetAttribute((const void *)k_sample_tree, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute((const void *)k_sample_tree_b, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         for (int cand : {16, 8, 4, 2, 1}) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cand);
@@ -541,12 +878,17 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
             at.val.clusterDim.x = cand; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
             cfg.attrs = &at; cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)k_sample_tree, &cfg) == cudaSuccess && nclusters >= 1) { CL = cand; break; }
+            int nclusters_b = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)k_sample_tree, &cfg) == cudaSuccess && nclusters >= 1 &&
+                cudaOccupancyMaxActiveClusters(&nclusters_b, (const void *)k_sample_tree_b, &cfg) == cudaSuccess && nclusters_b >= 1) { CL = cand; break; }
         }
         cudaGetLastError();
         if (CL == 0) CL = 1;
-        if (const char *e = getenv("ST_SAMPLE_CLUSTER")) { int v = atoi(e); if (v >= 1 && v <= 16) CL = v; }
         cluster_cached = CL;
+    }
+    if (const char *e = getenv("ST_SAMPLE_CLUSTER")) {      // smaller cluster (= smaller speculative batch): tests
+        int v = atoi(e);
+        if (v >= 1 && v <= CL && (v & (v - 1)) == 0) CL = v;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)n_comp * CL);
@@ -558,7 +900,8 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nt = (int)n;
     const int32_t *jump_c = jump;
-    ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree, a, jump_c, nt));
+    if (batched) ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_b, a, jump_c, nt, stamp, tlist_all, binfo));
+    else ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree, a, jump_c, nt));
     return ST_OK;
 }
 

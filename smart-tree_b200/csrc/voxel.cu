@@ -42,10 +42,15 @@ extern "C" int64_t st_hash_capacity(int64_t n) {
     return c;
 }
 
-__global__ void k_hash_insert(const int4 *__restrict__ coords, int n, uint64_t *keys, int32_t *vals, uint32_t mask) {
+__global__ void k_hash_insert(const int4 *__restrict__ coords, int n, uint64_t *keys, int32_t *vals, uint32_t mask, int32_t *status) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int4 c = coords[i];
+    // the packed key has 16 bits per field (15 for the batch): anything outside would alias another voxel
+    if ((unsigned)c.x >= ST_MAX_BATCH || (unsigned)c.y > ST_MAX_COORD || (unsigned)c.z > ST_MAX_COORD || (unsigned)c.w > ST_MAX_COORD) {
+        if (status) atomicOr(status, 1);
+        return;
+    }
     uint64_t key = pack_key(c.x, c.y, c.z, c.w);
     uint32_t s = hash_key(key) & mask;
     while (true) {
@@ -58,14 +63,16 @@ __global__ void k_hash_insert(const int4 *__restrict__ coords, int n, uint64_t *
     }
 }
 
-extern "C" int st_hash_build(const int32_t *coords, int64_t n, uint64_t *keys, int32_t *vals, int64_t capacity, void *stream) {
+extern "C" int st_hash_build(const int32_t *coords, int64_t n, uint64_t *keys, int32_t *vals, int64_t capacity, int32_t *status,
+                             void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
+    if (status) ST_CHECK_CUDA(cudaMemsetAsync(status, 0, sizeof(int32_t), s));
     ST_REQUIRE(capacity >= 2 * n && (capacity & (capacity - 1)) == 0, "capacity must be a power of two >= 2n");
     ST_REQUIRE(n < (1ll << 31), "n");
     ST_CHECK_CUDA(cudaMemsetAsync(keys, 0xFF, capacity * sizeof(uint64_t), s));
     ST_CHECK_CUDA(cudaMemsetAsync(vals, 0x7F, capacity * sizeof(int32_t), s));
     if (n) {
-        k_hash_insert<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, keys, vals, (uint32_t)(capacity - 1));
+        k_hash_insert<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, keys, vals, (uint32_t)(capacity - 1), status);
         ST_CHECK_LAUNCH();
     }
     return ST_OK;
@@ -73,21 +80,30 @@ extern "C" int st_hash_build(const int32_t *coords, int64_t n, uint64_t *keys, i
 
 // ------------------------------------------------------------------------------------ subm map
 __global__ void k_subm_map(const int4 *__restrict__ coords, int n, const uint64_t *__restrict__ keys,
-                           const int32_t *__restrict__ vals, uint32_t mask, int32_t *__restrict__ nbr) {
+                           const int32_t *__restrict__ vals, uint32_t mask, int32_t *__restrict__ nbr,
+                           const int32_t *__restrict__ shape) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int k = blockIdx.y;
     if (i >= n) return;
     int4 c = __ldg(coords + i);
     int dz = k / 9 - 1, dy = (k / 3) % 3 - 1, dx = k % 3 - 1;
-    int r = (k == 13) ? i : hash_lookup(keys, vals, mask, pack_key(c.x, c.y + dz, c.z + dy, c.w + dx));
+    int r;
+    if (k == 13) {
+        r = i;
+    } else {
+        const int qz = c.y + dz, qy = c.z + dy, qx = c.w + dx;
+        // strict_spconv_bounds: a neighbour location outside the declared spatial shape is not queried (spconv's bound check)
+        const bool clipped = shape && (qz >= __ldg(shape) || qy >= __ldg(shape + 1) || qx >= __ldg(shape + 2));
+        r = (clipped || qz < 0 || qy < 0 || qx < 0) ? -1 : hash_lookup(keys, vals, mask, pack_key(c.x, qz, qy, qx));
+    }
     nbr[(size_t)k * n + i] = r;
 }
 
 extern "C" int st_subm_map(const int32_t *coords, int64_t n, const uint64_t *keys, const int32_t *vals,
-                           int64_t capacity, int32_t *nbr, void *stream) {
+                           int64_t capacity, const int32_t *spatial_shape, int32_t *nbr, void *stream) {
     if (n == 0) return ST_OK;
     dim3 grid((unsigned)cdiv(n, 256), 27);
-    k_subm_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4 *)coords, (int)n, keys, vals, (uint32_t)(capacity - 1), nbr);
+    k_subm_map<<<grid, 256, 0, (cudaStream_t)stream>>>((const int4 *)coords, (int)n, keys, vals, (uint32_t)(capacity - 1), nbr, spatial_shape);
     ST_CHECK_LAUNCH();
     return ST_OK;
 }
@@ -123,7 +139,7 @@ __global__ void k_strided_candidates(const int4 *__restrict__ coords, int n, uin
 // input (4 M -> ~0.5 M keys to sort at level 0 of the bench tree).  Any other row order is still correct -- a G
 // split over several runs just emits duplicates, which the sort + unique pass removes as before.
 __global__ void k_strided_candidates_runs(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ cand, int *__restrict__ n_cand,
-                                          int morton) {
+                                          int morton, const int32_t *__restrict__ out_shape) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 c = __ldg(coords + i);
@@ -139,7 +155,14 @@ __global__ void k_strided_candidates_runs(const int4 *__restrict__ coords, int n
         for (unsigned e = 0; e < 8; ++e)
             if ((e & ~ev) == 0) offs |= 1u << e;
     }
+    if (out_shape) {                    // strict_spconv_bounds: outputs outside the declared output shape do not exist
+        const int sz = __ldg(out_shape), sy = __ldg(out_shape + 1), sx = __ldg(out_shape + 2);
+#pragma unroll
+        for (unsigned e = 0; e < 8; ++e)
+            if (gz - (int)(e >> 2) >= sz || gy - (int)((e >> 1) & 1) >= sy || gx - (int)(e & 1) >= sx) offs &= ~(1u << e);
+    }
     const int cnt = __popc(offs);
+    if (cnt == 0) return;
     int pos = atomicAdd(n_cand, cnt);
 #pragma unroll
     for (unsigned e = 0; e < 8; ++e) {
@@ -174,8 +197,8 @@ extern "C" size_t st_strided_coords_workspace_bytes(int64_t n) {
     return align_up(strided_cub_bytes(total)) + 3 * align_up(total * sizeof(uint64_t)) + 1024;
 }
 
-extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, int32_t *out_coords, int64_t *n_out_host,
-                                 void *workspace, size_t workspace_bytes, void *stream) {
+extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int morton_order, const int32_t *out_shape, int32_t *out_coords,
+                                 int64_t *n_out_host, void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     *n_out_host = 0;
     if (n == 0) return ST_OK;
@@ -192,11 +215,12 @@ extern "C" int st_strided_coords(const int32_t *coords, int64_t n, int morton_or
     if (!cv.ok()) { set_error("st_strided_coords: workspace too small"); return ST_ERR_WORKSPACE; }
     // run-deduplicated candidates (one small read-back of their number: the sort then handles ~8x fewer keys)
     ST_CHECK_CUDA(cudaMemsetAsync(n_sel, 0, sizeof(int), s));
-    k_strided_candidates_runs<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, cand, n_sel, morton_order);
+    k_strided_candidates_runs<<<(unsigned)cdiv(n, 256), 256, 0, s>>>((const int4 *)coords, (int)n, cand, n_sel, morton_order, out_shape);
     ST_CHECK_LAUNCH();
     int n_cand = 0;
     ST_CHECK_CUDA(cudaMemcpyAsync(&n_cand, n_sel, sizeof(int), cudaMemcpyDeviceToHost, s));
     ST_CHECK_CUDA(cudaStreamSynchronize(s));
+    if (n_cand == 0 && out_shape) return ST_OK;      // everything clipped
     ST_REQUIRE(n_cand > 0 && n_cand <= total, "candidate count");
     total = n_cand;
     ST_CHECK_CUDA(cub::DeviceRadixSort::SortKeys(cub_ws, cub_bytes, cand, sorted, (int)total, 0, 64, s));

@@ -80,13 +80,15 @@ class LevelPlan:
 
 
 class LevelIndex:
-    """Coordinate table and gather maps of one resolution level."""
+    """Coordinate table and gather maps of one resolution level.  `spatial_shape` (int32 device tensor (z,y,x), optional):
+    the shape spconv would bound-check neighbour locations against -- strict_spconv_bounds, see build_levels."""
 
-    def __init__(self, coords):
+    def __init__(self, coords, spatial_shape=None):
         self.coords = coords
         self.n = coords.shape[0]
+        self.spatial_shape = spatial_shape
         self.table = ops.CoordTable(coords)
-        self.nbr = ops.subm_map(coords, self.table)
+        self.nbr = ops.subm_map(coords, self.table, spatial_shape)
         self.down = None
         self.up = None
         self.child = None
@@ -114,24 +116,49 @@ class LevelIndex:
         return p
 
 
-def build_levels(coords: torch.Tensor, depth: int, morton: bool = False, inverse_plan: bool = False) -> List[LevelIndex]:
-    levels = [LevelIndex(coords)]
+def declared_spatial_shape(coords: torch.Tensor) -> torch.Tensor:
+    """The spatial_shape the reference hands to spconv: max(coords) per axis over the whole batch -- NOT max + 1
+    (/root/reference/smart_tree/model/sparse.py:15-19).  int32 device tensor (z,y,x)."""
+    if coords.shape[0] == 0:
+        return torch.zeros(3, dtype=torch.int32, device=coords.device)
+    return coords[:, 1:].max(0).values.int().contiguous()
+
+
+def build_levels(coords: torch.Tensor, depth: int, morton: bool = False, inverse_plan: bool = False,
+                 spatial_shape: torch.Tensor = None) -> List[LevelIndex]:
+    """Index structures of every level.  With `spatial_shape` (strict_spconv_bounds) the maps reproduce spconv's bound
+    checks against the declared shape: neighbour locations >= shape are invisible to the sub-manifold convs and strided
+    outputs >= out_shape = (shape - 1) // 2 + 1 are never created; each level passes its out_shape on as the next
+    level's shape, as spconv does.  Default (None): unbounded grid."""
+    levels = [LevelIndex(coords, spatial_shape)]
     for _ in range(depth - 1):
         cur = levels[-1]
-        oc = ops.strided_coords(cur.coords, morton=morton)
-        nxt = LevelIndex(oc)
+        out_shape = None
+        if cur.spatial_shape is not None:
+            out_shape = (torch.div(cur.spatial_shape - 1, 2, rounding_mode="floor") + 1).int().contiguous()
+        oc = ops.strided_coords(cur.coords, morton=morton, out_shape=out_shape)
+        nxt = LevelIndex(oc, out_shape)
         cur.child = nxt
         if inverse_plan:
             cur.down, cur.up, cur._plans["inv"] = ops.strided_maps(cur.coords, oc, nxt.table, inverse_plan=True)
         else:
             cur.down, cur.up = ops.strided_maps(cur.coords, oc, nxt.table)
         levels.append(nxt)
+    levels[0].table.check()          # coordinate range (deeper levels derive from level 0)
     return levels
 
 
 class SmartTreeEngine:
-    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = None):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], device="cuda", eps: float = 1e-4, conv_impl: str = None,
+                 strict_spconv_bounds: bool = None):
         import os
+        # strict_spconv_bounds: reproduce spconv's bound checks against the reference's declared spatial_shape = max(coords)
+        # (see build_levels).  Off by default: the library treats the grid as unbounded (DESIGN.md section 2).
+        if strict_spconv_bounds is None:
+            strict_spconv_bounds = bool(int(os.environ.get("ST_STRICT_SPCONV_BOUNDS", "0")))
+        self.strict_spconv_bounds = bool(strict_spconv_bounds)
+        # 3x3x3 layers with cin * cout <= fma_max run on the FFMA2 kernel under "auto", wider ones on tcgen05
+        self.fma_max = int(os.environ.get("ST_CONV_FMA_MAX", "128"))
         # "auto": tensor cores (tcgen05, per-thread gathers) where they win on B200 -- every 3x3x3 layer with >= 16
         # input or output channels; the 8 -> 8 layers stay on the FMA kernel (tools/conv_micro.py: 85 us fma vs 87 tc).
         # "tp": the tile-plan kernel (source rows of a 128-row tile staged in shared memory by bulk copies) for the
@@ -216,9 +243,13 @@ class SmartTreeEngine:
                 if which == "up" and nbr is None:
                     nbr = lv.up_map()
                 impl, plan = "tp", lv.plan(which, x.shape[0])
-            elif (self.conv_impl in ("tc", "tp") or (self.conv_impl == "auto" and max(cin, cout) >= 16)) and ops.conv_tc_supported(taps, cin, cout):
+            elif (self.conv_impl in ("tc", "tp") or (self.conv_impl == "auto" and cin * cout > self.fma_max)) and ops.conv_tc_supported(taps, cin, cout):
                 impl = "tc"
         wtc = layer.tc_weights() if impl != "fma" else None
+        sorted_inv = which == "up" and self.inverse_sorted and residual is None and in2 is None and cin <= 64 and lv._plans.get("inv") is not None
+        if impl == "fma" and sorted_inv:
+            # narrow decoder (16 -> 8 at level 0): FFMA2 kernel on parity-sorted rows, only the occurring taps are visited
+            return ops.conv_gather_inv(x, lv.inverse_plan(), layer.w, n_out, layer.scale, layer.shift, out=out, relu=relu)
         if which == "up" and nbr is None:
             if not (impl == "tc" and self.inverse_sorted and residual is None and in2 is None and cin <= 64):
                 nbr = lv.up_map()
@@ -266,11 +297,12 @@ class SmartTreeEngine:
         (batch, Z-order): level 0 through a permutation of the caller's rows (undone by the heads
         kernel), deeper levels by construction."""
         coords = coords.contiguous().int()
-        inv = self.inverse_sorted and self.conv_impl in ("auto", "tc")      # (the tile-plan path wants the unsorted up map)
+        inv = self.inverse_sorted and self.conv_impl in ("auto", "tc", "fma")      # (the tile-plan path wants the unsorted up map)
+        shape = declared_spatial_shape(coords) if self.strict_spconv_bounds else None
         if not self.morton:
-            return build_levels(coords, self.depth, inverse_plan=inv)
+            return build_levels(coords, self.depth, inverse_plan=inv, spatial_shape=shape)
         perm = ops.morton_perm(coords)
-        levels = build_levels(ops.gather_rows(coords, perm), self.depth, morton=True, inverse_plan=inv)      # int32 index: no widening pass
+        levels = build_levels(ops.gather_rows(coords, perm), self.depth, morton=True, inverse_plan=inv, spatial_shape=shape)      # int32 index: no widening pass
         levels[0].perm = perm
         return levels
 
@@ -280,15 +312,21 @@ class SmartTreeEngine:
         prediction dict (model.py:77-87); with fused_outputs also medial_vector / class index."""
         if not features.is_cuda:
             raise RuntimeError("SmartTreeEngine.forward needs CUDA tensors: there is no CPU path")
-        features = features.contiguous().float()
+        features = features.float()
         coords = coords.contiguous().int()
         n = features.shape[0]
         if levels is None:
             levels = self.build_levels(coords)
         perm = getattr(levels[0], "perm", None)
-        if perm is not None:
-            features = ops.gather_rows(features, perm)
-        x = self._conv(features, self.stem, None, n, relu=True)
+        scin, scout = self.stem.w.shape[1], self.stem.w.shape[2]
+        if scin <= 8 and scout in (8, 16) and features.dim() == 2 and features.stride(1) == 1:
+            # stem fused with the Z-order row permutation; reads the caller's rows in place (a column slice is fine)
+            x = ops.stem_conv(features, self.stem.w[0], self.stem.scale, self.stem.shift, row_index=perm, relu=True)
+        else:
+            features = features.contiguous()
+            if perm is not None:
+                features = ops.gather_rows(features, perm)
+            x = self._conv(features, self.stem, None, n, relu=True)
         if trace is not None:
             trace["input_conv"] = x
         x = self._ublock(x, 0, levels, trace)

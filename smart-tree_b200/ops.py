@@ -14,7 +14,7 @@ I32, I64, F32, U8 = torch.int32, torch.int64, torch.float32, torch.uint8
 LAUNCHES = 0
 LAST_SSSP_CTL = None
 _conv_profile = None
-_KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1,
+_KERNELS_PER_CALL = {"blocks": 7, "voxelize": 3, "hash_build": 1, "subm_map": 1, "strided_coords": 2, "strided_maps": 1, "conv": 1, "stem": 1,
                      "heads": 1, "knn": 4, "outlier": 4, "edges": 2, "cc": 5, "csr": 2, "sssp": 6, "tree_dist": 3,
                      "sample_tree": 5, "tubes": 1, "repair": 1, "finish_skeletons": 1, "plan": 1, "inverse_plan": 3, "devoxelize": 1, "gather_rows": 1}
 
@@ -145,7 +145,8 @@ def devoxelize(xyz, pair_point, pair_block, pair_voxel, block_centres, block_siz
 
 # ------------------------------------------------------------------ coordinate table / maps
 class CoordTable:
-    """Open-addressing hash of (b,z,y,x) -> row."""
+    """Open-addressing hash of (b,z,y,x) -> row.  Coordinates must satisfy 0 <= z,y,x <= 65533 and 0 <= b < 32768 (the
+    64-bit keys hold 16 bits per field); `check()` raises if any row violated that (one 4-byte read-back)."""
 
     def __init__(self, coords):
         lib = _lib.load()
@@ -154,18 +155,27 @@ class CoordTable:
         self.capacity = lib.st_hash_capacity(self.n)
         self.keys = torch.empty(self.capacity, dtype=I64, device=coords.device)
         self.vals = torch.empty(self.capacity, dtype=I32, device=coords.device)
+        self.status = torch.empty(1, dtype=I32, device=coords.device)
         _count("hash_build")
-        _lib.check(lib.st_hash_build(_ptr(coords), self.n, _ptr(self.keys), _ptr(self.vals), self.capacity, _stream()),
-                   "st_hash_build")
+        _lib.check(lib.st_hash_build(_ptr(coords), self.n, _ptr(self.keys), _ptr(self.vals), self.capacity, _ptr(self.status),
+                                     _stream()), "st_hash_build")
+
+    def check(self):
+        if int(self.status.item()) != 0:
+            raise _lib.StB200Error("voxel coordinates out of range: libst_b200 needs 0 <= z,y,x <= 65533 and 0 <= batch < 32768")
+        return self
 
 
-def subm_map(coords, table: CoordTable):
+def subm_map(coords, table: CoordTable, spatial_shape=None):
+    """nbr [27, n].  spatial_shape: optional int32 device tensor (z,y,x) -> strict_spconv_bounds clipping (st_b200.h)."""
     lib = _lib.load()
     n = coords.shape[0]
     nbr = torch.empty((27, n), dtype=I32, device=coords.device)
+    if spatial_shape is not None:
+        _req(spatial_shape, I32, "spatial_shape")
     _count("subm_map")
-    _lib.check(lib.st_subm_map(_ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.capacity, _ptr(nbr), _stream()),
-               "st_subm_map")
+    _lib.check(lib.st_subm_map(_ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.capacity, _ptr(spatial_shape), _ptr(nbr),
+                               _stream()), "st_subm_map")
     return nbr
 
 
@@ -181,16 +191,18 @@ def morton_perm(coords):
     return perm
 
 
-def strided_coords(coords, morton=False):
+def strided_coords(coords, morton=False, out_shape=None):
     lib = _lib.load()
     _req(coords, I32, "coords")
     n = coords.shape[0]
     out = torch.empty((max(8 * n, 1), 4), dtype=I32, device=coords.device)
     ws = _ws(lib.st_strided_coords_workspace_bytes(n), coords.device)
     m = C.c_int64(0)
+    if out_shape is not None:
+        _req(out_shape, I32, "out_shape")
     _count("strided_coords")
-    _lib.check(lib.st_strided_coords(_ptr(coords), n, 1 if morton else 0, _ptr(out), C.byref(m), _ptr(ws), ws.numel(), _stream()),
-               "st_strided_coords")
+    _lib.check(lib.st_strided_coords(_ptr(coords), n, 1 if morton else 0, _ptr(out_shape), _ptr(out), C.byref(m), _ptr(ws), ws.numel(),
+                                     _stream()), "st_strided_coords")
     return out[:m.value].clone() if m.value * 4 < out.shape[0] else out[:m.value]
 
 
@@ -303,6 +315,47 @@ def conv_gather_tc_inv(inp, plan, weight_tc, ntaps, cin, cout, n_out, scale=None
     if prof is not None:
         ev1.record()
         prof.append((cin, cout, ntaps, n_out, 0, ev0, ev1, "tcinv"))
+    return out
+
+
+def conv_gather_inv(inp, plan, weight, n_out, scale=None, shift=None, out=None, relu=False):
+    """Inverse conv through the FMA kernel on parity-sorted rows (st_conv_gather_inv); plan = inverse_plan(coords, up),
+    weight [ntaps, cin, cout]."""
+    lib = _lib.load()
+    _req_rows(inp, "inp"); _req(weight, F32, "weight")
+    row_index, up_sorted, tile_mask = plan
+    ntaps, cin, cout = weight.shape
+    if out is None:
+        out = torch.empty((n_out, cout), dtype=F32, device=inp.device)
+    _req_rows(out, "out")
+    assert out.shape == (n_out, cout) and inp.shape[1] == cin and up_sorted.shape == (ntaps, n_out)
+    _count("conv")
+    prof = _conv_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.check(lib.st_conv_gather_inv(_ptr(inp), _ld(inp), _ptr(up_sorted), _ptr(row_index), _ptr(tile_mask), n_out, ntaps, _ptr(weight),
+                                      cin, cout, _ptr(scale), _ptr(shift), _ptr(out), _ld(out), 1 if relu else 0, _stream()),
+               "st_conv_gather_inv")
+    if prof is not None:
+        ev1.record()
+        prof.append((cin, cout, ntaps, n_out, 0, ev0, ev1, "fmainv"))
+    return out
+
+
+def stem_conv(inp, weight, scale=None, shift=None, row_index=None, relu=True):
+    """out[i] = act(scale * (W . inp[row_index[i]]) + shift) (st_stem_conv): the 1x1 input conv fused with the Z-order row
+    permutation.  inp [N, >= cin] fp32 rows with unit column stride (a column slice is fine); weight [cin, cout]."""
+    lib = _lib.load()
+    _req_rows(inp, "inp"); _req(weight, F32, "weight")
+    cin, cout = weight.shape
+    n = inp.shape[0] if row_index is None else row_index.shape[0]
+    if row_index is not None:
+        _req(row_index, I32, "row_index")
+    out = torch.empty((n, cout), dtype=F32, device=inp.device)
+    _count("stem")
+    _lib.check(lib.st_stem_conv(_ptr(inp), _ld(inp), _ptr(row_index), n, _ptr(weight), cin, cout, _ptr(scale), _ptr(shift), _ptr(out),
+                                _ld(out), 1 if relu else 0, _stream()), "st_stem_conv")
     return out
 
 
@@ -483,7 +536,7 @@ def tree_distances(points, pred, is_root):
     _req(points, F32, "points"); _req(pred, I32, "pred"); _req(is_root, U8, "is_root")
     n = pred.shape[0]
     td = torch.empty(n, dtype=F32, device=pred.device)
-    ctl = torch.zeros(64, dtype=I32, device=pred.device)
+    ctl = torch.empty(64 + 2 * n, dtype=I32, device=pred.device)       # control block + (pred, edge length) per vertex
     _count("tree_dist")
     _lib.check(lib.st_tree_distances(_ptr(points), _ptr(pred), _ptr(is_root), n, _ptr(td), _ptr(ctl), _stream()),
                "st_tree_distances")

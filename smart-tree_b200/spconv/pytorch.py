@@ -1,7 +1,10 @@
 """spconv.pytorch-compatible modules on libst_b200 (inference only; fp32).
 
 Semantics follow SURVEY.md Appendix B1-B5.  Differences from real spconv, all deliberate:
-  * coordinates are unbounded -- `spatial_shape` is carried but never used for clipping (C-3)
+  * by default the grid is unbounded -- `spatial_shape` is carried but not used for clipping (SURVEY C-3); set
+    `smart_tree_b200.spconv.pytorch.STRICT_SPATIAL_SHAPE = True` (or ST_STRICT_SPCONV_BOUNDS=1) to reproduce spconv's
+    bound checks against the declared shape (neighbour locations >= shape are invisible, strided outputs >= out_shape
+    are not created).  Coordinates must satisfy 0 <= z,y,x <= 65533, 0 <= batch < 32768 (checked, raises otherwise)
   * the sub-manifold neighbour map is built once per index set and shared by every SubMConv3d
     that sees the same `indices` tensor (spconv rebuilds it when no indice_key is given, C-4)
   * the output rows of a strided SparseConv3d are sorted by (b,z,y,x) (spconv: hash order)"""
@@ -16,6 +19,19 @@ import torch.nn as nn
 
 from .. import ops
 from ..engine import LevelIndex, _conv_w
+
+
+import os as _os
+
+STRICT_SPATIAL_SHAPE = bool(int(_os.environ.get("ST_STRICT_SPCONV_BOUNDS", "0")))
+
+
+def _shape_tensor(spatial_shape, device):
+    if spatial_shape is None or not STRICT_SPATIAL_SHAPE:
+        return None
+    if torch.is_tensor(spatial_shape):
+        return spatial_shape.to(device=device, dtype=torch.int32).contiguous()
+    return torch.tensor([int(v) for v in spatial_shape], dtype=torch.int32, device=device)
 
 
 class ConvAlgo(enum.Enum):
@@ -41,7 +57,7 @@ class SparseConvTensor:
         tensor OBJECT (weakly referenced): ResBlock / UBlock in the reference build new
         SparseConvTensors from (features, indices, ...) (model_blocks.py:149-151,227-232) but pass the
         same indices tensor along, so every conv of a level shares one map."""
-        return _level_of(self.indices)
+        return _level_of(self.indices, self.spatial_shape)
 
     def dense(self):
         raise NotImplementedError("dense() is not part of the hot path")
@@ -59,13 +75,14 @@ def _register_level(indices, lv):
     _LEVEL_CACHE[id(indices)] = (weakref.ref(indices), lv)
 
 
-def _level_of(indices) -> LevelIndex:
+def _level_of(indices, spatial_shape=None) -> LevelIndex:
     ent = _LEVEL_CACHE.get(id(indices))
     if ent is not None and ent[0]() is indices and ent[2:] == ():
         return ent[1]
     if not indices.is_cuda:
         raise RuntimeError("smart_tree_b200.spconv runs on CUDA tensors only (no CPU fallback)")
-    lv = LevelIndex(indices.int().contiguous())
+    lv = LevelIndex(indices.int().contiguous(), _shape_tensor(spatial_shape, indices.device))
+    lv.table.check()
     lv.child = None
     _register_level(indices, lv)
     return lv
@@ -156,8 +173,11 @@ class SparseConv3d(_SparseConvBase):
     def forward(self, x: SparseConvTensor):
         lv = x.level()
         if lv.down is None:
-            oc = ops.strided_coords(lv.coords)
-            lv.child = LevelIndex(oc)
+            out_shape = None
+            if lv.spatial_shape is not None:
+                out_shape = (torch.div(lv.spatial_shape - 1, 2, rounding_mode="floor") + 1).int().contiguous()
+            oc = ops.strided_coords(lv.coords, out_shape=out_shape)
+            lv.child = LevelIndex(oc, out_shape)
             lv.child.child = None
             lv.down, lv.up = ops.strided_maps(lv.coords, oc, lv.child.table)
         child = lv.child

@@ -263,6 +263,14 @@ def test_inverse_conv_parity_sorted(cin, cout, n, extent):
     assert torch.all(buf[:, :8] == 0)
     plain = ops.conv_gather(_t(y), up_d, wt, n, _t(scale), _t(shift), relu=True, impl="tc", weight_tc=wtc)
     np.testing.assert_allclose(buf[:, 8:].cpu().numpy(), plain.cpu().numpy(), rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+    # FMA counterpart on the same plan (st_conv_gather_inv: only the taps named by the tile masks are visited) == the
+    # FMA kernel on the unsorted map, bit for bit (same per-row accumulation order), and == the oracle
+    buf2 = torch.zeros((n, cout + 8), device=DEV)
+    ops.conv_gather_inv(_t(y), plan, wt, n, _t(scale), _t(shift), out=buf2[:, 8:], relu=True)
+    np.testing.assert_allclose(buf2[:, 8:].cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+    assert torch.all(buf2[:, :8] == 0)
+    plain_fma = ops.conv_gather(_t(y), up_d, wt, n, _t(scale), _t(shift), relu=True, impl="fma")
+    assert torch.equal(buf2[:, 8:], plain_fma)
     # the fused builder (strided maps + plan in one call) gives the same maps and plan
     oc_d = _t(oc, torch.int32)
     dn2, up2, plan2 = ops.strided_maps(_t(c, torch.int32), oc_d, ops.CoordTable(oc_d), inverse_plan=True)
@@ -294,6 +302,71 @@ def test_conv_slices_and_fused_identity(impl):
     ref = np.maximum(U.gather_conv(cat[:, 16:].astype(np.float64), w, nbr, n) + cat.astype(np.float64) @ w2, 0)
     np.testing.assert_allclose(outbuf[:, :16].cpu().numpy(), ref, rtol=1e-4, atol=1e-5 * np.abs(ref).max())
     assert torch.all(outbuf[:, 16:] == 0)
+
+
+@pytest.mark.parametrize("cin,cout,ld", [(3, 8, 6), (3, 8, 3), (6, 16, 6), (8, 8, 8)])
+def test_stem_conv_fused_with_row_permutation(cin, cout, ld):
+    """st_stem_conv == the generic 1x1 conv applied to the permuted rows, reading a column slice in place."""
+    ops = _ops()
+    rng = np.random.default_rng(cin + cout)
+    n = 5003
+    base = rng.standard_normal((n, ld)).astype(np.float32)
+    w = rng.standard_normal((cin, cout)).astype(np.float32)
+    scale = rng.uniform(0.5, 2, cout).astype(np.float32)
+    shift = rng.standard_normal(cout).astype(np.float32)
+    perm = rng.permutation(n).astype(np.int32)
+    xb = _t(base)
+    got = ops.stem_conv(xb[:, :cin], _t(w), _t(scale), _t(shift), row_index=_t(perm), relu=True)
+    ref = np.maximum((base[perm, :cin].astype(np.float64) @ w) * scale + shift, 0)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-5, atol=1e-5)
+    got2 = ops.stem_conv(xb[:, :cin], _t(w), None, None, row_index=None, relu=False)
+    np.testing.assert_allclose(got2.cpu().numpy(), base[:, :cin].astype(np.float64) @ w, rtol=1e-5, atol=1e-5)
+
+
+def test_strict_spconv_bounds_maps_exact():
+    """strict_spconv_bounds (declared spatial_shape = max(coords), reference sparse.py:15-19): the sub-manifold map hides
+    neighbours on the max faces, the strided conv does not create outputs >= out_shape; CUDA == oracle, bit for bit, and
+    the whole network agrees under the strict rule."""
+    from smart_tree_b200.engine import SmartTreeEngine, build_levels, declared_spatial_shape
+    ops = _ops()
+    rng = np.random.default_rng(11)
+    c = _random_coords(rng, 6000, 21, batch=1)
+    ct = _t(c, torch.int32)
+    shape = U.declared_spatial_shape(c)
+    assert declared_spatial_shape(ct).cpu().numpy().tolist() == shape.tolist()
+    ref_lv = U.build_levels(c, 3, shape)
+    loose = U.build_levels(c, 3)
+    assert (ref_lv[0].nbr != loose[0].nbr).any() and len(ref_lv[1].coords) < len(loose[1].coords)
+    lv = build_levels(ct, 3, spatial_shape=declared_spatial_shape(ct))
+    assert np.array_equal(lv[0].nbr.cpu().numpy(), ref_lv[0].nbr)
+    for a, b in zip(lv[1:], ref_lv[1:]):
+        assert np.array_equal(a.coords.cpu().numpy(), b.coords)
+        assert np.array_equal(a.nbr.cpu().numpy(), b.nbr)
+    assert np.array_equal(lv[0].down.cpu().numpy(), ref_lv[0].down) and np.array_equal(lv[0].up.cpu().numpy(), ref_lv[0].up)
+    sd = _randomise(_load("noble-elevator-58"), 5)
+    feats = rng.standard_normal((len(c), 3)).astype(np.float32)
+    p = U.to_numpy_params(sd)
+    ref = U.forward(p, feats, c, levels=U.build_levels(c, U.unet_depth(p), shape))
+    unb = U.forward(p, feats, c)
+    got = SmartTreeEngine(sd, device=DEV, strict_spconv_bounds=True).forward(_t(feats), ct)
+    for k in ("radius", "class_l"):
+        _rel_close(got[k].cpu().numpy(), ref[k])
+        assert np.abs(ref[k] - unb[k]).max() > 1e-3 * np.abs(ref[k]).max()         # the switch does change the result
+
+
+def test_coordinate_range_is_checked():
+    """Coordinates outside what the packed 64-bit keys hold must raise instead of aliasing another voxel."""
+    from smart_tree_b200 import _lib
+    from smart_tree_b200.engine import build_levels
+    ops = _ops()
+    ok = torch.tensor([[0, 0, 0, 0], [0, 65533, 65533, 65533], [32767, 1, 2, 3]], dtype=torch.int32, device=DEV)
+    ops.CoordTable(ok).check()
+    for bad in ([0, 65534, 0, 0], [0, 0, -1, 0], [32768, 0, 0, 0], [0, 0, 0, 1 << 20]):
+        c = torch.cat([ok, torch.tensor([bad], dtype=torch.int32, device=DEV)])
+        with pytest.raises(_lib.StB200Error, match="out of range"):
+            ops.CoordTable(c).check()
+        with pytest.raises(_lib.StB200Error, match="out of range"):
+            build_levels(c, 2)
 
 
 def _cloud_inputs(seed, n, vs):
@@ -517,10 +590,20 @@ def _assert_same_skeletons(got, ref):
             assert np.array_equal(gb.radii.numpy().reshape(-1), rb.radii)
 
 
+@pytest.mark.parametrize("schedule", ["batched", "batched-cluster-4", "sequential", "hopwise-tree-dist"])
 @pytest.mark.parametrize("seed,n,vs", [(0, 50000, 0.02), (3, 30000, 0.02)])
-def test_skeletonizer_topology_bit_identical(seed, n, vs):
+def test_skeletonizer_topology_bit_identical(seed, n, vs, schedule, monkeypatch):
+    """Every schedule of the skeleton kernels gives the oracle's result bit for bit: sample_tree in speculative batches
+    (default, cluster of 16 or 4 CTAs = batch size) or strictly sequential; tree distances by chain walking (default)
+    or hop by hop."""
     from smart_tree_b200.data_types.cloud import Cloud
     from smart_tree_b200.skeleton.skeletonize import Skeletonizer
+    if schedule == "sequential":
+        monkeypatch.setenv("ST_SAMPLE_SEQUENTIAL", "1")
+    if schedule == "hopwise-tree-dist":
+        monkeypatch.setenv("ST_TREE_DIST_HOPWISE", "1")
+    if schedule == "batched-cluster-4":
+        monkeypatch.setenv("ST_SAMPLE_CLUSTER", "4")
     xyz, mv = _medial_case(seed, n, vs)
     sk = Skeletonizer(K=16, min_connection_length=0.02, minimum_graph_vertices=32, device=torch.device(DEV))
     got = sk.forward(Cloud(xyz=_t(xyz), medial_vector=_t(mv)))

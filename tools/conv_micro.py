@@ -23,25 +23,28 @@ MORTON = bool(int(os.environ.get("ST_MORTON", "1")))
 coords = bb.coords.contiguous()
 if MORTON:
     coords = coords[ops.morton_perm(coords).long()].contiguous()
-levels = build_levels(coords, 4, morton=MORTON, inverse_plan=(impl == "tcinv"))
+levels = build_levels(coords, 4, morton=MORTON, inverse_plan=(impl in ("tcinv", "fmainv")))
 print("levels", [l.n for l in levels], "z-order" if MORTON else "input order")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-cases = [(8, 8, 0), (16, 8, 0), (16, 16, 1), (32, 16, 1), (32, 32, 2), (64, 32, 2), (64, 64, 3)]
+cases = [(8, 8, 0), (16, 8, 0), (8, 16, 0), (16, 16, 1), (32, 16, 1), (16, 32, 1), (32, 32, 2), (64, 32, 2), (64, 64, 3)]
 if only:
     cases = [only]
 if os.environ.get("ST_TC_DBG"):
     from smart_tree_b200 import _lib as _l
     _l.load().st_debug_tc_set(int(os.environ["ST_TC_DBG"]))
-if impl == "tcinv":
+if impl in ("tcinv", "fmainv"):
     cases = [c for c in [(16, 8, 0), (32, 16, 1), (64, 32, 2)] if only is None or c == only]
 for cin, cout, li in cases:
     lv = levels[li]
-    if impl == "tcinv":
+    if impl in ("tcinv", "fmainv"):
         x = torch.randn(levels[li + 1].n, cin, device=dev)
         w = torch.randn(27, cin, cout, device=dev) / (4 * cin) ** 0.5
         wtc = ops.conv_tc_prepare(w)
         out = torch.empty(lv.n, cout, device=dev)
-        run = lambda: ops.conv_gather_tc_inv(x, lv.inverse_plan(), wtc, 27, cin, cout, lv.n, out=out, relu=True)
+        if impl == "tcinv":
+            run = lambda: ops.conv_gather_tc_inv(x, lv.inverse_plan(), wtc, 27, cin, cout, lv.n, out=out, relu=True)
+        else:
+            run = lambda: ops.conv_gather_inv(x, lv.inverse_plan(), w, lv.n, out=out, relu=True)
         for _ in range(3):
             run()
         ts = []
