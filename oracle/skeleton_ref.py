@@ -161,6 +161,7 @@ def sssp(n, edges, weights, root):
         a = sparse.csr_matrix((ww.astype(np.float64) + 1e-30, (u, v)), shape=(n, n))
         # float64 Dijkstra tree -> fp32 running sums along it: an upper bound of the fp32 fixed point
         d64, p64 = csgraph.dijkstra(a, directed=True, indices=root, return_predecessors=True)
+        p64 = p64.astype(np.int64)             # scipy returns int32: `par * n + v` below overflowed for n > 46340 vertices
         done = np.zeros(n, bool)
         done[root] = True
         pending = np.nonzero(p64 >= 0)[0]

@@ -73,6 +73,217 @@ struct ConvCfg {
     static constexpr int SMEM_BYTES = 2 * STAGE_FLOATS * 4;
 };
 
+// ---- epilogue shared by the FMA kernels: affine, residual, fused identity 1x1 conv, activation, slice store
+template <int RT, int CT, int COUT>
+__device__ __forceinline__ void conv_epilogue(const ConvArgs &a, const int (&rows)[RT], const unsigned long long (&acc)[RT][CT / 2], int co0) {
+#pragma unroll
+    for (int r = 0; r < RT; ++r) {
+        if (rows[r] >= a.n_out) continue;
+        const int row = a.out_index ? __ldg(a.out_index + rows[r]) : rows[r];      // output row (residual / in2 follow it)
+        float v[CT];
+#pragma unroll
+        for (int c = 0; c < CT / 2; ++c) f2_unpack(acc[r][c], v[2 * c], v[2 * c + 1]);
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            float sc = a.scale ? __ldg(a.scale + co0 + c) : 1.f;
+            float sh = a.shift ? __ldg(a.shift + co0 + c) : 0.f;
+            v[c] = fmaf(v[c], sc, sh);
+        }
+        if (a.res) {
+#pragma unroll
+            for (int c4 = 0; c4 < CT / 4; ++c4) {
+                float4 rr = __ldg((const float4 *)(a.res + (size_t)row * a.res_ld + co0) + c4);
+                v[c4 * 4 + 0] += rr.x; v[c4 * 4 + 1] += rr.y; v[c4 * 4 + 2] += rr.z; v[c4 * 4 + 3] += rr.w;
+            }
+        }
+        if (a.in2) {
+            float e[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) e[c] = 0.f;
+            const float *xr = a.in2 + (size_t)row * a.in2_ld;
+            for (int ci = 0; ci < a.cin2; ++ci) {
+                float xv = __ldg(xr + ci);
+#pragma unroll
+                for (int c4 = 0; c4 < CT / 4; ++c4) {
+                    float4 w4 = __ldg((const float4 *)(a.w2 + (size_t)ci * COUT + co0) + c4);
+                    e[c4 * 4 + 0] = fmaf(xv, w4.x, e[c4 * 4 + 0]);
+                    e[c4 * 4 + 1] = fmaf(xv, w4.y, e[c4 * 4 + 1]);
+                    e[c4 * 4 + 2] = fmaf(xv, w4.z, e[c4 * 4 + 2]);
+                    e[c4 * 4 + 3] = fmaf(xv, w4.w, e[c4 * 4 + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] += e[c];
+        }
+        if (a.act & ST_ACT_RELU) {
+#pragma unroll
+            for (int c = 0; c < CT; ++c) v[c] = fmaxf(v[c], 0.f);
+        }
+        float4 *o = (float4 *)(a.out + (size_t)row * a.out_ld + co0);
+#pragma unroll
+        for (int c4 = 0; c4 < CT / 4; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
+    }
+}
+
+// One 32-byte row per lane and instruction (LDG.256, sm_100): a gathered 8-channel row is one sector, so the L1 data
+// pipe serves it in one pass instead of two half-used ones.
+__device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
+// ---- narrow layers (8 or 16 input channels: level 0 and the encoder / decoder between levels 0 and 1) -----------------
+// ncu on the round-1 kernel (8 -> 8, level 0): L1 data-pipe wavefronts 65-80 % of peak, FMA pipe 37 %, DRAM 11 % -- these
+// layers are bound by what goes through the L1 data pipe: the gathered rows (27 x 32 B per voxel) and the per-tap weight
+// tile every warp re-reads from shared memory.  Hence
+//   * a thread owns FOUR output rows x 8 output channels: the 16 broadcast LDS.128 of an 8 x 8 weight tile serve 128 rows
+//     of a warp instead of 64;
+//   * a gathered row is ONE 32-byte load per lane (LDG.256): one sector, one pass of the data pipe instead of two
+//     half-used ones;
+//   * 16 input channels are two "virtual taps" of 8 (same map entry, second half of the row, second half of the weight
+//     tile); 16 / 32 output channels are 2 / 4 threads per row, each with its own 8 channels -- lanes of a row group issue
+//     the same gather address (one sector) and the weight LDS of the groups multicast from different banks;
+//   * map entries run two virtual taps ahead and feature rows one ahead of the arithmetic (registers), FFMA2 arithmetic.
+template <int CIN, int COUT>
+struct NarrowCfg {
+    static constexpr int THREADS = 128;
+    static constexpr int H = CIN / 8;                   // virtual taps per tap
+    static constexpr int CT = 8;                        // output channels per thread
+    static constexpr int TPR = COUT / 8;                // threads per output row
+    static constexpr int RT = 4;                        // rows per thread
+    static constexpr int ROW_SLOTS = THREADS / TPR;
+    static constexpr int ROWS = ROW_SLOTS * RT;         // rows per CTA: 512 / 256 / 128
+    static constexpr int TAP_FLOATS = CIN * COUT;
+    static constexpr int TPS_RAW = 4096 / TAP_FLOATS;   // taps per 16 KB stage
+    static constexpr int TPS = TPS_RAW < 1 ? 1 : (TPS_RAW > 27 ? 27 : TPS_RAW);
+    static constexpr int STAGE_FLOATS = TPS * TAP_FLOATS;
+    static constexpr int SMEM_BYTES = 2 * STAGE_FLOATS * 4;
+};
+
+template <int CIN, int COUT, bool V8>
+__global__ void __launch_bounds__(128, 4) k_conv_narrow(ConvArgs a) {
+    using C = NarrowCfg<CIN, COUT>;
+    extern __shared__ __align__(16) float smem[];
+    const int tid = threadIdx.x;
+    const int cg = tid % C::TPR;
+    const int slot = tid / C::TPR;
+    const int row0 = blockIdx.x * C::ROWS + slot;
+    int rows[C::RT];
+#pragma unroll
+    for (int r = 0; r < C::RT; ++r) rows[r] = row0 + r * C::ROW_SLOTS;
+    unsigned long long acc[C::RT][4];
+#pragma unroll
+    for (int r = 0; r < C::RT; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[r][c] = 0ull;
+
+    // taps this CTA has to visit (see k_conv_fma)
+    __shared__ int s_taps[32];
+    __shared__ int s_ntaps;
+    if (tid < 32) {
+        unsigned m = a.ntaps >= 32 ? 0xffffffffu : ((1u << a.ntaps) - 1u);
+        if (a.tile_mask) {
+            unsigned mm = 0;
+            const int tile0 = blockIdx.x * (C::ROWS / 128), ntile = (a.n_out + 127) / 128;
+            for (int t = 0; t < C::ROWS / 128; ++t)
+                if (tile0 + t < ntile) mm |= __ldg(a.tile_mask + tile0 + t);
+            m &= mm;
+        }
+        if (m & (1u << tid)) s_taps[__popc(m & ((1u << tid) - 1u))] = tid;
+        if (tid == 0) s_ntaps = __popc(m);
+    }
+    __syncthreads();
+    const int nlist = s_ntaps;
+
+    const int nstages = (a.ntaps + C::TPS - 1) / C::TPS;
+    auto issue = [&](int s) {
+        int t0 = s * C::TPS;
+        int nt = min(C::TPS, a.ntaps - t0);
+        const float *src = a.w + (size_t)t0 * C::TAP_FLOATS;
+        float *dst = smem + (s & 1) * C::STAGE_FLOATS;
+        for (int i = tid * 4; i < nt * C::TAP_FLOATS; i += C::THREADS * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    issue(0);
+    int li = 0;
+    for (int s = 0; s < nstages; ++s) {
+        if (s + 1 < nstages) { issue(s + 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+        __syncthreads();
+        const float *ws = smem + (s & 1) * C::STAGE_FLOATS;
+        const int t0 = s * C::TPS;
+        const int nt = min(C::TPS, a.ntaps - t0);
+        int lend = li;
+        while (lend < nlist && s_taps[lend] < t0 + nt) ++lend;
+        // virtual taps vi = H * (list position) + (half of the input row), for list positions [li, lend)
+        const int v0 = li * C::H, v1 = lend * C::H;
+        auto map_at = [&](int vi, int (&j)[C::RT]) {
+            const int k = vi < v1 ? s_taps[vi / C::H] : -1;
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) {
+                j[r] = -1;
+                if (k >= 0 && rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+            }
+        };
+        auto rows_at = [&](int vi, const int (&j)[C::RT], float4 (&x)[C::RT][2]) {
+            const int half = C::H == 1 ? 0 : vi % C::H;
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) {
+                x[r][0] = x[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j[r] >= 0) {
+                    const float *p = a.in + (size_t)j[r] * a.in_ld + 8 * half;
+                    if (V8) ldg256(p, x[r][0], x[r][1]);
+                    else { x[r][0] = __ldg((const float4 *)p); x[r][1] = __ldg((const float4 *)p + 1); }
+                }
+            }
+        };
+        int jn1[C::RT], jn2[C::RT];
+        float4 xn[C::RT][2];
+        {
+            int j0[C::RT];
+            map_at(v0, j0);
+            map_at(v0 + 1, jn1);
+            rows_at(v0, j0, xn);
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) jn2[r] = j0[r];
+        }
+        for (int vi = v0; vi < v1; ++vi) {
+            const int k = s_taps[vi / C::H];
+            const int half = C::H == 1 ? 0 : vi % C::H;
+            float4 xc[C::RT][2];
+            bool any = false;
+#pragma unroll
+            for (int r = 0; r < C::RT; ++r) {
+                any |= jn2[r] >= 0;
+                xc[r][0] = xn[r][0]; xc[r][1] = xn[r][1];
+                jn2[r] = jn1[r];
+            }
+            rows_at(vi + 1, jn1, xn);              // rows of the next virtual tap (its entries were loaded one step ago)
+            map_at(vi + 2, jn1);                   // entries of the one after that
+            if (!__any_sync(0xffffffffu, any)) continue;
+            const float *wt = ws + (k - t0) * C::TAP_FLOATS + half * 8 * COUT + cg * 8;
+#pragma unroll
+            for (int ci = 0; ci < 8; ++ci) {
+                const float4 wa = *(const float4 *)(wt + ci * COUT), wb = *(const float4 *)(wt + ci * COUT + 4);
+                const unsigned long long w01 = f2_pack(wa.x, wa.y), w23 = f2_pack(wa.z, wa.w), w45 = f2_pack(wb.x, wb.y), w67 = f2_pack(wb.z, wb.w);
+#pragma unroll
+                for (int r = 0; r < C::RT; ++r) {
+                    const float4 xq = xc[r][ci >> 2];
+                    const float xv = (ci & 3) == 0 ? xq.x : (ci & 3) == 1 ? xq.y : (ci & 3) == 2 ? xq.z : xq.w;
+                    const unsigned long long xx = f2_pack(xv, xv);
+                    acc[r][0] = ffma2(xx, w01, acc[r][0]);
+                    acc[r][1] = ffma2(xx, w23, acc[r][1]);
+                    acc[r][2] = ffma2(xx, w45, acc[r][2]);
+                    acc[r][3] = ffma2(xx, w67, acc[r][3]);
+                }
+            }
+        }
+        li = lend;
+        __syncthreads();
+    }
+    conv_epilogue<C::RT, 8, COUT>(a, rows, acc, cg * 8);
+}
+
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_fma(ConvArgs a) {
     using C = ConvCfg<CIN, COUT>;
@@ -215,55 +426,7 @@ __global__ void __launch_bounds__(256, (CIN <= 8 && COUT <= 8 ? 4 : 1)) k_conv_f
         __syncthreads();
     }
 
-    // ---- epilogue: affine, residual, fused identity 1x1 conv, activation, slice store
-    const int co0 = cg * C::CT;
-#pragma unroll
-    for (int r = 0; r < C::RT; ++r) {
-        if (rows[r] >= a.n_out) continue;
-        const int row = a.out_index ? __ldg(a.out_index + rows[r]) : rows[r];      // output row (residual / in2 follow it)
-        float v[C::CT];
-#pragma unroll
-        for (int c = 0; c < C::CT / 2; ++c) f2_unpack(acc[r][c], v[2 * c], v[2 * c + 1]);
-#pragma unroll
-        for (int c = 0; c < C::CT; ++c) {
-            float sc = a.scale ? __ldg(a.scale + co0 + c) : 1.f;
-            float sh = a.shift ? __ldg(a.shift + co0 + c) : 0.f;
-            v[c] = fmaf(v[c], sc, sh);
-        }
-        if (a.res) {
-#pragma unroll
-            for (int c4 = 0; c4 < C::CT / 4; ++c4) {
-                float4 rr = __ldg((const float4 *)(a.res + (size_t)row * a.res_ld + co0) + c4);
-                v[c4 * 4 + 0] += rr.x; v[c4 * 4 + 1] += rr.y; v[c4 * 4 + 2] += rr.z; v[c4 * 4 + 3] += rr.w;
-            }
-        }
-        if (a.in2) {
-            float e[C::CT];
-#pragma unroll
-            for (int c = 0; c < C::CT; ++c) e[c] = 0.f;
-            const float *xr = a.in2 + (size_t)row * a.in2_ld;
-            for (int ci = 0; ci < a.cin2; ++ci) {
-                float xv = __ldg(xr + ci);
-#pragma unroll
-                for (int c4 = 0; c4 < C::CT / 4; ++c4) {
-                    float4 w4 = __ldg((const float4 *)(a.w2 + (size_t)ci * COUT + co0) + c4);
-                    e[c4 * 4 + 0] = fmaf(xv, w4.x, e[c4 * 4 + 0]);
-                    e[c4 * 4 + 1] = fmaf(xv, w4.y, e[c4 * 4 + 1]);
-                    e[c4 * 4 + 2] = fmaf(xv, w4.z, e[c4 * 4 + 2]);
-                    e[c4 * 4 + 3] = fmaf(xv, w4.w, e[c4 * 4 + 3]);
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < C::CT; ++c) v[c] += e[c];
-        }
-        if (a.act & ST_ACT_RELU) {
-#pragma unroll
-            for (int c = 0; c < C::CT; ++c) v[c] = fmaxf(v[c], 0.f);
-        }
-        float4 *o = (float4 *)(a.out + (size_t)row * a.out_ld + co0);
-#pragma unroll
-        for (int c4 = 0; c4 < C::CT / 4; ++c4) o[c4] = make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]);
-    }
+    conv_epilogue<C::RT, C::CT, COUT>(a, rows, acc, cg * C::CT);
 }
 
 // Generic fallback for channel counts outside the tuned set (e.g. the 3->8 stem):
@@ -305,6 +468,20 @@ static int launch_fma(const ConvArgs &a, cudaStream_t s) {
     return ST_OK;
 }
 
+template <int CIN, int COUT>
+static int launch_narrow(const ConvArgs &a, cudaStream_t s) {
+    using C = NarrowCfg<CIN, COUT>;
+    static_assert(C::SMEM_BYTES <= 48 * 1024, "narrow conv stages must fit the default shared-memory limit");
+    unsigned grid = (unsigned)cdiv(a.n_out, C::ROWS);
+    // 32-byte gathers when every input row starts on a 32-byte boundary
+    if (((uintptr_t)a.in & 31) == 0 && a.in_ld % 8 == 0 && !getenv("ST_CONV_NO_V8"))
+        k_conv_narrow<CIN, COUT, true><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+    else
+        k_conv_narrow<CIN, COUT, false><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(a);
+    ST_CHECK_LAUNCH();
+    return ST_OK;
+}
+
 static bool aligned16(const void *p) { return ((uintptr_t)p & 15) == 0; }
 static int conv_dispatch(const ConvArgs &a, cudaStream_t s);
 
@@ -331,6 +508,11 @@ static int conv_dispatch(const ConvArgs &a, cudaStream_t s) {
     bool fast = aligned16(in) && aligned16(out) && aligned16(w) && (in_ld % 4 == 0) && (out_ld % 4 == 0) &&
                 (!residual || (aligned16(residual) && res_ld % 4 == 0)) && (!w2 || aligned16(w2));
     if (fast) {
+        if (!getenv("ST_CONV_NO_NARROW")) {
+#define ST_NARROW(CI, CO) if (cin == CI && cout == CO) return launch_narrow<CI, CO>(a, s);
+            ST_NARROW(8, 8) ST_NARROW(8, 16) ST_NARROW(16, 8) ST_NARROW(16, 16) ST_NARROW(16, 32)
+#undef ST_NARROW
+        }
 #define ST_CASE(CI, CO) if (cin == CI && cout == CO) return launch_fma<CI, CO>(a, s);
         ST_CASE(8, 8) ST_CASE(8, 16) ST_CASE(16, 8) ST_CASE(16, 16) ST_CASE(16, 32) ST_CASE(32, 16)
         ST_CASE(32, 32) ST_CASE(32, 64) ST_CASE(64, 32) ST_CASE(64, 64) ST_CASE(8, 4) ST_CASE(4, 4)

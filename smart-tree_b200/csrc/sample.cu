@@ -530,6 +530,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree(SampleArgs a, const int
 // Routes of 64 or more vertices are not batched: if candidate 0's is that long, the whole cluster runs the iteration
 // of k_sample_tree on it; a long route further back ends the batch before it.
 constexpr int BATCH_PATH = 64;
+// debug counters of component 0 of the last launch: [rounds, whole-cluster (long route) iterations, batches, members offered,
+// accepted, skipped, batches cut by a long member, cut because the start vertex was touched, cut because the route / parent
+// vertex was touched, claimed points of accepted members, cycles in batches, cycles in long iterations, ...]
+__device__ unsigned long long g_stb_stats[16];
 constexpr int ST_ACCEPT = 1, ST_SKIP = 2, ST_CUT = 0;
 
 __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
@@ -551,7 +555,12 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
     int32_t *const tlist = tlist_all + (size_t)cr * n_total + base;
     int32_t *const info = binfo + (size_t)c * 64;
     int cursor = 0, bid = 0, pcur = 0, iter = 0, epoch = 1;
+    unsigned long long dbg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dbg[i] = 0;
+    long long t_mark = clock64();
     while (true) {
+        ++dbg[0];
         // ---- A. the next B live entries of the (distance desc, index asc) list, same in every CTA
         int ncand = 0;
         for (int sp = cursor; ncand < B && sp < nc; sp += 1024) {
@@ -691,6 +700,8 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
             }
             ++iter;
             cursor = s_cand[0] + 1;
+            ++dbg[1];
+            { const long long t = clock64(); dbg[11] += (unsigned long long)(t - t_mark); t_mark = t; }
             __syncthreads();
             continue;
         }
@@ -765,6 +776,13 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
             }
             for (int j = stop; j < 16; ++j) s_status[j] = ST_CUT;
             s_stop = stop; s_newbid = b; s_newpcur = p;
+            ++dbg[2];
+            dbg[3] += ncand;
+            for (int j = 0; j < stop; ++j) { if (s_status[j] == ST_ACCEPT) ++dbg[4]; else ++dbg[5]; }
+            if (stop < ncand) {
+                const int mf = __ldcg(info + 4 * stop), mp = __ldcg(info + 4 * stop + 1), act = __ldcg(info + 4 * stop + 3);
+                if (!act) ++dbg[6]; else if (mf < stop) ++dbg[7]; else if (mp < stop) ++dbg[8];
+            }
         }
         __syncthreads();
         if (active && s_status[cr] == ST_ACCEPT) {
@@ -791,6 +809,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
                 a.branch_parent[base + mybid] = parent;
             }
         }
+        if (tid == 0) { const long long t = clock64(); dbg[10] += (unsigned long long)(t - t_mark); t_mark = t; }
         const int stop = s_stop;
         bid = s_newbid;
         pcur = s_newpcur;
@@ -799,6 +818,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
         cluster_sync_all();                                  // 3: commits visible before the next round reads the state
     }
     if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
+    if (tid == 0 && cr == 0 && c == 0) { dbg[15] = CL; for (int i = 0; i < 16; ++i) g_stb_stats[i] = dbg[i]; }
     cluster_sync_all();
 }
 
@@ -909,6 +929,10 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
 // [find, trace, claim, resolve, finish], iterations, traced path vertices
 extern "C" int st_debug_sample_iters(int *out_host) {
     ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_st_iter, sizeof(int) * 8192));
+    return ST_OK;
+}
+extern "C" int st_debug_sample_batch_stats(unsigned long long *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stb_stats, sizeof(unsigned long long) * 16));
     return ST_OK;
 }
 extern "C" int st_debug_sample_stats(unsigned long long *out_host) {

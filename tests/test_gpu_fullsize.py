@@ -168,10 +168,22 @@ def test_full_size_tree_matches_oracle(name, weights, seed, points, voxel):
     lc = pipe.labelled_cloud
     labelled = dict(xyz=lc.xyz.cpu().numpy(), medial_vector=lc.medial_vector.cpu().numpy(), class_l=lc.class_l.cpu().numpy().reshape(-1))
     t0 = time.perf_counter()
-    _, _, post = P.process_cloud(None, None, None, labelled=labelled)
+    _, ref_sk, post = P.process_cloud(None, None, None, labelled=labelled)
     report["skeleton_oracle_seconds"] = round(time.perf_counter() - t0, 1)
-    nb, worst = _compare_skeletons(skel, post)
+    # stage by stage first (a mismatch names the stage): components, SSSP predecessors, tree distances, branch paths
     last = pipe.skeletonizer.last
+    off = last["comp_off"].cpu().numpy()
+    assert len(ref_sk) == int(last["n_components"])
+    for c, r in enumerate(ref_sk):
+        lo, hi = int(off[c]), int(off[c + 1])
+        assert np.array_equal(last["order"][lo:hi].cpu().numpy(), r.vertex_ids), "component vertex sets"
+        assert np.array_equal(last["pred"][lo:hi].cpu().numpy(), r.preds), "SSSP predecessors"
+        assert np.array_equal(last["tree_dist"][lo:hi].cpu().numpy(), r.distances), "tree distances"
+        nbr, npth = int(last["comp_n_branches"][c]), int(last["comp_n_path"][c])
+        assert nbr == len(r.branches), "branch count"
+        assert np.array_equal(last["branch_parent"][lo:lo + nbr].cpu().numpy(), np.array([b.parent_id for b in r.branches])), "parent ids"
+        assert np.array_equal(last["path"][lo:lo + npth].cpu().numpy(), np.concatenate([b.path for b in r.branches])), "branch paths"
+    nb, worst = _compare_skeletons(skel, post)
     report["skeleton"] = {"branches": nb, "node_coordinate_max_abs_error": worst, "vertices": int(last["order"].shape[0]),
                           "components": int(last["n_components"]), "digest": skeleton_digest(skel.skeletons)}
     assert nb > 100

@@ -187,3 +187,28 @@ def test_devoxelised_inference_restates_its_definition():
                 seen[p] = True
                 assert np.array_equal(got["medial_vector"][p], vmed[first[b] + pcid[j]])
     assert np.array_equal(seen, got["class_l"] >= 0) and not seen[-2:].any() and seen[:-2].mean() > 0.9     # (sparse 1 m blocks of <= 20 points are dropped, dataset.py:178)
+
+
+def test_sssp_oracle_above_46341_vertices():
+    """Regression: scipy's dijkstra returns int32 predecessors, and `pred * n + v` overflowed for n > 46340 vertices --
+    the oracle then produced distances below the true fixed point and predecessor chains that never reach the root
+    (found by the full-size parity run: 245 529 skeleton vertices at BASELINE config C2)."""
+    rng = np.random.default_rng(0)
+    n = 60000
+    pts = rng.uniform(0, 1, (n, 3)).astype(np.float32) * np.float32([4, 0.3, 0.3])
+    idx, d2 = S.knn(pts, pts, 8, 0.08)
+    src = np.repeat(np.arange(n), 8)
+    ok = idx.reshape(-1) > 0
+    e = np.stack([src[ok], idx.reshape(-1)[ok]], 1)
+    w = np.sqrt(d2.reshape(-1)[ok]).astype(np.float32)
+    comp = S.connected_components(n, e, 32)[0]
+    assert len(comp) > 46341
+    loc = np.full(n, -1, np.int64); loc[comp] = np.arange(len(comp))
+    sel = np.isin(e[:, 0], comp)
+    pred, dist = S.sssp(len(comp), loc[e[sel]], w[sel], 0)
+    assert (dist < np.finfo(np.float32).max).all() and (pred >= 0).sum() == len(comp) - 1
+    # the fixed point: nothing relaxes any further, and every predecessor edge is tight
+    u, v = loc[e[sel]][:, 0], loc[e[sel]][:, 1]
+    assert not (dist[u] + w[sel] < dist[v]).any() and not (dist[v] + w[sel] < dist[u]).any()
+    td = S.tree_distances(pts[comp], pred, 0)
+    assert (td < np.finfo(np.float32).max).all()             # every chain reaches the root

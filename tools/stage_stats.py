@@ -75,11 +75,17 @@ except Exception as exc:
 sst = (C.c_uint * 5)()
 lib.st_debug_sssp_stats.argtypes = [C.c_void_p, C.c_void_p]
 lib.st_debug_sssp_stats(C.c_void_p(ops.LAST_SSSP_CTL.data_ptr()), sst)
+bst = (C.c_ulonglong * 16)()
+lib.st_debug_sample_batch_stats.argtypes = [C.c_void_p]
+lib.st_debug_sample_batch_stats(bst)
+bnames = ["rounds", "long_iterations", "batches", "members_offered", "accepted", "skipped", "cut_long_member", "cut_start_touched",
+          "cut_route_or_parent_touched", "claimed_points", "cycles_batches", "cycles_long"]
+batch_stats = {n: int(bst[i]) for i, n in enumerate(bnames)}
 names = ["find", "trace", "claim", "resolve", "finish"]
 cyc = {n: stats[i] for i, n in enumerate(names)}
 last = pipe.skeletonizer.last
 print(json.dumps({"ms_per_step_with_timers": tot, "ms_per_step": untimed, "sections_ms": rec, "min_med_max_ms": spread,
-                  "sample_tree_cycles": cyc, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
+                  "sample_tree_cycles": cyc, "sample_tree_batches": batch_stats, "sample_tree_iterations": stats[5], "sample_tree_path_vertices": stats[6],
                   "cluster_size": stats[7], "sssp_chunks_evals_improvements_x_lanemode": list(sst), "sssp_tree_max_depth_hops": max_depth, "branches": sum(len(s.branches) for s in sk.skeletons), "components": last["n_components"],
                   "skeleton_vertices": int(last["order"].shape[0]), "edges": int(last["edges"].shape[0]),
                   "voxels": int(pipe.model_inference.last_batch.feats.shape[0])}, indent=1))
