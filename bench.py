@@ -1,20 +1,24 @@
 #!/usr/bin/env python
 """Benchmark of the smart-tree hot path on B200 (contract: see the task statement / DESIGN.md).
 
-  python bench.py --gpus N --steps K --warmup W            # B200 arm (N>1: launched under torchrun)
-  python bench.py --impl reference --steps K --warmup W    # reference arm = CPU oracle port on host cores
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4|c5]     # B200 arm (N>1: launched under torchrun)
+  python bench.py --impl reference --steps K --warmup W [--config ...]      # reference arm = CPU oracle port, host cores
 
-One "step" = one pass of Pipeline.process_cloud over one synthetic tree cloud per rank:
-CentreCloud -> block tiling -> voxelise -> sparse UNet -> class filter -> skeletonise ->
-prune/repair/smooth, then (N>1) the NCCL gather of the packed skeletons.
-Workload = BASELINE.json configs[1]: noble-elevator-58, 1M-point tree, 1 cm voxels, one tree per GPU
-(weak scaling, seeds 0..N-1).  metric = points/s (whole job).
+One "step" = one pass of the hot path over one batch of synthetic input per rank:
+  tree configs (c2, c3, c4): Pipeline.process_cloud on one synthetic tree cloud per rank (CentreCloud -> block tiling ->
+      voxelise -> sparse UNet -> class filter -> skeletonise -> prune / repair / smooth), then (N > 1) ONE NCCL
+      all-gather of the packed skeletons.  Rank r gets the tree with seed seed0 + r: weak scaling, distinct trees.
+  plot config (c5): Pipeline.process_plot_sharded on one forest plot held by every rank -- blocks dealt round-robin,
+      all-gather of the labelled voxels, components dealt round-robin, all-gather of the packed skeletons.  Strong scaling.
+Default = c2 = BASELINE.json configs[1] (noble-elevator-58, 1 M-point tree, 1 cm voxels), the configuration the metric is
+quoted on.  metric = points/s (whole job).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -24,9 +28,24 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-WEIGHTS = os.path.join(ROOT, "smart-tree_b200", "model", "weights", "noble-elevator-58_model_weights.pt")
 METRIC = "points/sec through sparse-UNet+skeleton"
 UNIT = "points/s"
+
+# BASELINE.json configs[1..4] (SURVEY section 8d "Synthetic inputs")
+CONFIGS = {
+    "c2": dict(label="BASELINE.json configs[1]", weights="noble-elevator-58", points=1_000_000, voxel=0.01, block=4.0, buffer=0.4,
+               seed0=0, kind="tree"),
+    "c3": dict(label="BASELINE.json configs[2]", weights="noble-elevator-58", points=500_000, voxel=0.01, block=4.0, buffer=0.4,
+               seed0=0, kind="tree"),
+    "c4": dict(label="BASELINE.json configs[3]", weights="peach-forest-65", points=4_000_000, voxel=0.005, block=4.0, buffer=0.4,
+               seed0=1, kind="tree"),
+    "c5": dict(label="BASELINE.json configs[4]", weights="noble-elevator-58", points=500_000, voxel=0.01, block=0.64, buffer=0.4,
+               seed0=0, kind="plot", trees=40),
+}
+
+
+def weights_path(name):
+    return os.path.join(ROOT, "smart-tree_b200", "model", "weights", f"{name}_model_weights.pt")
 
 
 def parse():
@@ -35,20 +54,45 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--points", type=int, default=1_000_000)
-    ap.add_argument("--voxel", type=float, default=0.01)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--points", type=int, default=None, help="points per tree (default: the config's)")
+    ap.add_argument("--voxel", type=float, default=None)
+    ap.add_argument("--plot-trees", type=int, default=None, help="c5: trees in the plot (default 40 = 20 M points)")
     ap.add_argument("--cpu-sample-points", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="reference arm: wall-clock budget for the timed passes")
+    ap.add_argument("--gather-capacity", type=int, default=1 << 20, help="int32 words per rank of the packed-skeleton all-gather")
     ap.add_argument("--conv-impl", default=os.environ.get("ST_CONV_IMPL", "auto"))
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.points is not None:
+        cfg["points"] = args.points
+    if args.voxel is not None:
+        cfg["voxel"] = args.voxel
+    if args.plot_trees is not None and cfg["kind"] == "plot":
+        cfg["trees"] = args.plot_trees
+    args.cfg = cfg
+    return args
 
 
-def workload_config(args, world):
-    return {"workload": "noble-elevator-58 UNet inference + skeleton, 1M-point synthetic tube tree per GPU, 1cm voxels "
-                        "(BASELINE.json configs[1])",
-            "points_per_gpu": args.points, "voxel_size": args.voxel, "block_size": 4, "buffer_size": 0.4, "K": 16,
-            "weights": "noble-elevator-58", "trees": world, "tree_seed": 0, "parallelism": f"tree-sharded x{world}, NCCL all-gather of packed skeletons",
-            "l2": "256 MiB scratch write between timed iterations (inputs < 126 MB L2)"}
+def workload_config(args, world, points_override=None):
+    c = args.cfg
+    pts = c["points"] if points_override is None else points_override
+    if c["kind"] == "plot":
+        what = (f"{c['weights']} UNet inference + skeleton, forest plot of {c['trees']} synthetic tube trees x {pts} points "
+                f"({c['trees'] * pts} points), {c['voxel']} m voxels, {c['block']} m blocks ({c['label']})")
+        par = f"blocks and components dealt round-robin over {world} rank(s); NCCL all-gather of labelled voxels and of packed skeletons"
+        seeds = f"{c['seed0']}..{c['seed0'] + c['trees'] - 1}"
+        total = c["trees"] * pts
+    else:
+        what = (f"{c['weights']} UNet inference + skeleton, one {pts}-point synthetic tube tree per GPU, {c['voxel']} m voxels "
+                f"({c['label']})")
+        par = f"tree-sharded x{world} (rank r: seed {c['seed0']}+r), one NCCL all-gather of packed skeletons"
+        seeds = f"{c['seed0']}..{c['seed0'] + world - 1}"
+        total = pts * world
+    return {"workload": what, "config": args.config, "points_per_tree": pts, "total_points": total, "voxel_size": c["voxel"],
+            "block_size": c["block"], "buffer_size": c["buffer"], "K": 16, "weights": c["weights"], "tree_seeds": seeds,
+            "parallelism": par, "l2": "256 MiB scratch write between timed iterations (inputs < 126 MB L2)"}
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -97,64 +141,113 @@ class ClockSampler:
                 "samples": len(self.rows)}
 
 
-# ------------------------------------------------------------------------------------ reference arm (CPU oracle)
-def cpu_oracle_points_per_s(n_points, voxel, steps=1, warmup=0):
-    """Times the oracle port of Pipeline.process_cloud (numpy/scipy/torch-CPU, all host threads the
-    libraries use) on a bounded sample of the workload: a synthetic tree of `n_points`."""
+# ------------------------------------------------------------------------------------ reference arm (CPU oracle port)
+def cpu_oracle_pass(cfg, n_points, n_trees=1):
+    """One pass of the oracle port of the path (numpy / scipy / torch-CPU with all host threads the libraries use) over a
+    synthetic cloud of the configuration.  Returns (seconds, stage seconds, points processed)."""
     import numpy as np
     import torch
 
     from oracle import pipeline_ref as P
     from oracle import unet_ref as U
     from smart_tree_b200 import synth
-    sd = torch.load(WEIGHTS, map_location="cpu", weights_only=True)
+    sd = torch.load(weights_path(cfg["weights"]), map_location="cpu", weights_only=True)
     params = U.to_numpy_params(sd)
-    tr = synth.make_tree(0, n_points)
-    stages = {}
-
-    def one():
-        t0 = time.perf_counter()
-        lab = P.infer(params, P.centre_cloud(tr.xyz), tr.rgb, voxel, 4, 0.4)
-        t1 = time.perf_counter()
-        P.process_cloud(None, None, None, labelled=lab)
-        t2 = time.perf_counter()
-        stages["unet_s"], stages["skeleton_s"] = t1 - t0, t2 - t1
-        return t2 - t0
-
-    for _ in range(warmup):
-        one()
-    times = [one() for _ in range(max(steps, 1))]
-    return n_points / (sum(times) / len(times)), sum(times) / len(times), stages
+    if cfg["kind"] == "plot":
+        tr = synth.make_forest(range(cfg["seed0"], cfg["seed0"] + n_trees), n_points, pitch=5.0, cols=8)
+    else:
+        tr = synth.make_tree(cfg["seed0"], n_points)
+    t0 = time.perf_counter()
+    lab = P.infer(params, P.centre_cloud(tr.xyz), tr.rgb, cfg["voxel"], cfg["block"], cfg["buffer"])
+    t1 = time.perf_counter()
+    P.process_cloud(None, None, None, labelled=lab)
+    t2 = time.perf_counter()
+    return t2 - t0, {"unet_s": t1 - t0, "skeleton_s": t2 - t1}, int(tr.xyz.shape[0])
 
 
 def run_reference(args):
+    """The reference's own CPU path cannot run here (spconv / FRNN / cugraph absent, skeleton code CUDA-only: DESIGN.md
+    section 8), so this arm times the oracle port on the host cores -- at the DECLARED size for the default configuration
+    (every step is one full pass; the number of timed passes is capped by --ref-budget-s and reported), on a bounded
+    sample for the configurations whose full size would take the CPU far longer than a few minutes (stated in `config`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = args.cfg
     cores = os.cpu_count()
-    v, sec, stages = cpu_oracle_points_per_s(args.cpu_sample_points, args.voxel, args.steps, min(args.warmup, 1))
-    sample = f"synthetic tube tree seed 0, {args.cpu_sample_points} points, {args.voxel} m voxels (same pipeline, bounded sample)"
+    n_trees = 1
+    points = cfg["points"]
+    bounded = None
+    if cfg["kind"] == "plot":
+        n_trees, points = 1, min(points, 200_000)
+        bounded = f"one tree of {points} points instead of {cfg['trees']} x {cfg['points']} (0.64 m blocks overlap 11-fold: the full plot takes the CPU hours)"
+    elif points > 1_000_000:
+        bounded = f"{1_000_000} points instead of {points}"
+        points = 1_000_000
+    if args.warmup > 0:
+        cpu_oracle_pass(cfg, min(points, 100_000), n_trees)          # warm-up: thread pools, page cache, BLAS kernels
+    times, stages, npts = [], {}, points
+    t_begin = time.perf_counter()
+    while len(times) < max(args.steps, 1):
+        sec, stages, npts = cpu_oracle_pass(cfg, points, n_trees)
+        times.append(sec)
+        if time.perf_counter() - t_begin + sec > args.ref_budget_s:
+            break
+    sec = sum(times) / len(times)
+    v = npts / sec
+    sample = (f"oracle port (numpy/scipy/torch-CPU), {npts} points, {cfg['voxel']} m voxels, {len(times)} full pass(es) of "
+              f"{[round(t, 1) for t in times]} s (requested {args.steps} steps; capped by a {args.ref_budget_s:.0f} s budget)")
+    conf = workload_config(args, 1, points_override=points)
+    if bounded:
+        conf["bounded_sample"] = bounded
+    if cfg["kind"] == "plot":
+        conf["total_points"] = npts
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+            "steps_timed": len(times), "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak" if cfg["kind"] == "tree" else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": conf,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, **stages},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "note": "numpy port of the path written for this repository, not the upstream code: a reported baseline, not a like-for-like ratio; "
+                    "the north star's spconv baseline cannot be measured here (spconv is not installable)"}
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------ B200 arm
+def count_launches(fn):
+    """Kernels launched by one call of fn, measured with the CUPTI-backed torch profiler: (libst_b200 kernels, all kernels).
+    libst_b200 kernels are the ones named k_* (its CUB sorts / scans are counted as library kernels)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    ours = total = 0
+    names = {}
+    for ev in prof.events():
+        if ev.device_type != torch.autograd.DeviceType.CUDA or "mem" in ev.name.lower()[:6]:
+            continue
+        total += 1
+        if re.search(r"(^|[\s:])k_[a-z0-9_]+", ev.name):
+            ours += 1
+            key = re.search(r"k_[a-z0-9_]+", ev.name).group(0)
+            names[key] = names.get(key, 0) + 1
+    return ours, total, names
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from smart_tree_b200 import _lib, ops, synth
+    from smart_tree_b200 import _lib, _timing, ops, synth
     from smart_tree_b200 import dist as stdist
     from smart_tree_b200.data_types.cloud import Cloud
     from smart_tree_b200.dataset.augmentations import AugmentationPipeline, CentreCloud
     from smart_tree_b200.model.model_inference import ModelInference
     from smart_tree_b200.pipeline import Pipeline
     from smart_tree_b200.skeleton.skeletonize import Skeletonizer
+    from smart_tree_b200.util.digest import skeleton_digest
 
     rank, world, local = stdist.init_from_env()
     if not torch.cuda.is_available():
@@ -162,15 +255,21 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     _lib.check(_lib.load().st_device_check(local), "st_device_check")
+    cfg = args.cfg
+    plot = cfg["kind"] == "plot"
 
-    mi = ModelInference(None, WEIGHTS, args.voxel, 4, 0.4, device=dev)
+    mi = ModelInference(None, weights_path(cfg["weights"]), cfg["voxel"], cfg["block"], cfg["buffer"], device=dev)
     if args.conv_impl != "auto":
         mi.model.conv_impl = args.conv_impl
     pipe = Pipeline(AugmentationPipeline([CentreCloud()]), mi, Skeletonizer(16, 0.02, 32, device=dev), repair_skeletons=True,
                     smooth_skeletons=True, smooth_kernel_size=11, prune_skeletons=True, min_skeleton_radius=0.01,
                     min_skeleton_length=0.02, device=dev)
-    # weak scaling: every GPU gets the SAME workload tree (seed 0), so per-GPU work is exactly fixed as N grows
-    tr = synth.make_tree(0, args.points)
+    if plot:      # every rank holds the whole plot (strong scaling)
+        tr = synth.make_forest(range(cfg["seed0"], cfg["seed0"] + cfg["trees"]), cfg["points"], pitch=5.0, cols=8)
+        total_points = int(tr.xyz.shape[0])
+    else:         # weak scaling: one tree per rank, seeds seed0 .. seed0 + world - 1
+        tr = synth.make_tree(cfg["seed0"] + rank, cfg["points"])
+        total_points = cfg["points"] * world
     h_xyz = torch.from_numpy(tr.xyz).pin_memory()
     h_rgb = torch.from_numpy(tr.rgb).pin_memory()
     d_cloud = Cloud(xyz=h_xyz.to(dev), rgb=h_rgb.to(dev))
@@ -187,10 +286,16 @@ def run_b200(args):
             cloud = d_cloud
         else:
             cloud = Cloud(xyz=h_xyz.to(dev, non_blocking=True), rgb=h_rgb.to(dev, non_blocking=True))
-        sk = pipe.process_cloud(cloud=cloud)
+        if plot:
+            sk = pipe.process_plot_sharded(cloud, rank, world)
+        else:
+            sk = pipe.process_cloud(cloud=cloud)
+        g = None
         if world > 1:
-            return stdist.gather_skeletons([sk], [rank], device=dev), sk
-        return None, sk
+            g = stdist.gather_packed(sk, unit=rank, capacity=args.gather_capacity, device=dev)
+            if not resident:
+                g.to_host()               # end to end: every rank's packed skeletons land in host memory
+        return g, sk
 
     def timed(resident: bool, steps: int):
         barrier()
@@ -200,17 +305,16 @@ def run_b200(args):
         per_step = []
         for _ in range(steps):
             ts = time.perf_counter()
-            _, sk = step(resident)
-            per_step.append((time.perf_counter() - ts) * 1e3)     # the step ends with its result on the host
+            g, sk = step(resident)
+            per_step.append((time.perf_counter() - ts) * 1e3)     # the step ends with its (packed) result on the host
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
-        ms = max(ms, 0.0)
         t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), sk, per_step
+        return float(t[0]), float(t[1]), sk, g, per_step
 
     # the sampler starts BEFORE the warm-up: nvidia-smi's start-up (NVML initialisation) stalled one timed step in five
     # by ~10 ms when it was launched right at the start of the timed region; only samples taken after mark() count
@@ -222,27 +326,67 @@ def run_b200(args):
     import gc
     gc.collect()
     clocks.mark()
-    launches0 = ops.LAUNCHES
-    dev_ms, wall_ms, sk, steps_res = timed(True, args.steps)
-    launches = ops.LAUNCHES - launches0
+    dev_ms, wall_ms, sk, g, steps_res = timed(True, args.steps)
     stage_t = dict(pipe.timings)
     for _ in range(min(args.warmup, 2)):          # the host-buffer path warms up too (fresh device buffers every step)
         step(False)
-    e2e_ms, e2e_wall_ms, sk2, steps_e2e = timed(False, args.steps)
+    e2e_ms, e2e_wall_ms, sk2, g2, steps_e2e = timed(False, args.steps)
     clk = clocks.stop() if rank == 0 else None
     # the device timeline includes host gaps (the step has host sync points), so device-event time == step time
     ms_per_step = max(dev_ms, wall_ms) / args.steps
-    total_points = args.points * world
     value = total_points / (ms_per_step / 1e3)
     e2e_value = total_points / (max(e2e_ms, e2e_wall_ms) / args.steps / 1e3)
-    d2h = sum(b.xyz.numel() * 4 + b.radii.numel() * 4 + 16 for s in sk2.skeletons for b in s.branches.values())
+    packed = sk2.skeletons
+    d2h = int(packed.payload.nbytes + 16 + 4 * len(packed.cnb_h)) if getattr(packed, "payload", None) is not None else 0
+    if g2 is not None:
+        d2h += int(g2.buf.numel() * 4)
+
+    # ---- kernels launched by one step, measured (CUPTI); the lookup table of ops.py only as a fallback
+    launches_src = "torch.profiler (CUPTI), one step outside the timed region"
+    try:
+        if world > 1:
+            raise RuntimeError("profiled on single-GPU runs only")
+        ours, total_k, by_name = count_launches(lambda: step(True))
+    except Exception as exc:
+        l0 = ops.LAUNCHES
+        step(True)
+        ours, total_k, by_name = ops.LAUNCHES - l0, None, {}
+        launches_src = f"per-call table in smart_tree_b200/ops.py ({type(exc).__name__}: {exc})"
+    launches = ours * args.steps
+
+    # ---- skeleton kernels: one instrumented step (synchronising stage timers) -> SURVEY 8(d) algorithmic bytes / time
+    skel_roof = None
+    try:
+        _timing.enable(True)
+        for _ in range(3):
+            step(True)
+        torch.cuda.synchronize(dev)
+        sec = {k: float(np.median(v)) for k, v in _timing.SAMPLES.items()}
+        _timing.enable(False)
+        last = pipe.skeletonizer.last
+        n_v = int(last["order"].shape[0])
+        n_e = int(last["edges"].shape[0])
+        iters = int(last["comp_n_branches"].sum().item())
+        peaks_ = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        pk = float(peaks_.get("hbm_gbs", 6650.0))
+        sssp_b = 12.0 * 2 * n_e              # one sweep over every arc (both directions): col + weight + neighbour distance
+        st_b = 4.0 * n_v * max(iters, 1)     # the reference's argmax scan: n * 4 B per emitted branch
+        skel_roof = {"vertices": n_v, "edges": n_e, "branches": iters, "stage_ms": {k: round(v, 3) for k, v in sec.items() if k.startswith("skel.") or k.startswith("infer.")},
+                     "k_sssp": {"algorithmic_bytes": sssp_b, "ms": sec.get("skel.sssp"), "achieved_gbs": sssp_b / sec["skel.sssp"] / 1e6,
+                                "frac": sssp_b / sec["skel.sssp"] / 1e6 / pk, "note": ">= E*12 B per sweep, one sweep counted; latency-bound (tree depth in hops)"},
+                     "k_sample_tree": {"algorithmic_bytes": st_b, "ms": sec.get("skel.sample_tree"), "achieved_gbs": st_b / sec["skel.sample_tree"] / 1e6,
+                                       "frac": st_b / sec["skel.sample_tree"] / 1e6 / pk,
+                                       "note": ">= n*4 B per branch (the reference's argmax scan, replaced here by a sorted cursor); latency-bound"}}
+    except Exception as exc:
+        _timing.enable(False)
+        skel_roof = {"error": repr(exc)}
 
     # ---- roofline of the dominant kernel family (3x3x3 gather conv): one instrumented, warm forward
     bb = mi.last_batch
     roof = None
     if bb is not None and bb.feats.shape[0]:
         levels = mi.model.build_levels(bb.coords)
-        feats = bb.feats[:, :3].contiguous()
+        feats = bb.feats[:, :3]
         for _ in range(2):
             mi.model.forward(feats, bb.coords, levels=levels)
         per = {}
@@ -278,35 +422,53 @@ def run_b200(args):
         try:          # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture (profiles/README.md)
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if top in tj:
-                traffic, traffic_src = tj[top]["dram_bytes_per_launch"], "profiles/ncu_conv_r1c.csv (dram__bytes_read.sum + dram__bytes_write.sum)"
+                traffic, traffic_src = tj[top]["dram_bytes_per_launch"], tj[top].get("source", "profiles/ (dram__bytes_read.sum + dram__bytes_write.sum)")
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": top, "achieved": table[top]["gbps"], "peak": peak, "unit": "GB/s",
                 "frac": table[top]["gbps"] / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_kind,
                 "all_gather_convs": {"achieved": tot_b / tot_ms / 1e6, "frac": tot_b / tot_ms / 1e6 / peak, "ms_per_forward": tot_ms},
-                "per_kernel": table, "level_voxels": [lv.n for lv in levels]}
+                "per_kernel": table, "level_voxels": [lv.n for lv in levels], "skeleton_kernels": skel_roof}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            v, sec, stages = cpu_oracle_points_per_s(args.cpu_sample_points, args.voxel)
-            cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
-                   "sample": f"synthetic tube tree seed 0, {args.cpu_sample_points} points, {args.voxel} m voxels, 1 pass ({sec:.1f} s)",
-                   **stages}
+        try:      # best of 3 after one warm-up, on a bounded sample of the workload
+            n_s = min(args.cpu_sample_points, cfg["points"])
+            cpu_oracle_pass(cfg, n_s)
+            runs = [cpu_oracle_pass(cfg, n_s) for _ in range(3)]
+            sec, stages, npts = min(runs, key=lambda r: r[0])
+            cpu = {"value": npts / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"oracle port on a bounded sample: synthetic tube tree seed {cfg['seed0']}, {npts} points, {cfg['voxel']} m voxels; "
+                             f"best of 3 passes after 1 warm-up ({[round(r[0], 2) for r in runs]} s)", **stages}
         except Exception as exc:  # the oracle is only a reported baseline
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc}"}
 
     if rank == 0:
+        digest = skeleton_digest(sk.skeletons)
+        verified = None
+        try:
+            gold = json.load(open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")))
+            key = f"{args.config}:{cfg['points']}:{cfg['voxel']}" + (f":{cfg['trees']}" if plot else "")
+            if key in gold and world == 1:
+                verified = gold[key]["topology"] == digest["topology"]
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args, world),
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if plot else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h_xyz.numel() * 4 + h_rgb.numel() * 4),
                         "d2h_bytes_per_step": int(d2h)},
-                "gpu_launches": int(launches), "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "gpu_launches": int(launches), "gpu_launches_per_step": int(ours), "all_kernels_per_step": total_k,
+                "gpu_launches_source": launches_src, "kernels_per_step": by_name,
+                "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
                 "stages_ms": {k: v * 1e3 for k, v in stage_t.items()},
                 "step_ms": {"resident": [round(v, 2) for v in steps_res], "host_buffers": [round(v, 2) for v in steps_e2e]},
-                "result": {"skeletons": len(sk.skeletons), "branches": sum(len(s.branches) for s in sk.skeletons),
-                           "voxels": int(bb.feats.shape[0]) if bb is not None else 0}}
+                "result": {"skeletons": len(sk.skeletons), "branches": digest["branches"], "nodes": digest["nodes"],
+                           "voxels": int(bb.feats.shape[0]) if bb is not None else 0, "digest": digest,
+                           "digest_matches_oracle_verified_golden": verified,
+                           "digest_note": "tests/test_gpu_fullsize.py verifies this configuration against the oracle and records the digest "
+                                          "(tests/golden/bench_digests.json); null = no golden for this size"},
+                "spconv_baseline": "unmeasurable here (spconv is not installable in this image): the >= 10x spconv target of the north star is not evaluated"}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

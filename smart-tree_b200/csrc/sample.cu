@@ -6,6 +6,8 @@
 //   * points near the path are claimed through the uniform grid: one warp per path vertex scans the
 //     cell rows within r = max path radius and races a 64-bit atomicMin of (d2 bits, path position)
 //     per point -> nearest path vertex, ties to the lowest position, exactly the FRNN K=1 result
+#include <string.h>
+
 #include "grid.cuh"
 
 using namespace st;
@@ -822,6 +824,499 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
     cluster_sync_all();
 }
 
+
+// ------------------------------------------------------------------------------------ speculative rounds, cluster-cooperative
+// Second design of the speculative scheme (k_sample_tree_b above ran one member per CTA: counters on the bench tree showed
+// (i) three of four candidates taken in sorted order are claimed by the member just before them -- the vertices next to
+// a branch tip all have nearly the tip's distance -- and (ii) the claim of a 40-vertex route on ONE CTA costs more than
+// the whole sequential iteration on sixteen).  Here
+//   * a round looks at a WINDOW of up to 256 live entries of the sorted list and picks up to 16 members that are
+//     mutually far apart (a heuristic: it only decides how much of the round survives, never the result);
+//   * every CTA knows every member's route; the claim tasks of all members are laid end to end and spread over all
+//     CTAs of the cluster, survivors go to ONE shared list tagged with their member;
+//   * every CTA then derives the verdicts itself from the stamps (no exchange): member g stands iff no earlier member
+//     touched its start vertex, route or parent vertex; a window entry that was passed over must have been claimed by an
+//     ACCEPTED member before it in the list -- otherwise the sequential loop would have picked it, and the round ends
+//     right before it;
+//   * accepted members commit together (labels through atomicMax: branch ids grow with the member index).
+// Two cluster barriers per round.  Routes of 64 or more vertices run as one whole-cluster iteration of k_sample_tree.
+constexpr int MB = 16;         // members per round
+constexpr int MP = 64;         // route slots per member
+constexpr int WIN = 256;       // live entries examined per round
+constexpr int SCAN_CHUNKS = 4; // order-list positions examined per round = 1024 * SCAN_CHUNKS
+
+struct RoundSmem {
+    float4 path[MB * MP];      // xyz + radius of member g's route vertex h at [g * MP + h]  (the long-route path reuses it as [1024])
+    int2 queue[32][QUEUE_LEN];
+    int off[1024], beg[1024], jj[1024];
+    int pv[MB * MP];           // vertex ids (component-local) of the routes
+    int win_pos[WIN + 1];      // positions (in the sorted list) of the window's live entries (+ the first one beyond it)
+    int win_gap[WIN];          // >= 0: member index of a selected entry;  < 0: -(g + 1), passed over after member g
+    float4 selpt[MB];          // start vertex of each member: xyz + radius
+    int sel[MB], len[MB], term[MB], rbits[MB], parent[MB], mf[MB], mp[MB], status[MB], bid[MB], pcur[MB], toff[MB + 1], R[MB];
+    int gapneed[MB], gapbad[MB];
+    int scan[32];
+    int first[MB];
+    int nsel, nwin, stop_entry, newbid, newpcur, minpos_dummy, first_long, term_long, rbits_long;
+};
+
+__device__ __forceinline__ int stamp_who(int sv, int epoch) { return (sv >> 4) == epoch ? 15 - (sv & 15) : 16; }
+
+__global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
+                                                           int32_t *clist_all, int32_t *ccnt_all) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RoundSmem &S = *reinterpret_cast<RoundSmem *>(smem_raw);
+    const unsigned CL = cluster_size(), cr = cluster_rank();
+    const int c = blockIdx.x / CL;
+    const int base = a.comp_off[c];
+    const int nc = a.comp_off[c + 1] - base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gwarp = cr * 32 + warp, nwarp = CL * 32;
+    const int gtid = cr * 1024 + tid, nthr = CL * 1024;
+    int32_t *const clist = clist_all + (size_t)16 * base;      // claimed (member << 28 | local vertex), capacity 16 * nc
+    int32_t *const ccnt = ccnt_all + 2 * c;                     // two counters, alternating by round parity
+    int cursor = 0, bid = 0, pcur = 0, iter = 0, epoch = 1;
+    unsigned long long dbg[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) dbg[i] = 0;
+    long long t_mark = clock64();
+    while (true) {
+        ++dbg[0];
+        // ---- A. window: the live entries among the next 4096 positions of the (distance desc, index asc) list
+        int live[SCAN_CHUNKS];
+#pragma unroll
+        for (int k = 0; k < SCAN_CHUNKS; ++k) {
+            const int pos = cursor + k * 1024 + tid;
+            live[k] = pos < nc ? (__ldcg(a.distw + __ldg(a.order + base + pos)) > 0.f ? 1 : 0) : 0;
+        }
+        int nlive = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_CHUNKS; ++k) {
+            int total;
+            const int rank = block_excl_scan_1024(live[k], S.scan, total);
+            if (live[k] && nlive + rank <= WIN) S.win_pos[nlive + rank] = cursor + k * 1024 + tid;
+            nlive += total;
+            __syncthreads();
+        }
+        const int scan_end = min(cursor + SCAN_CHUNKS * 1024, nc);
+        if (nlive == 0) {
+            if (scan_end >= nc) break;
+            cursor = scan_end;
+            continue;
+        }
+        int nwin = min(nlive, WIN);
+        // position where the window ends: the first live entry beyond it, or the end of the scanned range
+        int win_end = nlive > WIN ? S.win_pos[WIN] : scan_end;
+        // ---- B. members: greedy in list order, an entry is taken iff it is far from every member taken so far (warp 0)
+        if (warp == 0) {
+            int nsel = 0;
+            for (int e0 = 0; e0 < nwin && nsel < MB; e0 += 32) {
+                const int e = e0 + lane;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                bool far = false;
+                if (e < nwin) {
+                    const int v = __ldg(a.order + base + S.win_pos[e]);
+                    p = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
+                    far = true;
+                    for (int m = 0; m < nsel; ++m) {
+                        const float4 q = S.selpt[m];
+                        const float rho = 2.f * fmaxf(p.w, q.w);
+                        if (dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < rho * rho) far = false;
+                    }
+                }
+                int gap = nsel - 1;                       // member index the passed-over entries of this chunk come after
+                unsigned todo = __ballot_sync(0xffffffffu, far);
+                int mine = -1;                            // member index if this lane's entry gets selected
+                int my_gap = gap;
+                while (todo && nsel < MB) {
+                    const int l = __ffs(todo) - 1;
+                    todo &= ~(1u << l);
+                    const float4 q = make_float4(__shfl_sync(0xffffffffu, p.x, l), __shfl_sync(0xffffffffu, p.y, l),
+                                                 __shfl_sync(0xffffffffu, p.z, l), __shfl_sync(0xffffffffu, p.w, l));
+                    if (lane == l) { mine = nsel; S.selpt[nsel] = p; S.sel[nsel] = e; }
+                    // lanes after l that were still candidates re-test against the new member; lanes after l come after it in the list
+                    if (lane > l) {
+                        my_gap = nsel;
+                        const float rho = 2.f * fmaxf(p.w, q.w);
+                        if (far && dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < rho * rho) far = false;
+                    }
+                    todo &= __ballot_sync(0xffffffffu, far);
+                    ++nsel;
+                }
+                // lanes whose entry lies beyond the MB-th member are outside the round (handled by truncating nwin below)
+                if (e < nwin) S.win_gap[e] = mine >= 0 ? mine : -(my_gap + 1);
+                __syncwarp();
+            }
+            if (lane == 0) S.nsel = nsel;
+        }
+        __syncthreads();
+        int nsel = S.nsel;
+        if (nsel == MB && S.sel[MB - 1] + 1 < nwin) {           // the round ends right after its last member
+            nwin = S.sel[MB - 1] + 1;
+            win_end = S.win_pos[nwin];
+        }
+        // ---- C. routes: thread (g, h) resolves ancestor h of member g (two octal digits = at most two dependent loads)
+        const int g = tid >> 6, h = tid & 63;
+        if (tid < MB) { S.first[tid] = 1024; S.rbits[tid] = 0; S.mf[tid] = 16; S.mp[tid] = 16; S.term[tid] = -1; S.gapneed[tid] = 0; S.gapbad[tid] = INT_MAX; }
+        __syncthreads();
+        int x = -1;
+        if (g < nsel) {
+            x = __ldg(a.order + base + S.win_pos[S.sel[g]]) - base;
+#pragma unroll
+            for (int L = 0; L < 2; ++L) {
+                const int d = (h >> (3 * L)) & 7;
+                if (d && x >= 0) x = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + x);
+            }
+            const bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
+            if (stop) atomicMin(&S.first[g], h);
+        }
+        __syncthreads();
+        if (S.first[0] == 1024) {
+            // =========================== long route: one iteration of k_sample_tree on candidate 0, whole cluster
+            const int f = __ldg(a.order + base + S.win_pos[0]) - base;
+            int len = 0, cur = f, term = -1;
+            float rl = 0.f;
+            int *out = a.path_out + base + pcur;
+            if (tid == 0) { S.rbits_long = 0; S.term_long = -1; }
+            __syncthreads();
+            while (true) {
+                if (tid == 0) S.first_long = 1024;
+                __syncthreads();
+                int y = cur;
+#pragma unroll
+                for (int L = 0; L < JUMP_L; ++L) {
+                    const int d = (tid >> (3 * L)) & 7;
+                    if (d && y >= 0) y = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + y);
+                }
+                const bool stop = y < 0 || __ldcg(a.alloc + base + y) != 0;
+                if (stop) atomicMin(&S.first_long, tid);
+                __syncthreads();
+                const int first = S.first_long;
+                if (tid == first) S.term_long = y;
+                const int cnt = min(first, max(nc - pcur - len, 0));
+                if (tid < cnt) {
+                    out[len + tid] = y;
+                    const int v = base + y;
+                    const float rv = a.radii[v];
+                    if (len + tid < PATH_SMEM) S.path[len + tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                    rl = fmaxf(rl, rv);
+                }
+                __syncthreads();
+                len += cnt;
+                if (first < 1024) { term = S.term_long; break; }
+                if (cnt < 1024) { term = -1; break; }
+                cur = __ldg(jump + (size_t)(7 * 3 + 1) * n_total + base + cur);
+                __syncthreads();
+            }
+            const int parent = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));
+            const int *path = out;
+            for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));
+            if (lane == 0 && rl > 0.f) atomicMax(&S.rbits_long, __float_as_int(rl));
+            __syncthreads();
+            const float r = __int_as_float(S.rbits_long);
+            const float r2 = __fmul_rn(r, r);
+            const bool emit = len >= 2;
+            int32_t *const cnt_cur = a.touch_cnt + 2 * c + (iter & 1);
+            if (cr == 0 && tid == 0) a.touch_cnt[2 * c + ((iter + 1) & 1)] = 0;
+            const int R = (int)ceilf(r * 1.0001f * a.g.inv_h) + 1;
+            const int R2 = (2 * R + 1) * (2 * R + 1);
+            const long long ntask = (long long)len * R2;
+            const int nflat = (int)min((long long)min(len, PATH_SMEM) * R2, (long long)INT_MAX);
+            if (len <= SCAN_PATH) {
+                if (r > 0.f)
+                    claim_flat<1>(a, base, nc, S.path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, S.queue[warp], S.off, S.beg, S.jj, S.scan, cr, CL);
+            } else {
+                if (r > 0.f) {
+                    claim_flat<0>(a, base, nc, S.path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, S.off, S.beg, S.jj, S.scan, cr, CL);
+                    for (long long t = (long long)nflat + gwarp; t < ntask; t += nwarp) {
+                        const int jj = (int)(t / R2);
+                        const int v = base + path[jj];
+                        claim_task(a, base, nc, a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], (unsigned)(len - 1 - jj),
+                                   (int)(t % R2), R, r, r2, lane, cnt_cur);
+                    }
+                }
+                cluster_sync_all();
+                const int ntouch = __ldcg(cnt_cur);
+                for (int k = gtid; k < ntouch; k += nthr) {
+                    const int gi = __ldcg(a.touched + base + k);
+                    const unsigned long long bkey = __ldcg(a.best + gi);
+                    const int jj = len - 1 - (int)(unsigned)(bkey & 0xFFFFFFFFull);
+                    const float d2 = __uint_as_float((unsigned)(bkey >> 32));
+                    const float vr = jj < PATH_SMEM ? S.path[jj].w : a.radii[base + path[jj]];
+                    if (sqrtf(d2) < vr) {
+                        a.distw[gi] = -1.f;
+                        a.alloc[gi] = 1;
+                        if (emit) a.branch_id[gi] = bid;
+                    }
+                    __stcg(a.best + gi, BEST_NONE);
+                }
+            }
+            for (int jj = gtid; jj < len; jj += nthr) {
+                const int v = base + path[jj];
+                a.distw[v] = -1.f;
+                a.alloc[v] = 1;
+                if (emit) a.branch_id[v] = bid;
+            }
+            cluster_sync_all();
+            if (emit) {
+                if (cr == 0) {
+                    for (int jj = tid; jj < len / 2; jj += blockDim.x) {
+                        const int t = out[jj];
+                        out[jj] = out[len - 1 - jj];
+                        out[len - 1 - jj] = t;
+                    }
+                    if (tid == 0) {
+                        a.branch_len[base + bid] = len;
+                        a.branch_parent[base + bid] = parent;
+                    }
+                }
+                ++bid;
+                pcur += len;
+            }
+            ++iter;
+            cursor = S.win_pos[0] + 1;
+            ++dbg[1];
+            { const long long t = clock64(); dbg[11] += (unsigned long long)(t - t_mark); t_mark = t; }
+            __syncthreads();
+            continue;
+        }
+        // =========================== round: a long member ends the round before it
+        for (int m = 1; m < nsel; ++m)
+            if (S.first[m] == 1024) { nsel = m; nwin = S.sel[m]; win_end = S.win_pos[nwin]; ++dbg[6]; break; }
+        const int epoch_tag = epoch * 16;
+        float rl = 0.f;
+        if (g < nsel) {
+            const int len = S.first[g];
+            if (h < len) {
+                S.pv[g * MP + h] = x;
+                const int v = base + x;
+                const float rv = a.radii[v];
+                S.path[g * MP + h] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                rl = rv;
+                if ((unsigned)(g % (int)CL) == cr) atomicMax(stamp + v, epoch_tag + 15 - g);      // the route stamps its own vertices
+            } else if (h == len) {
+                S.term[g] = x;
+            }
+            if (h == 0) S.len[g] = len;
+        }
+        for (int o = 16; o; o >>= 1) rl = fmaxf(rl, __shfl_xor_sync(0xffffffffu, rl, o));       // a warp lies inside one member's 64 threads
+        if (lane == 0 && rl > 0.f && g < nsel) atomicMax(&S.rbits[g], __float_as_int(rl));
+        __syncthreads();
+        if (tid < nsel) {
+            const int term = S.term[tid];
+            S.parent[tid] = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));      // state before this round (nobody has committed yet)
+        }
+        if (tid == 0) {
+            int t = 0;
+            for (int m = 0; m < nsel; ++m) {
+                const float r = __int_as_float(S.rbits[m]);
+                const int R = r > 0.f ? (int)ceilf(r * 1.0001f * a.g.inv_h) + 1 : 0;
+                S.R[m] = R;
+                S.toff[m] = t;
+                t += r > 0.f ? S.len[m] * (2 * R + 1) * (2 * R + 1) : 0;
+            }
+            S.toff[nsel] = t;
+            if (cr == 0) ccnt[(epoch + 1) & 1] = 0;      // next round's list counter (idle since the previous round's last barrier)
+        }
+        __syncthreads();
+        // ---- D. claim, all members at once, tasks interleaved over the CTAs of the cluster
+        int32_t *const cnt_cur = ccnt + (epoch & 1);
+        {
+            const int T = S.toff[nsel];
+            int qn = 0;
+            int2 *queue = S.queue[warp];
+            const float4 none = make_float4(0.f, 0.f, 0.f, __int_as_float(-1));
+            auto drain = [&](int first, int count) {
+                bool hit = false;
+                int word = 0, gi = -1, m = 0;
+                if (lane < count) {
+                    const int2 e = queue[first + lane];
+                    m = e.y >> 6;
+                    const int j = e.y & 63, len = S.len[m];
+                    const float4 q = __ldg(a.sorted + e.x);
+                    const float4 p = S.path[e.y];
+                    const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
+                    bool own = true;
+                    for (int j2 = 0; j2 < len; ++j2) own = own && !(claim_key(q, S.path[m * MP + j2], (unsigned)(len - 1 - j2)) < key);
+                    hit = own && sqrtf(d2) < p.w;
+                    gi = __float_as_int(q.w);
+                    word = (m << 28) | (gi - base);
+                }
+                const unsigned mask = __ballot_sync(0xffffffffu, hit);
+                if (!mask) return;
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(cnt_cur, __popc(mask));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (hit) {
+                    clist[pos + __popc(mask & ((1u << lane) - 1u))] = word;
+                    atomicMax(stamp + gi, epoch_tag + 15 - m);
+                }
+            };
+            for (int tb = 0; (long long)tb * CL < T; tb += 1024) {
+                const long long t = (long long)(tb + tid) * CL + cr;
+                int beg = 0, end = 0, slot = 0;
+                if (t < T) {
+                    int m = 0;
+                    while (m + 1 < nsel && S.toff[m + 1] <= t) ++m;
+                    const int R = S.R[m], R2 = (2 * R + 1) * (2 * R + 1);
+                    const int local = (int)(t - S.toff[m]);
+                    const int jj = local / R2;
+                    slot = m * MP + jj;
+                    const float r = __int_as_float(S.rbits[m]);
+                    row_range(a, S.path[slot], local % R2, R, r * 1.0001f + 1e-7f, beg, end);
+                }
+                int total;
+                const int ex = block_excl_scan_1024(end > beg ? end - beg : 0, S.scan, total);
+                S.off[tid] = ex; S.beg[tid] = beg; S.jj[tid] = slot;
+                __syncthreads();
+                auto locate = [&](int e, int &tp, int &sl) -> float4 {
+                    if (e >= total) { tp = 0; sl = 0; return none; }
+                    int lo = 0, hi = 1023;
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if (S.off[mid] <= e) lo = mid; else hi = mid - 1;
+                    }
+                    tp = S.beg[lo] + (e - S.off[lo]);
+                    sl = S.jj[lo];
+                    return __ldg(a.sorted + tp);
+                };
+                int tpn, sln;
+                float4 qnext = locate(tid, tpn, sln);
+                for (int e0 = 0; e0 < total; e0 += 1024) {
+                    const float4 q = qnext;
+                    const int tp = tpn, sl = sln;
+                    qnext = locate(e0 + 1024 + tid, tpn, sln);
+                    const int gi = __float_as_int(q.w);
+                    bool cand = false;
+                    if (gi >= base && gi < base + nc) {
+                        const int m = sl >> 6, j = sl & 63, len = S.len[m];
+                        const float r = __int_as_float(S.rbits[m]);
+                        const float r2 = __fmul_rn(r, r);
+                        const float4 p = S.path[sl];
+                        const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
+                        if (d2 < r2) {
+                            const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
+                            cand = true;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int j2 = j + (k < 2 ? k - 2 : k - 1);
+                                if (j2 >= 0 && j2 < len && claim_key(q, S.path[m * MP + j2], (unsigned)(len - 1 - j2)) < key) cand = false;
+                            }
+                        }
+                    }
+                    const unsigned mk = __ballot_sync(0xffffffffu, cand);
+                    if (cand) queue[qn + __popc(mk & ((1u << lane) - 1u))] = make_int2(tp, sl);
+                    qn += __popc(mk);
+                    __syncwarp();
+                    if (qn >= 32) {
+                        qn -= 32;
+                        drain(qn, 32);
+                        __syncwarp();
+                    }
+                }
+                __syncthreads();
+            }
+            __syncwarp();
+            drain(0, qn);
+        }
+        cluster_sync_all();                                  // 1: every claim and stamp of the round is in place
+        // ---- E. verdict inputs, every CTA for itself: who touched the members' vertices and the passed-over entries
+        if (g < nsel) {
+            const int len = S.len[g];
+            if (h <= len) {
+                const int term = S.term[g];
+                const int v = h < len ? S.pv[g * MP + h] : (term >= 0 ? term : nc - 1);
+                const int who = stamp_who(__ldcg(stamp + base + v), epoch);
+                if (h == 0) S.mf[g] = who; else atomicMin(&S.mp[g], who);
+            }
+        }
+        if (tid < nwin && S.win_gap[tid] < 0) {
+            const int after = -S.win_gap[tid] - 1;          // passed over after member `after`
+            const int v = __ldg(a.order + base + S.win_pos[tid]);
+            const int who = stamp_who(__ldcg(stamp + v), epoch);
+            if (who <= after) atomicOr(&S.gapneed[after], 1 << who);
+            else atomicMin(&S.gapbad[after], tid);           // nobody before it claimed it: the sequential loop would pick it
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int b = bid, p = pcur, stop_entry = nwin;
+            unsigned acc = 0;
+            int m = 0;
+            for (; m < nsel; ++m) {
+                const int mf = S.mf[m], mp = S.mp[m];
+                if (mf < m) {
+                    if (acc & (1u << mf)) S.status[m] = ST_SKIP;      // claimed by an accepted earlier member: never picked
+                    else { stop_entry = S.sel[m]; ++dbg[7]; break; }
+                } else if (mp < m) {
+                    stop_entry = S.sel[m]; ++dbg[8];
+                    break;
+                } else {
+                    S.status[m] = ST_ACCEPT;
+                    acc |= 1u << m;
+                    S.bid[m] = b;
+                    S.pcur[m] = p;
+                    if (S.len[m] >= 2) { ++b; p += S.len[m]; }
+                    ++dbg[4];
+                }
+                // the entries passed over after member m must all have been claimed by accepted members
+                if (S.gapbad[m] != INT_MAX || (S.gapneed[m] & ~acc)) {
+                    stop_entry = S.sel[m] + 1; ++dbg[9];
+                    ++m;
+                    break;
+                }
+            }
+            for (int k = m; k < MB; ++k) S.status[k] = ST_CUT;
+            S.stop_entry = stop_entry; S.newbid = b; S.newpcur = p;
+            ++dbg[2];
+            dbg[3] += nsel;
+            dbg[5] += nwin;
+        }
+        __syncthreads();
+        // ---- F. commit, whole cluster
+        {
+            const int ntouch = __ldcg(cnt_cur);
+            for (int k = gtid; k < ntouch; k += nthr) {
+                const int word = __ldcg(clist + k);
+                const int m = (word >> 28) & 15, v = base + (word & 0x0FFFFFFF);
+                if (S.status[m] == ST_ACCEPT) {
+                    a.distw[v] = -1.f;
+                    a.alloc[v] = 1;
+                    if (S.len[m] >= 2) atomicMax(a.branch_id + v, S.bid[m]);
+                }
+            }
+            if (g < nsel && S.status[g] == ST_ACCEPT && (unsigned)(g % (int)CL) == cr) {
+                const int len = S.len[g];
+                const bool emit = len >= 2;
+                if (h < len) {
+                    const int lv = S.pv[g * MP + h];
+                    const int v = base + lv;
+                    a.distw[v] = -1.f;
+                    a.alloc[v] = 1;
+                    if (emit) {
+                        atomicMax(a.branch_id + v, S.bid[g]);
+                        a.path_out[base + S.pcur[g] + (len - 1 - h)] = lv;      // root side first
+                    }
+                }
+                if (emit && h == 0) {
+                    a.branch_len[base + S.bid[g]] = len;
+                    a.branch_parent[base + S.bid[g]] = S.parent[g];
+                }
+            }
+        }
+        if (tid == 0) { const long long t = clock64(); dbg[10] += (unsigned long long)(t - t_mark); t_mark = t; }
+        const int stop_entry = S.stop_entry;
+        bid = S.newbid;
+        pcur = S.newpcur;
+        cursor = stop_entry < nwin ? S.win_pos[stop_entry] : win_end;
+        ++epoch;
+        cluster_sync_all();                                  // 2: commits visible before the next round reads the state
+    }
+    if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
+    if (tid == 0 && cr == 0 && c == 0) { dbg[15] = CL; for (int i = 0; i < 16; ++i) g_stb_stats[i] = dbg[i]; }
+    cluster_sync_all();
+}
+
 static size_t sort_bytes(int64_t n) {
     size_t b = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, b, (unsigned long long *)nullptr, (unsigned long long *)nullptr, (int32_t *)nullptr,
@@ -861,8 +1356,15 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     size_t sb = sort_bytes(n);
     void *sort_ws = cv.take<char>(sb);
     if (!cv.ok()) { set_error("st_sample_tree: workspace too small"); return ST_ERR_WORKSPACE; }
-    const bool batched = !getenv("ST_SAMPLE_SEQUENTIAL");      // speculative batches (k_sample_tree_b); same result either way
-    if (batched) ST_CHECK_CUDA(cudaMemsetAsync(stamp, 0, n * sizeof(int32_t), s));
+    // schedule of the greedy loop (same result either way): speculative rounds spread over the cluster (default), one
+    // speculative member per CTA (ST_SAMPLE_MODE=members), or strictly sequential (ST_SAMPLE_SEQUENTIAL=1)
+    int mode = 2;
+    if (const char *e = getenv("ST_SAMPLE_MODE")) mode = !strcmp(e, "members") ? 1 : !strcmp(e, "sequential") ? 0 : 2;
+    if (getenv("ST_SAMPLE_SEQUENTIAL")) mode = 0;
+    if (mode) {
+        ST_CHECK_CUDA(cudaMemsetAsync(stamp, 0, n * sizeof(int32_t), s));
+        ST_CHECK_CUDA(cudaMemsetAsync(binfo, 0, (size_t)n_comp * 64 * sizeof(int32_t), s));
+    }
     k_st_init<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(pred, tree_dist, (int)n, distw, alloc, branch_id, best, comp_off, n_comp, keys, vals);
     ST_CHECK_LAUNCH();
     int key_bits = 33;                                   // 32 distance bits + the component index above them
@@ -889,6 +1391,8 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     if (CL == 0) {
         cudaFuncSetAttribute((const void *)k_sample_tree, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaFuncSetAttribute((const void *)k_sample_tree_b, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute((const void *)k_sample_tree_c, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute((const void *)k_sample_tree_c, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RoundSmem));
         for (int cand : {16, 8, 4, 2, 1}) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cand);
@@ -898,9 +1402,12 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
             at.val.clusterDim.x = cand; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
             cfg.attrs = &at; cfg.numAttrs = 1;
             int nclusters = 0;
-            int nclusters_b = 0;
+            int nclusters_b = 0, nclusters_c = 0;
+            cudaLaunchConfig_t cfg_c = cfg;
+            cfg_c.dynamicSmemBytes = sizeof(RoundSmem);
             if (cudaOccupancyMaxActiveClusters(&nclusters, (const void *)k_sample_tree, &cfg) == cudaSuccess && nclusters >= 1 &&
-                cudaOccupancyMaxActiveClusters(&nclusters_b, (const void *)k_sample_tree_b, &cfg) == cudaSuccess && nclusters_b >= 1) { CL = cand; break; }
+                cudaOccupancyMaxActiveClusters(&nclusters_b, (const void *)k_sample_tree_b, &cfg) == cudaSuccess && nclusters_b >= 1 &&
+                cudaOccupancyMaxActiveClusters(&nclusters_c, (const void *)k_sample_tree_c, &cfg_c) == cudaSuccess && nclusters_c >= 1) { CL = cand; break; }
         }
         cudaGetLastError();
         if (CL == 0) CL = 1;
@@ -920,8 +1427,15 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     cfg.attrs = &at; cfg.numAttrs = 1;
     int nt = (int)n;
     const int32_t *jump_c = jump;
-    if (batched) ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_b, a, jump_c, nt, stamp, tlist_all, binfo));
-    else ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree, a, jump_c, nt));
+    if (mode == 2) {
+        ST_REQUIRE(n < (1ll << 28), "components of at most 2^28 vertices");
+        cfg.dynamicSmemBytes = sizeof(RoundSmem);
+        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo));
+    } else if (mode == 1) {
+        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_b, a, jump_c, nt, stamp, tlist_all, binfo));
+    } else {
+        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree, a, jump_c, nt));
+    }
     return ST_OK;
 }
 

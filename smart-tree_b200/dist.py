@@ -126,6 +126,82 @@ def gather_skeletons(local: List[DisjointTreeSkeleton], unit_ids: List[int], dev
     return GatheredSkeletons([(ng[r][:int(all_counts[r, 0])].cpu(), mg[r][:int(all_counts[r, 1])].cpu()) for r in range(world)])
 
 
+# ---------------------------------------------------------------------------------------------- packed gather (one collective)
+class GatheredPacked:
+    """Every rank's packed skeleton buffer after ONE all-gather (device-resident int32 [world, cap]); host copy and the
+    reference's object model only on demand."""
+
+    def __init__(self, buf, world):
+        self.buf, self.world = buf, world
+        self._host = None
+
+    def to_host(self):
+        """One device->host copy of the gathered buffer -> list of (unit, PackedSkeletons) per rank."""
+        if self._host is None:
+            from .data_types.packed import PackedSkeletons
+            h = self.buf.cpu().numpy()
+            self._host = [PackedSkeletons.from_wire(h[r]) for r in range(self.world)]
+        return self._host
+
+    @property
+    def n_branches(self):
+        return int(sum(p.nb for _, p in self.to_host()))
+
+    def skeletons(self):
+        """{(unit, skeleton id): TreeSkeleton} over all ranks."""
+        out = {}
+        for unit, p in self.to_host():
+            for s in p:
+                out[(unit, s._id)] = s
+        return out
+
+    def __len__(self):
+        return sum(len(p) for _, p in self.to_host())
+
+
+def gather_packed(local: DisjointTreeSkeleton, unit: int, capacity: int = 1 << 20, device=None) -> GatheredPacked:
+    """All-gather of the packed result of one skeletoniser call per rank (the path's only exchange).
+    The device buffer st_finish_skeletons wrote is shipped as it is -- no Python re-packing of branches: ONE all-gather
+    of `capacity` int32 words per rank (the used prefix carries its own length) and one read-back of the `world` length
+    words (all ranks must agree on whether anything overflowed).  If a rank's result does not fit, the collective is
+    repeated once with the largest size (rare: the default capacity holds ~200 k nodes)."""
+    from .data_types.packed import PackedSkeletons
+    packed = local.skeletons
+    if not isinstance(packed, PackedSkeletons):
+        if len(packed) != 0:
+            raise TypeError("gather_packed needs the packed result of Skeletonizer.forward (use gather_skeletons for object lists)")
+        d0 = device if device is not None else torch.device("cpu")
+        packed = PackedSkeletons(0, 0, [], [], None, torch.zeros(0, dtype=torch.int32, device=d0), False)      # nothing to skeletonise
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    wire = packed.wire(unit)
+    dev = device if device is not None else wire.device
+    if world > 1 and dist.get_backend() != "nccl":
+        dev = torch.device("cpu")
+    wire = wire.to(dev)
+    need = int(wire.numel())
+
+    def exchange(cap):
+        send = torch.zeros(cap, dtype=torch.int32, device=dev)
+        m = min(need, cap)
+        send[:m] = wire[:m]
+        send[0] = need                        # true length, also when truncated: the receivers see the overflow
+        if world == 1:
+            return send.unsqueeze(0)
+        recv = torch.empty((world, cap), dtype=torch.int32, device=dev)
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(recv, send)
+        else:
+            dist.all_gather(list(recv.unbind(0)), send)
+        return recv
+
+    cap = max(int(capacity), 16)
+    recv = exchange(cap)
+    biggest = int(recv[:, 0].max().item())
+    if biggest > cap:
+        recv = exchange(biggest)
+    return GatheredPacked(recv, world)
+
+
 # ---------------------------------------------------------------------------------------------- labelled voxels (plots)
 def labelled_part(lc, voxel_block):
     """One rank's labelled voxels as two tables: f[n,9] = xyz, rgb, medial_vector and i[n,2] = class, global block."""

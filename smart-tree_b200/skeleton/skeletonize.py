@@ -30,16 +30,15 @@ class Skeletonizer:
         self.last = None       # intermediate tensors of the last call (for tests / diagnostics)
 
     @staticmethod
-    def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post=None) -> List[TreeSkeleton]:
+    def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post=None, comp_ids=None):
         """Branch assembly and (optionally) prune / repair / smooth on the device in one launch
         (st_finish_skeletons), then two device->host copies in total: a 4-word header + the per-component
         branch counts, and ONE packed buffer with the branch table, the node array [R,4] (xyz, radius; one
         spare row in front of each branch for the repair connection point) and the smoothed radii.
-        `post` = dict(prune=(min_radius, min_length) | None, repair=bool, smooth=kernel_size) or None."""
-        import numpy as np
-
-        from ..data_types.branch import BranchSkeleton, PackedBranchSkeleton
-        from ..data_types.tree import NodeStore
+        `post` = dict(prune=(min_radius, min_length) | None, repair=bool, smooth=kernel_size) or None.
+        Returns a PackedSkeletons: the result as packed host arrays (+ the device buffer for the multi-GPU gather);
+        the TreeSkeleton / BranchSkeleton objects are built from it on first access."""
+        from ..data_types.packed import PackedSkeletons
         post = post or {}
         prune = post.get("prune")
         k = int(post.get("smooth") or 0)
@@ -48,54 +47,11 @@ class Skeletonizer:
                                    repair=bool(post.get("repair")), smooth_kernel=k)
         hdr = torch.cat([out[:4], cnb]).cpu().numpy()
         nb, nrow = int(hdr[0]), int(hdr[1])
-        cnb_h = hdr[4:4 + ncomp]
-        if nb == 0:
-            return [TreeSkeleton(c, {}) for c in range(ncomp)]
-        payload = out[4:4 + 4 * nb + 5 * nrow].cpu().numpy()
-        bmeta = payload[:4 * nb].reshape(nb, 4)
-        nodes = torch.from_numpy(payload[4 * nb:4 * nb + 4 * nrow].view(np.float32).reshape(nrow, 4))
-        smooth = torch.from_numpy(payload[4 * nb + 4 * nrow:].view(np.float32))
-        store = NodeStore(nodes, None)
-        flags = bmeta[:, 3]
-        kept = np.flatnonzero(flags & 1)
-        if len(kept) == 0:
-            return [TreeSkeleton(c, {}) for c in range(ncomp)]
-        conn = (flags[kept] & 2) != 0
-        first = bmeta[kept, 0] + np.where(conn, 0, 1)
-        cnt = bmeta[kept, 0] + bmeta[kept, 1] + 1 - first
-        comp_of = np.repeat(np.arange(ncomp), cnb_h)
-        local = np.arange(nb) - np.repeat(np.cumsum(cnb_h) - cnb_h, cnb_h)
-        rows_l, lens_l, pars_l, flags_l = bmeta[kept, 0].tolist(), bmeta[kept, 1].tolist(), bmeta[kept, 2].tolist(), flags[kept].tolist()
-        comp_l, bid_l = comp_of[kept].tolist(), local[kept].tolist()
-        per_comp = [dict() for _ in range(ncomp)]
-        if post:
-            # post-processing is complete: pack the surviving rows (one gather) so that the per-branch views come
-            # from two gap-free split calls (a view costs ~0.5 us; gaps would double their number)
-            csum = np.cumsum(cnt)
-            rows = np.repeat(first - (csum - cnt), cnt) + np.arange(int(csum[-1]))
-            sm_row = np.repeat((flags[kept] & 4) != 0, cnt)
-            packed = nodes[torch.from_numpy(rows)]
-            radcol = torch.where(torch.from_numpy(sm_row), smooth[torch.from_numpy(rows)], packed[:, 3])
-            xyz_all = packed[:, :3]
-            starts = (csum - cnt).tolist()
-            sizes = cnt.tolist()
-            for i in range(len(rows_l)):
-                # per-branch views are cut on first access (PackedBranchSkeleton)
-                per_comp[comp_l[i]][bid_l[i]] = PackedBranchSkeleton(bid_l[i], pars_l[i], xyz_all, radcol, starts[i], sizes[i],
-                                                                      radii_1d=bool(flags_l[i] & 4))
-            return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
-        # plain assembly: keep the spare rows (object-level repair writes the connection points there)
-        gaps = np.empty(2 * len(kept) + 1, np.int64)
-        gaps[0:-1:2] = first - np.concatenate([[0], (first + cnt)[:-1]])
-        gaps[1::2] = cnt
-        gaps[-1] = nrow - (first[-1] + cnt[-1])
-        sizes = gaps.tolist()
-        xyz_views = nodes[:, :3].split(sizes)[1::2]
-        rad_views = nodes[:, 3:4].split(sizes)[1::2]
-        for i in range(len(rows_l)):
-            per_comp[comp_l[i]][bid_l[i]] = BranchSkeleton(bid_l[i], pars_l[i], xyz_views[i], rad_views[i],
-                                                           _flat=(store, rows_l[i], lens_l[i], False))
-        return [TreeSkeleton(c, per_comp[c]) for c in range(ncomp)]
+        cnb_h = hdr[4:4 + ncomp].copy()
+        dev_payload = out[4:4 + 4 * nb + 5 * nrow]
+        payload = dev_payload.cpu().numpy() if nb else None
+        ids = list(range(ncomp)) if comp_ids is None else [int(c) for c in comp_ids]
+        return PackedSkeletons(nb, nrow, cnb_h, ids, payload, dev_payload, bool(post))
 
     def forward(self, cloud: Cloud, post: dict = None, shard=None) -> DisjointTreeSkeleton:
         """`post` (optional, not in the reference signature): post-processing to fuse into the device-side branch
@@ -177,10 +133,8 @@ class Skeletonizer:
         if shard is not None and post and (not self.component_ids or self.component_ids[0] != 0):
             post = {k: v for k, v in post.items() if k != "prune"}        # only the globally first skeleton is pruned (quirk C-18)
         with section("skel.emit"):
-            skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post)
-            if shard is not None:
-                for sk_, gid in zip(skeletons, self.component_ids):
-                    sk_._id = gid                                            # global (size-ordered) component index
+            # skeleton ids = global (size-ordered) component indices, also when only this rank's share was extracted
+            skeletons = self._emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post, comp_ids=self.component_ids)
         self.last = dict(keep=keep, order=order, comp_off=comp_off, pred=pred_local, dist=dist, tree_dist=tdist, roots=src,
                          path=path, branch_len=blen, branch_parent=bpar, comp_n_branches=cnb, comp_n_path=cnp,
                          n_components=ncomp, edges=graph.edges, edge_weights=graph.edge_weights)

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                        "--cpu-sample-points", "4000", "--voxel", "0.02"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--points", "4000", "--voxel", "0.02"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -24,6 +24,9 @@ def test_reference_arm_json_line():
     for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "vs_baseline", "dtype", "data", "config"):
         assert k in d
     assert "workload" in d["config"] and "model" not in d["config"]
+    # the line declares the size it actually ran (round-1 finding: 100 k points timed under a 1 M-point label)
+    assert d["config"]["points_per_tree"] == 4000 and d["config"]["total_points"] == 4000 and "4000 points" in d["cpu_baseline"]["sample"]
+    assert d["steps_timed"] == 1
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")

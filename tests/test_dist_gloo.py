@@ -121,3 +121,66 @@ def test_merge_labelled_any_world_single_process():
         parts = [stdist.labelled_part(lc.filter((blk % world) == r), blk[(blk % world) == r]) for r in range(world)]
         m = stdist.merge_labelled(parts)
         assert torch.equal(m.xyz, lc.xyz) and torch.equal(m.medial_vector, lc.medial_vector) and torch.equal(m.class_l, lc.class_l)
+
+
+# ---------------------------------------------------------------- packed gather: the device buffer of st_finish_skeletons, one collective
+def _fake_packed(unit, nbranch, post_done=True):
+    """A PackedSkeletons as Skeletonizer._emit builds it (include/st_b200.h: bmeta | nodes | smooth), two components."""
+    from smart_tree_b200.data_types.packed import PackedSkeletons
+    g = np.random.default_rng(unit)
+    lens = [2 + (unit + b) % 5 for b in range(nbranch)] + [3]
+    cnb = np.array([nbranch, 1], np.int32)
+    nb, nrow = len(lens), sum(lens) + len(lens)
+    bmeta = np.zeros((nb, 4), np.int32)
+    row = 0
+    for b, ln in enumerate(lens):
+        local = b if b < nbranch else 0
+        bmeta[b] = (row, ln, local - 1, 1 | (2 if local > 0 and post_done else 0) | (4 if ln > 4 and post_done else 0))
+        row += ln + 1
+    nodes = g.standard_normal((nrow, 4)).astype(np.float32)
+    smooth = g.uniform(0, 1, nrow).astype(np.float32)
+    payload = np.concatenate([bmeta.reshape(-1), nodes.view(np.int32).reshape(-1), smooth.view(np.int32)])
+    return PackedSkeletons(nb, nrow, cnb, [0, 1], payload, torch.from_numpy(payload.copy()), post_done)
+
+
+def _summary(packed_list):
+    out = {}
+    for unit, p in packed_list:
+        for s in p:
+            out[(unit, s._id)] = (len(s.branches), float(sum(float(b.xyz.sum()) + float(b.radii.sum()) for b in s.branches.values())),
+                                  [b.parent_id for b in s.branches.values()])
+    return out
+
+
+def _packed_worker(rank, world, port, out, capacity):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    stdist.init_from_env(backend="gloo")
+    local = DisjointTreeSkeleton(_fake_packed(10 + rank, 3 + 4 * rank))
+    g = stdist.gather_packed(local, unit=10 + rank, capacity=capacity, device=torch.device("cpu"))
+    assert g.n_branches == sum(3 + 4 * r + 1 for r in range(world)) and len(g) == 2 * world
+    out[rank] = _summary(g.to_host())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("capacity", [1 << 16, 64])        # 64 words: every rank overflows -> the collective is repeated at the largest size
+def test_packed_gather_world2(capacity):
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_packed_worker, args=(2, port, out, capacity), nprocs=2, join=True)
+    expect = _summary([(10 + r, _fake_packed(10 + r, 3 + 4 * r)) for r in range(2)])
+    assert out[0] == expect and out[1] == expect
+
+
+def test_packed_wire_roundtrip_and_lazy_objects():
+    from smart_tree_b200.data_types.packed import PackedSkeletons
+    for post_done in (True, False):
+        p = _fake_packed(3, 5, post_done)
+        assert p._objs is None and len(p) == 2 and bool(p)                  # nothing materialised yet
+        unit, q = PackedSkeletons.from_wire(p.wire(unit=42).numpy())
+        assert unit == 42 and q.nb == p.nb and q.nrow == p.nrow and q.comp_ids == [0, 1]
+        assert _summary([(0, p)]) == _summary([(0, q)])
+        sk = p[0]
+        assert sorted(sk.branches) == list(range(5)) and p._objs is not None
+        b1 = sk.branches[1]
+        assert b1.parent_id == 0 and b1.xyz.shape[0] == (2 + (3 + 1) % 5) + (1 if post_done else 0)      # + the repair connection point

@@ -5,7 +5,7 @@ minute of host time); the measured error statistics are written to gpurun_out/pa
 profiles/ by hand) together with the result digest that bench.py prints for the same configuration.
 
 Per-element measures (what "1e-3 rel" means here, written out):
-  * radius (log radius), class logits:   |got - ref| / max(|ref|, 0.01 * rms(ref))          per element
+  * radius (log radius), class logits:   |got - ref| / max(|ref|, 0.01 * rms(ref), 1e-6)    per element
   * medial_vector (exp(radius) * dir):   ||got - ref|| / max(||ref||, 0.01 * rms||ref||)    per row
   * direction (unit vectors):            ||got - ref||                                      per row
     F.normalize divides by ||v||: a row whose un-normalised head output v is k times smaller than typical amplifies
@@ -45,7 +45,7 @@ def elem_errors(got, ref, v_raw=None):
     out = {}
     for k in ("radius", "class_l"):
         r = ref[k].astype(np.float64)
-        floor = 0.01 * np.sqrt((r * r).mean())
+        floor = max(0.01 * np.sqrt((r * r).mean()), 1e-6)       # (peach-forest-65's class logits are identically 0 on tube clouds)
         out[k] = np.abs(got[k].astype(np.float64) - r) / np.maximum(np.abs(r), floor)
     d = np.linalg.norm(got["direction"].astype(np.float64) - ref["direction"].astype(np.float64), axis=1)
     out["direction_raw"] = d
@@ -54,7 +54,7 @@ def elem_errors(got, ref, v_raw=None):
         out["direction"] = d * np.minimum(1.0, nv / np.median(nv))
     mr = np.linalg.norm(ref["medial_vector"].astype(np.float64), axis=1)
     md = np.linalg.norm(got["medial_vector"].astype(np.float64) - ref["medial_vector"].astype(np.float64), axis=1)
-    out["medial_vector"] = md / np.maximum(mr, 0.01 * np.sqrt((mr * mr).mean()))
+    out["medial_vector"] = md / np.maximum(mr, max(0.01 * np.sqrt((mr * mr).mean()), 1e-9))
     return out
 
 

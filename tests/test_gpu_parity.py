@@ -590,20 +590,22 @@ def _assert_same_skeletons(got, ref):
             assert np.array_equal(gb.radii.numpy().reshape(-1), rb.radii)
 
 
-@pytest.mark.parametrize("schedule", ["batched", "batched-cluster-4", "sequential", "hopwise-tree-dist"])
+@pytest.mark.parametrize("schedule", ["batched", "batched-cluster-4", "batched-cluster-1", "members", "sequential", "hopwise-tree-dist"])
 @pytest.mark.parametrize("seed,n,vs", [(0, 50000, 0.02), (3, 30000, 0.02)])
 def test_skeletonizer_topology_bit_identical(seed, n, vs, schedule, monkeypatch):
-    """Every schedule of the skeleton kernels gives the oracle's result bit for bit: sample_tree in speculative batches
-    (default, cluster of 16 or 4 CTAs = batch size) or strictly sequential; tree distances by chain walking (default)
-    or hop by hop."""
+    """Every schedule of the skeleton kernels gives the oracle's result bit for bit: sample_tree in speculative rounds
+    spread over a cluster of 16 / 4 / 1 CTAs (default), with one speculative member per CTA, or strictly sequential;
+    tree distances by chain walking (default) or hop by hop."""
     from smart_tree_b200.data_types.cloud import Cloud
     from smart_tree_b200.skeleton.skeletonize import Skeletonizer
     if schedule == "sequential":
         monkeypatch.setenv("ST_SAMPLE_SEQUENTIAL", "1")
     if schedule == "hopwise-tree-dist":
         monkeypatch.setenv("ST_TREE_DIST_HOPWISE", "1")
-    if schedule == "batched-cluster-4":
-        monkeypatch.setenv("ST_SAMPLE_CLUSTER", "4")
+    if schedule.startswith("batched-cluster-"):
+        monkeypatch.setenv("ST_SAMPLE_CLUSTER", schedule.rsplit("-", 1)[1])
+    if schedule == "members":
+        monkeypatch.setenv("ST_SAMPLE_MODE", "members")
     xyz, mv = _medial_case(seed, n, vs)
     sk = Skeletonizer(K=16, min_connection_length=0.02, minimum_graph_vertices=32, device=torch.device(DEV))
     got = sk.forward(Cloud(xyz=_t(xyz), medial_vector=_t(mv)))
