@@ -133,6 +133,8 @@ __device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
         : "l"(p));
 }
 
+__device__ __align__(32) float g_zero_row[16];      // all zeros: where the gathers of absent neighbours point
+
 // ---- narrow layers (8 or 16 input channels: level 0 and the encoder / decoder between levels 0 and 1) -----------------
 // ncu on the round-1 kernel (8 -> 8, level 0): L1 data-pipe wavefronts 65-80 % of peak, FMA pipe 37 %, DRAM 11 % -- these
 // layers are bound by what goes through the L1 data pipe: the gathered rows (27 x 32 B per voxel) and the per-tap weight
@@ -217,50 +219,33 @@ __global__ void __launch_bounds__(128, 4) k_conv_narrow(ConvArgs a) {
         while (lend < nlist && s_taps[lend] < t0 + nt) ++lend;
         // virtual taps vi = H * (list position) + (half of the input row), for list positions [li, lend)
         const int v0 = li * C::H, v1 = lend * C::H;
+        // Entries of the gather map for virtual tap vi (the tap offset k * n_out is uniform: one 64-bit multiply per tap).
         auto map_at = [&](int vi, int (&j)[C::RT]) {
             const int k = vi < v1 ? s_taps[vi / C::H] : -1;
+            const int32_t *mk = a.map ? a.map + (size_t)max(k, 0) * a.n_out : nullptr;
 #pragma unroll
             for (int r = 0; r < C::RT; ++r) {
                 j[r] = -1;
-                if (k >= 0 && rows[r] < a.n_out) j[r] = a.map ? __ldg(a.map + (size_t)k * a.n_out + rows[r]) : rows[r];
+                if (k >= 0 && rows[r] < a.n_out) j[r] = mk ? __ldg(mk + rows[r]) : rows[r];
             }
         };
-        auto rows_at = [&](int vi, const int (&j)[C::RT], float4 (&x)[C::RT][2]) {
+        // Rows of virtual tap vi: an absent neighbour reads the all-zero row instead of being predicated off (no register
+        // zeroing, no predicate per load; the lanes without a neighbour all hit the same L1 sector).  Returns "any present".
+        auto rows_at = [&](int vi, const int (&j)[C::RT], float4 (&x)[C::RT][2]) -> bool {
             const int half = C::H == 1 ? 0 : vi % C::H;
-#pragma unroll
-            for (int r = 0; r < C::RT; ++r) {
-                x[r][0] = x[r][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j[r] >= 0) {
-                    const float *p = a.in + (size_t)j[r] * a.in_ld + 8 * half;
-                    if (V8) ldg256(p, x[r][0], x[r][1]);
-                    else { x[r][0] = __ldg((const float4 *)p); x[r][1] = __ldg((const float4 *)p + 1); }
-                }
-            }
-        };
-        int jn1[C::RT], jn2[C::RT];
-        float4 xn[C::RT][2];
-        {
-            int j0[C::RT];
-            map_at(v0, j0);
-            map_at(v0 + 1, jn1);
-            rows_at(v0, j0, xn);
-#pragma unroll
-            for (int r = 0; r < C::RT; ++r) jn2[r] = j0[r];
-        }
-        for (int vi = v0; vi < v1; ++vi) {
-            const int k = s_taps[vi / C::H];
-            const int half = C::H == 1 ? 0 : vi % C::H;
-            float4 xc[C::RT][2];
             bool any = false;
 #pragma unroll
             for (int r = 0; r < C::RT; ++r) {
-                any |= jn2[r] >= 0;
-                xc[r][0] = xn[r][0]; xc[r][1] = xn[r][1];
-                jn2[r] = jn1[r];
+                any |= j[r] >= 0;
+                const float *p = j[r] >= 0 ? a.in + (size_t)j[r] * a.in_ld + 8 * half : g_zero_row;
+                if (V8) ldg256(p, x[r][0], x[r][1]);
+                else { x[r][0] = __ldg((const float4 *)p); x[r][1] = __ldg((const float4 *)p + 1); }
             }
-            rows_at(vi + 1, jn1, xn);              // rows of the next virtual tap (its entries were loaded one step ago)
-            map_at(vi + 2, jn1);                   // entries of the one after that
-            if (!__any_sync(0xffffffffu, any)) continue;
+            return any;
+        };
+        auto compute = [&](int vi, const float4 (&x)[C::RT][2]) {
+            const int k = s_taps[vi / C::H];
+            const int half = C::H == 1 ? 0 : vi % C::H;
             const float *wt = ws + (k - t0) * C::TAP_FLOATS + half * 8 * COUT + cg * 8;
 #pragma unroll
             for (int ci = 0; ci < 8; ++ci) {
@@ -268,7 +253,7 @@ __global__ void __launch_bounds__(128, 4) k_conv_narrow(ConvArgs a) {
                 const unsigned long long w01 = f2_pack(wa.x, wa.y), w23 = f2_pack(wa.z, wa.w), w45 = f2_pack(wb.x, wb.y), w67 = f2_pack(wb.z, wb.w);
 #pragma unroll
                 for (int r = 0; r < C::RT; ++r) {
-                    const float4 xq = xc[r][ci >> 2];
+                    const float4 xq = x[r][ci >> 2];
                     const float xv = (ci & 3) == 0 ? xq.x : (ci & 3) == 1 ? xq.y : (ci & 3) == 2 ? xq.z : xq.w;
                     const unsigned long long xx = f2_pack(xv, xv);
                     acc[r][0] = ffma2(xx, w01, acc[r][0]);
@@ -277,6 +262,22 @@ __global__ void __launch_bounds__(128, 4) k_conv_narrow(ConvArgs a) {
                     acc[r][3] = ffma2(xx, w67, acc[r][3]);
                 }
             }
+        };
+        // software pipeline, unrolled by two so that the two row buffers swap roles instead of being copied:
+        // map entries run two virtual taps ahead of the arithmetic, feature rows one
+        int ja[C::RT], jb[C::RT];
+        float4 xa[C::RT][2], xb[C::RT][2];
+        map_at(v0, ja);
+        map_at(v0 + 1, jb);
+        bool any_a = rows_at(v0, ja, xa), any_b = false;
+        for (int vi = v0; vi < v1; vi += 2) {
+            any_b = rows_at(vi + 1, jb, xb);           // rows of vi + 1 (entries loaded one step ago)
+            map_at(vi + 2, ja);                        // entries of vi + 2
+            if (__any_sync(0xffffffffu, any_a)) compute(vi, xa);
+            if (vi + 1 >= v1) break;
+            any_a = rows_at(vi + 2, ja, xa);           // rows of vi + 2
+            map_at(vi + 3, jb);                        // entries of vi + 3
+            if (__any_sync(0xffffffffu, any_b)) compute(vi + 1, xb);
         }
         li = lend;
         __syncthreads();

@@ -174,7 +174,7 @@ __device__ __forceinline__ void grid_barrier(unsigned *ctr, unsigned &phase) {
 // the kernel stops after a whole chunk in which no counter moved.
 constexpr int SSSP_PASSES = 64;
 constexpr int SSSP_G = 4;
-constexpr int SSSP_NF_PASSES = 32;    // polls between barriers in the near-far kernel (~ hops per threshold step)
+constexpr int SSSP_NF_PASSES = 64;    // polls between barriers in the near-far kernel (tools/sssp_sweep.py: 64 polls, step 0.125 m best on the bench tree)
 constexpr float ST_INF = __builtin_huge_valf();
 
 struct SsspCtl {
@@ -503,7 +503,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     if (rc) return rc;
     if (blocks > (int)g) blocks = (int)g;
     int nn = (int)n;
-    if (!(delta > 0.f)) delta = 0.05f;
+    if (!(delta > 0.f)) delta = 0.125f;
     int npass = SSSP_NF_PASSES;
     if (const char *e = getenv("ST_SSSP_PASSES")) { int v = atoi(e); if (v >= 1 && v <= 1024) npass = v; }
     int adv = 1;                           // threshold schedule (see k_sssp); any value gives the same result

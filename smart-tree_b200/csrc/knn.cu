@@ -94,8 +94,8 @@ extern "C" int st_knn(const float *src, int64_t n, const float *dst, int64_t m, 
     const int self_query = (src == dst && n == m) ? 1 : 0;
 #define ST_K(KK) case KK: k_knn<KK><<<g, 128, 0, s>>>(src, (int)n, gb.g, gb.cell_start, gb.sorted, r, query_radius, idx, d2, self_query); break;
     switch (K) {
-        ST_K(1) ST_K(2) ST_K(4) ST_K(8) ST_K(16) ST_K(24) ST_K(32)
-        default: set_error("st_knn: K=%d not instantiated (1,2,4,8,16,24,32)", K); return ST_ERR_UNSUPPORTED;
+        ST_K(1) ST_K(2) ST_K(4) ST_K(8) ST_K(16) ST_K(24) ST_K(32) ST_K(48) ST_K(64)
+        default: set_error("st_knn: K=%d not instantiated (1,2,4,8,16,24,32,48,64; the Python wrapper rounds up and slices)", K); return ST_ERR_UNSUPPORTED;
     }
 #undef ST_K
     ST_CHECK_LAUNCH();

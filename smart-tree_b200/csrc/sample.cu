@@ -108,8 +108,24 @@ __device__ __forceinline__ unsigned long long claim_key(float4 q, float4 o, unsi
 }
 
 // lanes < count each settle one queued (sorted position, path index) pair
+// `lohi` (optional): per path vertex j the index interval [lo, hi] (lo | hi << 16) that contains every path vertex within
+// 2 r of it.  A vertex that beats j for a point within r of j is itself within r of the point, hence within 2 r of j: the
+// scan over [lo, hi] decides exactly what the scan over the whole path decides, ~20x cheaper on a 300-vertex route.
+__device__ __forceinline__ void path_windows(const float4 *s_path, int len, float r, int *lohi, int t0, int nt) {
+    const float lim = 2.f * r * 1.001f + 1e-6f, lim2 = lim * lim;
+    for (int j = t0; j < len; j += nt) {
+        const float4 p = s_path[j];
+        int lo = j, hi = j;
+        for (int j2 = 0; j2 < len; ++j2) {
+            const float4 q = s_path[j2];
+            if (dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) <= lim2) { lo = min(lo, j2); hi = max(hi, j2); }
+        }
+        lohi[j] = lo | (hi << 16);
+    }
+}
+
 __device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s_path, int len, const int2 *queue, int first, int count,
-                                            int lane, int bid) {
+                                            int lane, int bid, const int *lohi = nullptr) {
     if (lane >= count) return;
     const int2 e = queue[first + lane];
     const float4 q = __ldg(a.sorted + e.x);
@@ -117,7 +133,9 @@ __device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s
     const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
     const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - e.y);
     bool own = true;
-    for (int j2 = 0; j2 < len; ++j2) own = own && !(claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key);
+    int jlo = 0, jhi = len - 1;
+    if (lohi) { const int w = lohi[e.y]; jlo = w & 0xFFFF; jhi = w >> 16; }
+    for (int j2 = jlo; j2 <= jhi; ++j2) own = own && !(claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key);
     if (own && sqrtf(d2) < p.w) {
         const int gi = __float_as_int(q.w);
         a.distw[gi] = -1.f;
@@ -221,7 +239,8 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &tot
 template <int MODE>
 __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc, const float4 *s_path, int len, int nflat, int R2, int R,
                                            float r, float r2, int bid, int32_t *touch_cnt, int2 *queue, int *s_off, int *s_beg,
-                                           int *s_jj, int *s_warp, unsigned cr, unsigned CL, const Collect *co = nullptr) {
+                                           int *s_jj, int *s_warp, unsigned cr, unsigned CL, const Collect *co = nullptr,
+                                           const int *lohi = nullptr) {
     constexpr bool SHORT = MODE != 0;
     const int tid = threadIdx.x, lane = tid & 31;
     const float rr = r * 1.0001f + 1e-7f;
@@ -280,7 +299,7 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
                 if (qn >= 32) {
                     qn -= 32;
                     if (MODE == 2) claim_drain_collect(a, s_path, len, queue, qn, 32, lane, *co);
-                    else claim_drain(a, s_path, len, queue, qn, 32, lane, bid);
+                    else claim_drain(a, s_path, len, queue, qn, 32, lane, bid, lohi);
                     __syncwarp();
                 }
             } else if (cand) {
@@ -293,7 +312,7 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
     if (SHORT) {
         __syncwarp();
         if (MODE == 2) claim_drain_collect(a, s_path, len, queue, 0, qn, lane, *co);
-        else claim_drain(a, s_path, len, queue, 0, qn, lane, bid);
+        else claim_drain(a, s_path, len, queue, 0, qn, lane, bid, lohi);
     }
 }
 
@@ -842,16 +861,19 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
 // Two cluster barriers per round.  Routes of 64 or more vertices run as one whole-cluster iteration of k_sample_tree.
 constexpr int MB = 16;         // members per round
 constexpr int MP = 64;         // route slots per member
-constexpr int WIN = 256;       // live entries examined per round
-constexpr int SCAN_CHUNKS = 4; // order-list positions examined per round = 1024 * SCAN_CHUNKS
+constexpr int WIN = 512;       // live entries examined per round
+constexpr int SCAN_CHUNKS = 4; // order-list positions examined per scan step = 1024 * SCAN_CHUNKS
+constexpr int SCAN_STEPS = 8;  // scan steps per round at most (late in the loop live entries are ~1 in 400)
 
 struct RoundSmem {
     float4 path[MB * MP];      // xyz + radius of member g's route vertex h at [g * MP + h]  (the long-route path reuses it as [1024])
     int2 queue[32][QUEUE_LEN];
     int off[1024], beg[1024], jj[1024];
     int pv[MB * MP];           // vertex ids (component-local) of the routes
+    int lohi[MB * MP];         // path_windows of every route vertex (member-local indices)
     int win_pos[WIN + 1];      // positions (in the sorted list) of the window's live entries (+ the first one beyond it)
     int win_gap[WIN];          // >= 0: member index of a selected entry;  < 0: -(g + 1), passed over after member g
+    float4 win_pt[WIN];        // xyz + radius of the window entries (member selection)
     float4 selpt[MB];          // start vertex of each member: xyz + radius
     int sel[MB], len[MB], term[MB], rbits[MB], parent[MB], mf[MB], mp[MB], status[MB], bid[MB], pcur[MB], toff[MB + 1], R[MB];
     int gapneed[MB], gapbad[MB];
@@ -882,23 +904,25 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     long long t_mark = clock64();
     while (true) {
         ++dbg[0];
-        // ---- A. window: the live entries among the next 4096 positions of the (distance desc, index asc) list
-        int live[SCAN_CHUNKS];
+        // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 4096 positions at a time
+        int nlive = 0, scan_end = cursor;
+        for (int step = 0; step < SCAN_STEPS && nlive <= WIN && scan_end < nc; ++step) {
+            int live[SCAN_CHUNKS];
 #pragma unroll
-        for (int k = 0; k < SCAN_CHUNKS; ++k) {
-            const int pos = cursor + k * 1024 + tid;
-            live[k] = pos < nc ? (__ldcg(a.distw + __ldg(a.order + base + pos)) > 0.f ? 1 : 0) : 0;
-        }
-        int nlive = 0;
+            for (int k = 0; k < SCAN_CHUNKS; ++k) {
+                const int pos = scan_end + k * 1024 + tid;
+                live[k] = pos < nc ? (__ldcg(a.distw + __ldg(a.order + base + pos)) > 0.f ? 1 : 0) : 0;
+            }
 #pragma unroll
-        for (int k = 0; k < SCAN_CHUNKS; ++k) {
-            int total;
-            const int rank = block_excl_scan_1024(live[k], S.scan, total);
-            if (live[k] && nlive + rank <= WIN) S.win_pos[nlive + rank] = cursor + k * 1024 + tid;
-            nlive += total;
-            __syncthreads();
+            for (int k = 0; k < SCAN_CHUNKS; ++k) {
+                int total;
+                const int rank = block_excl_scan_1024(live[k], S.scan, total);
+                if (live[k] && nlive + rank <= WIN) S.win_pos[nlive + rank] = scan_end + k * 1024 + tid;
+                nlive += total;
+                __syncthreads();
+            }
+            scan_end = min(scan_end + SCAN_CHUNKS * 1024, nc);
         }
-        const int scan_end = min(cursor + SCAN_CHUNKS * 1024, nc);
         if (nlive == 0) {
             if (scan_end >= nc) break;
             cursor = scan_end;
@@ -907,6 +931,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         int nwin = min(nlive, WIN);
         // position where the window ends: the first live entry beyond it, or the end of the scanned range
         int win_end = nlive > WIN ? S.win_pos[WIN] : scan_end;
+        if (tid < nwin) {
+            const int v = __ldg(a.order + base + S.win_pos[tid]);
+            S.win_pt[tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
+        }
+        __syncthreads();
         // ---- B. members: greedy in list order, an entry is taken iff it is far from every member taken so far (warp 0)
         if (warp == 0) {
             int nsel = 0;
@@ -915,8 +944,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                 float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
                 bool far = false;
                 if (e < nwin) {
-                    const int v = __ldg(a.order + base + S.win_pos[e]);
-                    p = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
+                    p = S.win_pt[e];
                     far = true;
                     for (int m = 0; m < nsel; ++m) {
                         const float4 q = S.selpt[m];
@@ -1023,8 +1051,12 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             const long long ntask = (long long)len * R2;
             const int nflat = (int)min((long long)min(len, PATH_SMEM) * R2, (long long)INT_MAX);
             if (len <= SCAN_PATH) {
-                if (r > 0.f)
-                    claim_flat<1>(a, base, nc, S.path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, S.queue[warp], S.off, S.beg, S.jj, S.scan, cr, CL);
+                if (r > 0.f) {
+                    path_windows(S.path, len, r, S.lohi, tid, 1024);
+                    __syncthreads();
+                    claim_flat<1>(a, base, nc, S.path, len, nflat, R2, R, r, r2, emit ? bid : -1, nullptr, S.queue[warp], S.off, S.beg, S.jj, S.scan, cr, CL,
+                                  nullptr, S.lohi);
+                }
             } else {
                 if (r > 0.f) {
                     claim_flat<0>(a, base, nc, S.path, len, nflat, R2, R, r, r2, -1, cnt_cur, nullptr, S.off, S.beg, S.jj, S.scan, cr, CL);
@@ -1106,6 +1138,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             const int term = S.term[tid];
             S.parent[tid] = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));      // state before this round (nobody has committed yet)
         }
+        if (g < nsel) path_windows(S.path + g * MP, S.len[g], __int_as_float(S.rbits[g]), S.lohi + g * MP, h, MP);
         if (tid == 0) {
             int t = 0;
             for (int m = 0; m < nsel; ++m) {
@@ -1138,7 +1171,8 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
                     const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
                     bool own = true;
-                    for (int j2 = 0; j2 < len; ++j2) own = own && !(claim_key(q, S.path[m * MP + j2], (unsigned)(len - 1 - j2)) < key);
+                    const int w = S.lohi[e.y];
+                    for (int j2 = w & 0xFFFF; j2 <= (w >> 16); ++j2) own = own && !(claim_key(q, S.path[m * MP + j2], (unsigned)(len - 1 - j2)) < key);
                     hit = own && sqrtf(d2) < p.w;
                     gi = __float_as_int(q.w);
                     word = (m << 28) | (gi - base);

@@ -443,11 +443,21 @@ def heads_fused(feat, params, want_logits=True, out_index=None):
 
 
 # ------------------------------------------------------------------ kNN / graph
+_KNN_KS = (1, 2, 4, 8, 16, 24, 32, 48, 64)
+
+
 def knn(src, dst, K, r, query_radius=None):
     """idx[n,K] i32 (-1 padded), d2[n,K] f32 squared distances (-1 padded)."""
     lib = _lib.load()
     _req(src, F32, "src"); _req(dst, F32, "dst")
     n, m = src.shape[0], dst.shape[0]
+    k_req = int(K)
+    if k_req < 1 or k_req > 64:
+        raise _lib.StB200Error(f"knn: K={k_req} outside 1..64 (the register top-K kernels; the reference runs K=16)")
+    K = next(k for k in _KNN_KS if k >= k_req)          # the kernel is instantiated for these; the K nearest are a prefix
+    if K != k_req:
+        idx, d2 = knn(src, dst, K, r, query_radius)
+        return idx[:, :k_req].contiguous(), d2[:, :k_req].contiguous()
     idx = torch.empty((n, K), dtype=I32, device=src.device)
     d2 = torch.empty((n, K), dtype=F32, device=src.device)
     ws = _ws(lib.st_knn_workspace_bytes(m), src.device)

@@ -34,7 +34,7 @@ def _read_ply(path):
             elif tok[0] == "property" and in_vertex:
                 props.append((tok[2], _PLY_TYPES[tok[1]]))
         if fmt == "ascii":
-            data = np.loadtxt(f, max_rows=n, ndmin=2)
+            data = np.loadtxt(f, max_rows=n, ndmin=2) if n else np.zeros((0, len(props)))
             cols = {name: data[:, i] for i, (name, _) in enumerate(props)}
         else:
             end = "<" if fmt == "binary_little_endian" else ">"
@@ -44,7 +44,7 @@ def _read_ply(path):
     xyz = np.stack([cols["x"], cols["y"], cols["z"]], 1).astype(np.float64)
     if all(c in cols for c in ("red", "green", "blue")):
         rgb = np.stack([cols["red"], cols["green"], cols["blue"]], 1).astype(np.float64)
-        if rgb.max() > 1.0:
+        if dict(props)["red"] in ("u1", "i1", "u2", "i2"):          # integer colour channels are 0..255 (open3d does the same)
             rgb = rgb / 255.0
     else:
         rgb = np.zeros_like(xyz)

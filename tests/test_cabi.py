@@ -83,3 +83,20 @@ def test_packed_branch_skeleton_is_a_lazy_branch_skeleton():
     assert type(f) is BranchSkeleton and len(f) == 3
     b.xyz, b.radii = nodes[:2], rad[:2].unsqueeze(1)                      # object-level post-processing may replace them
     assert len(b) == 2 and b.radii.shape == (2, 1)
+
+
+def test_pyproject_console_script_mirrors_the_reference():
+    """`run-smart-tree` (reference pyproject.toml:36) is declared and resolves to a callable; every sub-package listed."""
+    import importlib
+    import tomllib
+    with open(os.path.join(ROOT, "pyproject.toml"), "rb") as f:
+        cfg = tomllib.load(f)
+    target = cfg["project"]["scripts"]["run-smart-tree"]
+    assert target == "smart_tree_b200.cli:main"
+    mod, fn = target.split(":")
+    assert callable(getattr(importlib.import_module(mod), fn))
+    pkgs = set(cfg["tool"]["setuptools"]["packages"])
+    here = os.path.join(ROOT, "smart-tree_b200")
+    found = {"smart_tree_b200"} | {"smart_tree_b200." + d for d in os.listdir(here)
+                                   if os.path.exists(os.path.join(here, d, "__init__.py"))}
+    assert pkgs == found

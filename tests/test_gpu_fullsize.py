@@ -172,6 +172,13 @@ def test_full_size_tree_matches_oracle(name, weights, seed, points, voxel):
     report["skeleton_oracle_seconds"] = round(time.perf_counter() - t0, 1)
     # stage by stage first (a mismatch names the stage): components, SSSP predecessors, tree distances, branch paths
     last = pipe.skeletonizer.last
+    if not ref_sk:
+        # nothing to skeletonise (peach-forest-65 on tube clouds: every voxel fails the outlier test with its predicted
+        # radius): both paths must agree on that
+        assert len(skel.skeletons) == 0 and (last is None or int(last["n_components"]) == 0)
+        report["skeleton"] = {"branches": 0, "note": "no component survives the outlier filter -- oracle and CUDA agree"}
+        _write(name, report)
+        return
     off = last["comp_off"].cpu().numpy()
     assert len(ref_sk) == int(last["n_components"])
     for c, r in enumerate(ref_sk):
@@ -188,6 +195,9 @@ def test_full_size_tree_matches_oracle(name, weights, seed, points, voxel):
                           "components": int(last["n_components"]), "digest": skeleton_digest(skel.skeletons)}
     assert nb > 100
     _write(name, report)
+    # the digest bench.py prints for this configuration (tests/golden/bench_digests.json is refreshed from these files)
+    with open(os.path.join(ROOT, "gpurun_out", f"digest_{name}.json"), "w") as f:
+        json.dump({f"{name}:{points}:{voxel}": report["skeleton"]["digest"]}, f)
 
 
 def test_strict_spconv_bounds_on_c2():
