@@ -284,11 +284,16 @@ int st_csr_build(const int32_t *edges, const float *weights, int64_t n_edges,
                  const int32_t *vertex_map /* optional: edge endpoints are renumbered through it, < 0 drops the edge */,
                  int64_t n, int32_t *row_ptr, int32_t *col, float *w, int64_t *n_arcs_host,
                  void *workspace, size_t workspace_bytes, void *stream);
+/* orig_id (optional, [n]): the caller may number the GRAPH in any order that suits the kernel -- spatial (Z) order makes the
+ * vertex range of a CTA a compact blob, so that most hops of a shortest-path chain stay in its shared memory -- and pass the
+ * map back to its own numbering: vertex v of the graph is vertex orig_id[v] of the caller.  dist / pred are then written in
+ * the CALLER's numbering (dist[orig_id[v]], pred values are caller ids) and the tie rule "lowest predecessor" is evaluated
+ * on caller ids, i.e. the result does not depend on the graph's numbering.  `sources` are graph vertices.                */
 int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n,
             const int32_t *sources, int32_t n_sources,
             float delta /* threshold step of the distance-ordered schedule; any value gives the same result; <=0: default */,
             float *dist, int32_t *pred,
-            int32_t *sweeps_host, void *ctl_workspace /* 256 + 12n B, device */, void *stream);
+            int32_t *sweeps_host, void *ctl_workspace /* 256 + 16n B, device */, const int32_t *orig_id, void *stream);
 /* pred_graph + second sssp             smart_tree/skeleton/shortest_path.py:46-55
  * tree_dist[v] = tree_dist[pred[v]] + ||p_v - p_pred(v)||, 0 at roots (pred<0 & reachable
  * flag), FLT_MAX where unreachable[v] != 0.                                              */

@@ -71,7 +71,7 @@ SIGNATURES = {
     "st_connected_components": (C.c_int, [_p, _i64, _i64, _p, _p, _p]),
     "st_csr_workspace_bytes": (_sz, [_i64, _i64]),
     "st_csr_build": (C.c_int, [_p, _p, _i64, _p, _i64, _p, _p, _p, _pi64, _p, _sz, _p]),
-    "st_sssp": (C.c_int, [_p, _p, _p, _i64, _p, _i32, _f, _p, _p, _pi32, _p, _p]),
+    "st_sssp": (C.c_int, [_p, _p, _p, _i64, _p, _i32, _f, _p, _p, _pi32, _p, _p, _p]),
     "st_tree_distances": (C.c_int, [_p, _p, _p, _i64, _p, _p, _p]),
     "st_sample_tree_workspace_bytes": (_sz, [_i64, _i32]),
     "st_sample_tree": (C.c_int, [_p, _p, _p, _p, _p, _i32, _i64, _f, _p, _p, _p, _p, _p, _p, _sz, _p]),

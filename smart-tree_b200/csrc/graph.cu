@@ -420,6 +420,171 @@ __global__ void __launch_bounds__(256) k_sssp_nf_big(const int32_t *__restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------ SSSP with CTA-local propagation
+// Same relaxation and the same distance-ordered acceptance as k_sssp, but every CTA keeps the distances and the wake-up
+// counters of its own contiguous vertex range in SHARED memory.  With the vertices numbered in spatial (Z) order -- the
+// caller builds the CSR that way and passes the map back to its own numbering as `orig_id` -- a CTA's range is a blob a few
+// hops across: most hops of a shortest-path chain then stay inside one CTA and cost a shared-memory round trip instead of
+// two L2 round trips (poll + relax), only the hops that cross a range boundary go through global memory as before.
+//   * a vertex' distance lives in sdist (owner CTA, authoritative for its warps) AND in dist[] (written through on every
+//     accepted improvement: what remote CTAs read);
+//   * notifications to a neighbour in the same range bump its shared counter, to a neighbour elsewhere its global one;
+//     the gpu-scope fence an accepted improvement needs before a REMOTE neighbour may be woken is only paid by vertices
+//     that have remote neighbours to wake;
+//   * per outer pass one poll of the global counters and up to `nlocal` polls of the shared ones.
+// Any schedule converges to the same fp32 fixed point (see k_sssp).
+template <int G>
+__global__ void __launch_bounds__(1024, 1) k_sssp_local(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                                        const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta,
+                                                        int npass, int adv, int nlocal) {
+    extern __shared__ __align__(16) unsigned char sssp_smem[];
+    constexpr int VB = 1024 * G;                         // vertices per CTA
+    volatile float *sdist = reinterpret_cast<volatile float *>(sssp_smem);
+    int *sflag = reinterpret_cast<int *>(sssp_smem + (size_t)VB * sizeof(float));
+    unsigned phase = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int v0 = blockIdx.x * VB;
+    for (int i = threadIdx.x; i < VB; i += 1024) {
+        sdist[i] = v0 + i < n ? __ldcg(dist + v0 + i) : ST_INF;
+        sflag[i] = 0;
+    }
+    __syncthreads();
+    int seenL[G], seenG[G], rb[G], re[G];
+    float pend[G];
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const int v = v0 + ((k * 32 + warp) << 5) + lane;
+        seenL[k] = 0; seenG[k] = 0;
+        pend[k] = ST_INF;
+        rb[k] = v < n ? __ldg(row_ptr + v) : 0;
+        re[k] = v < n ? __ldg(row_ptr + v + 1) : 0;
+    }
+    auto rd = [&](int u) -> float {                     // current distance of u: shared if it is ours, L2 otherwise
+        const unsigned lu = (unsigned)(u - v0);
+        return lu < (unsigned)VB ? sdist[lu] : __ldcg(dist + u);
+    };
+    float T = delta;
+    for (unsigned chunk = 0;; ++chunk) {
+        bool consumed = false;
+        for (int pass = 0; pass < npass; ++pass) {
+            unsigned wokeG = 0;                              // bit k: group k has a lane whose GLOBAL counter moved (per lane)
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                const int v = v0 + ((k * 32 + warp) << 5) + lane;
+                const int cnt = v < n ? __ldcg(dirty + v) : seenG[k];
+                if (cnt != seenG[k]) wokeG |= 1u << k;
+                seenG[k] = cnt;
+            }
+            if (__any_sync(0xffffffffu, wokeG != 0)) __threadfence();      // counter observed -> the remote distance behind it is visible
+            for (int q = 0; q < nlocal; ++q) {
+                bool any = false;
+#pragma unroll
+                for (int k = 0; k < G; ++k) {
+                    const int lv = ((k * 32 + warp) << 5) + lane;
+                    const int v = v0 + lv;
+                    const int cnt = *(volatile int *)(sflag + lv);
+                    const bool woke = v < n && (cnt != seenL[k] || ((wokeG >> k) & 1u) || pend[k] <= T);
+                    seenL[k] = cnt;
+                    unsigned mask = __ballot_sync(0xffffffffu, woke);
+                    if (!mask) continue;
+                    any = true;
+                    if (woke) pend[k] = ST_INF;
+                    while (mask) {            // woken vertices one after the other, each relaxed by the whole warp
+                        const int l = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int lvv = ((k * 32 + warp) << 5) + l;
+                        const int vv = v0 + lvv;
+                        const int b = __shfl_sync(0xffffffffu, rb[k], l), e = __shfl_sync(0xffffffffu, re[k], l);
+                        const float cur = sdist[lvv];
+                        float best = cur;
+                        int u0 = -1, u1 = -1;
+                        float c0 = ST_INF, c1 = ST_INF, d0 = 0.f, d1 = 0.f, ww0 = 0.f, ww1 = 0.f;
+                        if (b + lane < e) { u0 = __ldg(col + b + lane); ww0 = __ldg(w + b + lane); d0 = rd(u0); c0 = __fadd_rn(d0, ww0); }
+                        if (b + 32 + lane < e) { u1 = __ldg(col + b + 32 + lane); ww1 = __ldg(w + b + 32 + lane); d1 = rd(u1); c1 = __fadd_rn(d1, ww1); }
+                        best = fminf(best, fminf(c0, c1));
+                        for (int a = b + 64 + lane; a < e; a += 32) best = fminf(best, __fadd_rn(rd(__ldg(col + a)), __ldg(w + a)));
+                        for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+                        if (best < cur) {
+                            if (best <= T) {
+                                consumed = true;
+                                if (lane == 0) { sdist[lvv] = best; __stcg(dist + vv, best); }
+                                __threadfence_block();
+                                __syncwarp();
+                                __threadfence_block();
+                                // u can only improve through vv if d[vv] + w < d[u]
+                                bool remote = false;
+                                auto notify = [&](int u, float ww, float du) {
+                                    if (u < 0 || !(__fadd_rn(best, ww) < du)) return;
+                                    const unsigned lu = (unsigned)(u - v0);
+                                    if (lu < (unsigned)VB) atomicAdd(sflag + lu, 1);
+                                    else remote = true;
+                                };
+                                notify(u0, ww0, d0);
+                                notify(u1, ww1, d1);
+                                for (int a = b + 64 + lane; a < e; a += 32) { const int u = __ldg(col + a); notify(u, __ldg(w + a), rd(u)); }
+                                if (__any_sync(0xffffffffu, remote)) {
+                                    __threadfence();          // the improvement is visible device-wide before a remote owner is woken
+                                    auto notify_remote = [&](int u, float ww, float du) {
+                                        if (u < 0 || !(__fadd_rn(best, ww) < du)) return;
+                                        if ((unsigned)(u - v0) >= (unsigned)VB) atomicAdd(dirty + u, 1);
+                                    };
+                                    notify_remote(u0, ww0, d0);
+                                    notify_remote(u1, ww1, d1);
+                                    for (int a = b + 64 + lane; a < e; a += 32) { const int u = __ldg(col + a); notify_remote(u, __ldg(w + a), __ldcg(dist + u)); }
+                                }
+                            } else if (lane == l) {
+                                pend[k] = best;       // parked until the threshold reaches it (or a neighbour wakes it again)
+                            }
+                        }
+                    }
+                }
+                wokeG = 0;
+                if (!any) break;                    // nothing moved in this warp's groups: back to the global poll
+            }
+        }
+        float pmin = ST_INF;
+#pragma unroll
+        for (int k = 0; k < G; ++k) pmin = fminf(pmin, pend[k]);
+        for (int o = 16; o; o >>= 1) pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+        if (lane == 0 && pmin < ST_INF) atomicMin(&ctl->min_pend[chunk % 3], __float_as_uint(pmin));
+        if (__syncthreads_or(consumed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->changed[(chunk + 1) % 3] = 0; ctl->min_pend[(chunk + 1) % 3] = 0x7F800000u; }
+        grid_barrier(&ctl->barrier, phase);
+        const unsigned anyc = *(volatile unsigned *)&ctl->changed[chunk % 3];
+        const unsigned mp = *(volatile unsigned *)&ctl->min_pend[chunk % 3];
+        if (!anyc) {
+            if (mp == 0x7F800000u) {
+                if (blockIdx.x == 0 && threadIdx.x == 0) ctl->chunks = chunk + 1;
+                break;
+            }
+            T = fmaxf(T, __uint_as_float(mp)) + delta;
+        } else if (adv && mp != 0x7F800000u) {
+            T = fmaxf(T, __uint_as_float(mp) + delta);
+        }
+    }
+}
+
+// dist / pred in the caller's numbering when the graph is numbered in spatial order: out[orig[v]] = value of v, predecessor =
+// the neighbour with the lowest ORIGINAL id among those that attain the distance (the tie rule is stated in the caller's ids)
+__global__ void k_sssp_pred_orig(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, const float *__restrict__ w,
+                                 int n, const float *__restrict__ dist, const int32_t *__restrict__ orig, float *__restrict__ dist_out,
+                                 int32_t *__restrict__ pred_out) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    float dv = dist[v];
+    int best = INT_MAX;
+    if (dv != ST_INF) {
+        for (int a = row_ptr[v]; a < row_ptr[v + 1]; ++a) {
+            int u = col[a];
+            if (__fadd_rn(dist[u], w[a]) == dv) best = min(best, __ldg(orig + u));
+        }
+    }
+    const int o = orig[v];
+    pred_out[o] = best == INT_MAX ? -1 : best;
+    dist_out[o] = dv == ST_INF ? FLT_MAX : dv;
+}
+
 __global__ void k_sssp_seed(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col, int *dirty,
                             const int32_t *__restrict__ sources, int ns) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -473,16 +638,39 @@ static int coop_grid(const void *kernel, int threads, int device, int &blocks) {
     return ST_OK;
 }
 
+__global__ void k_set_pred_sources_orig(int32_t *pred, const int32_t *__restrict__ sources, const int32_t *__restrict__ orig, int ns) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ns) pred[orig[sources[i]]] = -1;
+}
+
+template <int G>
+static int launch_sssp_local(int blocks_needed, int device, void **args, cudaStream_t s, bool &launched) {
+    const size_t smem = (size_t)8 * 1024 * G;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute((const void *)k_sssp_local<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    int per_sm = 0, sms = 0;
+    ST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_sssp_local<G>, 1024, smem));
+    ST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    launched = false;
+    if (per_sm * sms < blocks_needed) return ST_OK;
+    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_local<G>, dim3(blocks_needed), dim3(1024), args, smem, s));
+    launched = true;
+    return ST_OK;
+}
+
 extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t n, const int32_t *sources,
-                       int32_t n_sources, float delta, float *dist, int32_t *pred, int32_t *sweeps_host, void *ctl_workspace,
-                       void *stream) {
+                       int32_t n_sources, float delta, float *dist_out, int32_t *pred, int32_t *sweeps_host, void *ctl_workspace,
+                       const int32_t *orig_id, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (sweeps_host) *sweeps_host = 0;
     if (n == 0) return ST_OK;
-    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 12n bytes) required");
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 16n bytes) required");
     int device = 0;
     ST_CHECK_CUDA(cudaGetDevice(&device));
     SsspCtl *ctl = (SsspCtl *)ctl_workspace;
+    // with orig_id the relaxation runs on an internal distance array in the graph's numbering; the results are scattered
+    // to the caller's numbering at the end
+    float *dist = orig_id ? (float *)((char *)ctl_workspace + 256 + 12 * (size_t)n) : dist_out;
     ST_CHECK_CUDA(cudaMemsetAsync(ctl, 0, sizeof(SsspCtl), s));
     k_sssp_ctl_init<<<1, 1, 0, s>>>(ctl);
     unsigned g = (unsigned)cdiv(n, 256);
@@ -512,7 +700,28 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     // near-far counter variant: poll state in registers when every resident warp can own its vertices there, in global
     // memory otherwise (ctl_workspace holds dirty[n], seen[n], pend[n]); ST_SSSP_FLAGS=1 forces the old flag variant
     const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n && !getenv("ST_SSSP_FORCE_BIG");      // (env: tests exercise the large-graph kernel)
-    if (small) {
+    // CTA-local propagation (k_sssp_local): the smallest range per CTA for which the whole graph is resident
+    bool local_done = false;
+    if (!getenv("ST_SSSP_NO_LOCAL") && !getenv("ST_SSSP_FORCE_BIG") && !getenv("ST_SSSP_FLAGS")) {
+        int nlocal = 8;
+        if (const char *e = getenv("ST_SSSP_NLOCAL")) { int v = atoi(e); if (v >= 1 && v <= 256) nlocal = v; }
+        void *largs[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta,
+                         (void *)&npass, (void *)&adv, (void *)&nlocal};
+        int gsel = 0;
+        if (const char *e = getenv("ST_SSSP_LOCAL_G")) gsel = atoi(e);
+        for (int G : {1, 2, 4, 8}) {
+            if (local_done || (gsel && G != gsel)) continue;
+            const int need = (int)cdiv(n, 1024 * (int64_t)G);
+            int rc2 = ST_OK;
+            if (G == 1) rc2 = launch_sssp_local<1>(need, device, largs, s, local_done);
+            else if (G == 2) rc2 = launch_sssp_local<2>(need, device, largs, s, local_done);
+            else if (G == 4) rc2 = launch_sssp_local<4>(need, device, largs, s, local_done);
+            else rc2 = launch_sssp_local<8>(need, device, largs, s, local_done);
+            if (rc2) return rc2;
+        }
+    }
+    if (local_done) {
+    } else if (small) {
         ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp, dim3(blocks), dim3(256), args, 0, s));
     } else if (getenv("ST_SSSP_FLAGS")) {
         ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_big, dim3(blocks), dim3(256), args, 0, s));
@@ -530,13 +739,22 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
                          (void *)&ctl, (void *)&delta, (void *)&npass, (void *)&adv};
         ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_nf_big, dim3(blocks2), dim3(256), args2, 0, s));
     }
-    k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
-    ST_CHECK_LAUNCH();
-    k_sssp_finish<<<g, 256, 0, s>>>(dist, (int)n);
-    ST_CHECK_LAUNCH();
-    if (n_sources) {
-        k_set_pred_sources<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(pred, sources, n_sources);
+    if (orig_id) {
+        k_sssp_pred_orig<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, orig_id, dist_out, pred);
         ST_CHECK_LAUNCH();
+        if (n_sources) {
+            k_set_pred_sources_orig<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(pred, sources, orig_id, n_sources);
+            ST_CHECK_LAUNCH();
+        }
+    } else {
+        k_sssp_pred<<<g, 256, 0, s>>>(row_ptr, col, w, (int)n, dist, pred);
+        ST_CHECK_LAUNCH();
+        k_sssp_finish<<<g, 256, 0, s>>>(dist, (int)n);
+        ST_CHECK_LAUNCH();
+        if (n_sources) {
+            k_set_pred_sources<<<(unsigned)cdiv(n_sources, 256), 256, 0, s>>>(pred, sources, n_sources);
+            ST_CHECK_LAUNCH();
+        }
     }
     if (sweeps_host) {
         unsigned chunks = 0;

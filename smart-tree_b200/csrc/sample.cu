@@ -51,7 +51,7 @@ struct SampleArgs {
     Grid g;
     const int32_t *cell_start;
     const float4 *sorted;
-    const int32_t *order;
+    int32_t *order;         // (distance desc, index asc) list; k_sample_tree_c compacts it in place
     float *distw;
     uint8_t *alloc;
     int32_t *branch_id;
@@ -860,10 +860,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const i
 //   * accepted members commit together (labels through atomicMax: branch ids grow with the member index).
 // Two cluster barriers per round.  Routes of 64 or more vertices run as one whole-cluster iteration of k_sample_tree.
 constexpr int MB = 16;         // members per round
-constexpr int MP = 64;         // route slots per member
+constexpr int MP = 128;        // route slots per member (two per thread of the member's 64)
+constexpr int MPS = 7;         // log2(MP)
 constexpr int WIN = 512;       // live entries examined per round
-constexpr int SCAN_CHUNKS = 4; // order-list positions examined per scan step = 1024 * SCAN_CHUNKS
-constexpr int SCAN_STEPS = 8;  // scan steps per round at most (late in the loop live entries are ~1 in 400)
+constexpr int SCAN_STEPS = 4;  // scan steps of 8192 list positions per round at most (the list is compacted as the loop goes)
 
 struct RoundSmem {
     float4 path[MB * MP];      // xyz + radius of member g's route vertex h at [g * MP + h]  (the long-route path reuses it as [1024])
@@ -874,6 +874,7 @@ struct RoundSmem {
     int win_pos[WIN + 1];      // positions (in the sorted list) of the window's live entries (+ the first one beyond it)
     int win_gap[WIN];          // >= 0: member index of a selected entry;  < 0: -(g + 1), passed over after member g
     float4 win_pt[WIN];        // xyz + radius of the window entries (member selection)
+    int win_v[WIN];            // vertex id (global) of the window entries: `order` is compacted in place at the end of the round
     float4 selpt[MB];          // start vertex of each member: xyz + radius
     int sel[MB], len[MB], term[MB], rbits[MB], parent[MB], mf[MB], mp[MB], status[MB], bid[MB], pcur[MB], toff[MB + 1], R[MB];
     int gapneed[MB], gapbad[MB];
@@ -904,24 +905,31 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     long long t_mark = clock64();
     while (true) {
         ++dbg[0];
-        // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 4096 positions at a time
+        // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 8192 positions at a time
+        //         (eight consecutive positions per thread: two 16-byte loads of the list, one block scan per step)
+        long long t_ph = clock64();
         int nlive = 0, scan_end = cursor;
         for (int step = 0; step < SCAN_STEPS && nlive <= WIN && scan_end < nc; ++step) {
-            int live[SCAN_CHUNKS];
+            int vtx[8];
+            unsigned lmask = 0;
+            const int p0 = scan_end + tid * 8;
 #pragma unroll
-            for (int k = 0; k < SCAN_CHUNKS; ++k) {
-                const int pos = scan_end + k * 1024 + tid;
-                live[k] = pos < nc ? (__ldcg(a.distw + __ldg(a.order + base + pos)) > 0.f ? 1 : 0) : 0;
-            }
+            for (int k = 0; k < 8; ++k) vtx[k] = p0 + k < nc ? __ldcg(a.order + base + p0 + k) : -1;
 #pragma unroll
-            for (int k = 0; k < SCAN_CHUNKS; ++k) {
-                int total;
-                const int rank = block_excl_scan_1024(live[k], S.scan, total);
-                if (live[k] && nlive + rank <= WIN) S.win_pos[nlive + rank] = scan_end + k * 1024 + tid;
-                nlive += total;
-                __syncthreads();
+            for (int k = 0; k < 8; ++k)
+                if (vtx[k] >= 0 && __ldcg(a.distw + vtx[k]) > 0.f) lmask |= 1u << k;
+            int total;
+            int rank = block_excl_scan_1024(__popc(lmask), S.scan, total);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (lmask & (1u << k)) {
+                    if (nlive + rank <= WIN) { S.win_pos[nlive + rank] = p0 + k; if (nlive + rank < WIN) S.win_v[nlive + rank] = vtx[k]; }
+                    ++rank;
+                }
             }
-            scan_end = min(scan_end + SCAN_CHUNKS * 1024, nc);
+            nlive += total;
+            __syncthreads();
+            scan_end = min(scan_end + 8192, nc);
         }
         if (nlive == 0) {
             if (scan_end >= nc) break;
@@ -932,10 +940,11 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         // position where the window ends: the first live entry beyond it, or the end of the scanned range
         int win_end = nlive > WIN ? S.win_pos[WIN] : scan_end;
         if (tid < nwin) {
-            const int v = __ldg(a.order + base + S.win_pos[tid]);
+            const int v = S.win_v[tid];
             S.win_pt[tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
         }
         __syncthreads();
+        if (tid == 0) { const long long t = clock64(); dbg[12] += (unsigned long long)(t - t_ph); t_ph = t; }
         // ---- B. members: greedy in list order, an entry is taken iff it is far from every member taken so far (warp 0)
         if (warp == 0) {
             int nsel = 0;
@@ -987,21 +996,26 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         const int g = tid >> 6, h = tid & 63;
         if (tid < MB) { S.first[tid] = 1024; S.rbits[tid] = 0; S.mf[tid] = 16; S.mp[tid] = 16; S.term[tid] = -1; S.gapneed[tid] = 0; S.gapbad[tid] = INT_MAX; }
         __syncthreads();
-        int x = -1;
+        int xs[2] = {-1, -1};                               // ancestors h and h + 64 of member g
         if (g < nsel) {
-            x = __ldg(a.order + base + S.win_pos[S.sel[g]]) - base;
 #pragma unroll
-            for (int L = 0; L < 2; ++L) {
-                const int d = (h >> (3 * L)) & 7;
-                if (d && x >= 0) x = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + x);
+            for (int t = 0; t < 2; ++t) {
+                const int hh = h + 64 * t;
+                int x = S.win_v[S.sel[g]] - base;
+#pragma unroll
+                for (int L = 0; L < 3; ++L) {
+                    const int d = (hh >> (3 * L)) & 7;
+                    if (d && x >= 0) x = __ldg(jump + (size_t)(7 * L + d - 1) * n_total + base + x);
+                }
+                xs[t] = x;
+                const bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
+                if (stop) atomicMin(&S.first[g], hh);
             }
-            const bool stop = x < 0 || __ldcg(a.alloc + base + x) != 0;
-            if (stop) atomicMin(&S.first[g], h);
         }
         __syncthreads();
         if (S.first[0] == 1024) {
             // =========================== long route: one iteration of k_sample_tree on candidate 0, whole cluster
-            const int f = __ldg(a.order + base + S.win_pos[0]) - base;
+            const int f = S.win_v[0] - base;
             int len = 0, cur = f, term = -1;
             float rl = 0.f;
             int *out = a.path_out + base + pcur;
@@ -1119,15 +1133,19 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         float rl = 0.f;
         if (g < nsel) {
             const int len = S.first[g];
-            if (h < len) {
-                S.pv[g * MP + h] = x;
-                const int v = base + x;
-                const float rv = a.radii[v];
-                S.path[g * MP + h] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
-                rl = rv;
-                if ((unsigned)(g % (int)CL) == cr) atomicMax(stamp + v, epoch_tag + 15 - g);      // the route stamps its own vertices
-            } else if (h == len) {
-                S.term[g] = x;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int hh = h + 64 * t, x = xs[t];
+                if (hh < len) {
+                    S.pv[g * MP + hh] = x;
+                    const int v = base + x;
+                    const float rv = a.radii[v];
+                    S.path[g * MP + hh] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], rv);
+                    rl = fmaxf(rl, rv);
+                    if ((unsigned)(g % (int)CL) == cr) atomicMax(stamp + v, epoch_tag + 15 - g);      // the route stamps its own vertices
+                } else if (hh == len) {
+                    S.term[g] = x;
+                }
             }
             if (h == 0) S.len[g] = len;
         }
@@ -1138,7 +1156,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             const int term = S.term[tid];
             S.parent[tid] = __ldcg(a.branch_id + base + (term >= 0 ? term : nc - 1));      // state before this round (nobody has committed yet)
         }
-        if (g < nsel) path_windows(S.path + g * MP, S.len[g], __int_as_float(S.rbits[g]), S.lohi + g * MP, h, MP);
+        if (g < nsel) path_windows(S.path + g * MP, S.len[g], __int_as_float(S.rbits[g]), S.lohi + g * MP, h, 64);
         if (tid == 0) {
             int t = 0;
             for (int m = 0; m < nsel; ++m) {
@@ -1152,6 +1170,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             if (cr == 0) ccnt[(epoch + 1) & 1] = 0;      // next round's list counter (idle since the previous round's last barrier)
         }
         __syncthreads();
+        if (tid == 0) { const long long t = clock64(); dbg[13] += (unsigned long long)(t - t_ph); t_ph = t; }
         // ---- D. claim, all members at once, tasks interleaved over the CTAs of the cluster
         int32_t *const cnt_cur = ccnt + (epoch & 1);
         {
@@ -1164,8 +1183,8 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                 int word = 0, gi = -1, m = 0;
                 if (lane < count) {
                     const int2 e = queue[first + lane];
-                    m = e.y >> 6;
-                    const int j = e.y & 63, len = S.len[m];
+                    m = e.y >> MPS;
+                    const int j = e.y & (MP - 1), len = S.len[m];
                     const float4 q = __ldg(a.sorted + e.x);
                     const float4 p = S.path[e.y];
                     const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
@@ -1224,7 +1243,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     const int gi = __float_as_int(q.w);
                     bool cand = false;
                     if (gi >= base && gi < base + nc) {
-                        const int m = sl >> 6, j = sl & 63, len = S.len[m];
+                        const int m = sl >> MPS, j = sl & (MP - 1), len = S.len[m];
                         const float r = __int_as_float(S.rbits[m]);
                         const float r2 = __fmul_rn(r, r);
                         const float4 p = S.path[sl];
@@ -1254,20 +1273,25 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             __syncwarp();
             drain(0, qn);
         }
+        if (tid == 0) { const long long t = clock64(); dbg[14] += (unsigned long long)(t - t_ph); t_ph = t; }
         cluster_sync_all();                                  // 1: every claim and stamp of the round is in place
         // ---- E. verdict inputs, every CTA for itself: who touched the members' vertices and the passed-over entries
         if (g < nsel) {
             const int len = S.len[g];
-            if (h <= len) {
-                const int term = S.term[g];
-                const int v = h < len ? S.pv[g * MP + h] : (term >= 0 ? term : nc - 1);
-                const int who = stamp_who(__ldcg(stamp + base + v), epoch);
-                if (h == 0) S.mf[g] = who; else atomicMin(&S.mp[g], who);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const int hh = h + 64 * t;
+                if (hh <= len) {
+                    const int term = S.term[g];
+                    const int v = hh < len ? S.pv[g * MP + hh] : (term >= 0 ? term : nc - 1);
+                    const int who = stamp_who(__ldcg(stamp + base + v), epoch);
+                    if (hh == 0) S.mf[g] = who; else atomicMin(&S.mp[g], who);
+                }
             }
         }
         if (tid < nwin && S.win_gap[tid] < 0) {
             const int after = -S.win_gap[tid] - 1;          // passed over after member `after`
-            const int v = __ldg(a.order + base + S.win_pos[tid]);
+            const int v = S.win_v[tid];
             const int who = stamp_who(__ldcg(stamp + v), epoch);
             if (who <= after) atomicOr(&S.gapneed[after], 1 << who);
             else atomicMin(&S.gapbad[after], tid);           // nobody before it claimed it: the sequential loop would pick it
@@ -1322,14 +1346,18 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             if (g < nsel && S.status[g] == ST_ACCEPT && (unsigned)(g % (int)CL) == cr) {
                 const int len = S.len[g];
                 const bool emit = len >= 2;
-                if (h < len) {
-                    const int lv = S.pv[g * MP + h];
-                    const int v = base + lv;
-                    a.distw[v] = -1.f;
-                    a.alloc[v] = 1;
-                    if (emit) {
-                        atomicMax(a.branch_id + v, S.bid[g]);
-                        a.path_out[base + S.pcur[g] + (len - 1 - h)] = lv;      // root side first
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int hh = h + 64 * t;
+                    if (hh < len) {
+                        const int lv = S.pv[g * MP + hh];
+                        const int v = base + lv;
+                        a.distw[v] = -1.f;
+                        a.alloc[v] = 1;
+                        if (emit) {
+                            atomicMax(a.branch_id + v, S.bid[g]);
+                            a.path_out[base + S.pcur[g] + (len - 1 - hh)] = lv;      // root side first
+                        }
                     }
                 }
                 if (emit && h == 0) {
@@ -1342,7 +1370,12 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         const int stop_entry = S.stop_entry;
         bid = S.newbid;
         pcur = S.newpcur;
-        cursor = stop_entry < nwin ? S.win_pos[stop_entry] : win_end;
+        // The window entries from the cut onwards are the only live entries of [their position, win_end): pack them against
+        // win_end (they only move right, in order), so that the next round's scan starts on a dense run of live entries
+        // instead of re-reading the dead ones.  Nobody reads the list before the barrier below (win_v is the round's copy).
+        const int keep = nwin - stop_entry;
+        if (cr == 0 && tid < keep) a.order[base + win_end - keep + tid] = S.win_v[stop_entry + tid];
+        cursor = win_end - keep;
         ++epoch;
         cluster_sync_all();                                  // 2: commits visible before the next round reads the state
     }

@@ -525,20 +525,37 @@ def csr_build(edges, weights, n, vertex_map=None):
     return row_ptr, col[:na.value], w[:na.value]
 
 
-def sssp(row_ptr, col, w, n, sources, want_sweeps=False, delta=0.0):
+def sssp(row_ptr, col, w, n, sources, want_sweeps=False, delta=0.0, orig_id=None):
+    """dist [n] f32, pred [n] i32.  orig_id (optional, i32 [n]): the graph is numbered in another order than the caller's
+    (spatial order, see spatial_order); results come back in the caller's numbering (include/st_b200.h)."""
     lib = _lib.load()
     _req(sources, I32, "sources")
+    if orig_id is not None:
+        _req(orig_id, I32, "orig_id")
     dev = row_ptr.device
     dist = torch.empty(n, dtype=F32, device=dev)
     pred = torch.empty(n, dtype=I32, device=dev)
-    ctl = torch.empty(64 + 3 * n, dtype=I32, device=dev)      # control block + dirty[n] (+ seen[n], pend[n] for large graphs)
+    ctl = torch.empty(64 + 4 * n, dtype=I32, device=dev)      # control block + dirty[n] (+ seen[n], pend[n] for large graphs) + internal dist[n]
     sweeps = C.c_int32(0)
     _count("sssp")
     _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], float(delta), _ptr(dist), _ptr(pred),
-                           C.byref(sweeps) if want_sweeps else None, _ptr(ctl), _stream()), "st_sssp")
+                           C.byref(sweeps) if want_sweeps else None, _ptr(ctl), _ptr(orig_id), _stream()), "st_sssp")
     global LAST_SSSP_CTL
     LAST_SSSP_CTL = ctl
     return (dist, pred, sweeps.value) if want_sweeps else (dist, pred)
+
+
+def spatial_order(points, group, cell=0.02):
+    """Z-order of points [m,3] inside their group (int tensor [m], e.g. the component index, < 32768): returns
+    perm i32 [m] (k-th vertex in spatial order) and rank i32 [m] (spatial position of each vertex).  Cells of `cell` metres;
+    any order is valid for st_sssp -- this one keeps the vertex range of a CTA compact."""
+    lo = points.min(0).values
+    q = ((points - lo) / cell).floor().clamp_(0, 65533).int()
+    coords = torch.stack([group.int(), q[:, 2], q[:, 1], q[:, 0]], 1).contiguous()
+    perm = morton_perm(coords)
+    rank = torch.empty_like(perm)
+    rank[perm.long()] = torch.arange(perm.shape[0], dtype=I32, device=perm.device)
+    return perm, rank
 
 
 def tree_distances(points, pred, is_root):

@@ -28,6 +28,7 @@ class Skeletonizer:
         self.minimum_graph_vertices = minimum_graph_vertices
         self.device = device
         self.last = None       # intermediate tensors of the last call (for tests / diagnostics)
+        self.spatial_sssp = bool(int(os.environ.get("ST_SSSP_SPATIAL", "1")))
 
     @staticmethod
     def _emit(sub_medial, sub_radius, path, blen, bpar, cnb, cnp, off32, ncomp, post=None, comp_ids=None):
@@ -101,11 +102,20 @@ class Skeletonizer:
             comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
             comp_off[1:] = torch.cumsum(sizes, 0)
             comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
-            # induced edges, renumbered (skeletonize.py:60-71): done inside the CSR build through new_id
-            row_ptr, col, w = ops.csr_build(graph.edges, graph.edge_weights, m, vertex_map=new_id)
             sub_xyz = cloud.xyz[order]
             sub_medial = medial[order].contiguous()
             sub_radius = radius[order].contiguous()
+            # induced edges, renumbered (skeletonize.py:60-71): done inside the CSR build through a vertex map.  The CSR
+            # is only read by the SSSP, which may number the graph as it likes (st_sssp orig_id): vertices in Z-order of
+            # their medial points inside each component, so that a CTA's vertex range is a compact blob
+            sperm = None
+            if self.spatial_sssp and ncomp < 32768:
+                sperm, srank = ops.spatial_order(sub_medial, comp_of)
+                vmap = torch.full((n,), -1, dtype=torch.int32, device=dev)
+                vmap[order] = srank
+            else:
+                vmap = new_id
+            row_ptr, col, w = ops.csr_build(graph.edges, graph.edge_weights, m, vertex_map=vmap)
             # root of each component = first argmin of surface y (cloud.py:205-206)
             y = sub_xyz[:, 1].contiguous()
             if ncomp <= 64:       # components are contiguous segments: a plain argmin per segment
@@ -120,7 +130,10 @@ class Skeletonizer:
             # threshold step of the distance-ordered SSSP schedule (any value is exact; tools/sssp_sweep.py: with the threshold
             # advancing at every barrier, 0.125 m and 64 polls per barrier were best on the 6 m bench tree: 4.4 -> 3.1 ms)
             delta = float(os.environ.get("ST_SSSP_DELTA", 6.25 * self.min_connection_length))
-            dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous(), delta=delta)
+            if sperm is not None:
+                dist, pred = ops.sssp(row_ptr, col, w, m, srank[src].contiguous(), delta=delta, orig_id=sperm)
+            else:
+                dist, pred = ops.sssp(row_ptr, col, w, m, src.int().contiguous(), delta=delta)
         with section("skel.tree_dist"):
             is_root = torch.zeros(m, dtype=torch.uint8, device=dev)
             is_root[src] = 1

@@ -551,14 +551,19 @@ def test_connected_components_exact():
     assert sum(len(c) for c in comps) == len(med)
 
 
-@pytest.mark.parametrize("variant", ["registers", "large-graph", "large-graph-flags"])
+@pytest.mark.parametrize("variant", ["cta-local", "cta-local-spatial", "cta-local-G8", "registers", "large-graph", "large-graph-flags"])
 def test_sssp_and_tree_distances_exact(variant, monkeypatch):
-    """The three relaxation schedules (poll state in registers / in global memory for graphs beyond the resident
-    capacity / the older flag variant) all reach the same fp32 fixed point and predecessors."""
-    if variant != "registers":
+    """Every relaxation schedule reaches the same fp32 fixed point and predecessors: CTA-local propagation in shared memory
+    (default) in the caller's numbering or with the graph renumbered in spatial order (st_sssp orig_id), poll state in
+    registers, in global memory for graphs beyond the resident capacity, and the older flag variant."""
+    if variant in ("large-graph", "large-graph-flags"):
         monkeypatch.setenv("ST_SSSP_FORCE_BIG", "1")
     if variant == "large-graph-flags":
         monkeypatch.setenv("ST_SSSP_FLAGS", "1")
+    if variant == "registers":
+        monkeypatch.setenv("ST_SSSP_NO_LOCAL", "1")
+    if variant == "cta-local-G8":
+        monkeypatch.setenv("ST_SSSP_LOCAL_G", "8")
     ops = _ops()
     xyz, med, rad, e, w = _graph_case()
     comp = S.connected_components(len(med), e, 32)[0]
@@ -567,8 +572,15 @@ def test_sssp_and_tree_distances_exact(variant, monkeypatch):
     le, lw = loc[e[sel]], w[sel]
     root = int(np.argmin(xyz[comp, 1]))
     rpred, rdist = S.sssp(len(comp), le, lw, root)
-    row_ptr, col, ww = ops.csr_build(_t(le, torch.int32), _t(lw), len(comp))
-    dist, pred, sweeps = ops.sssp(row_ptr, col, ww, len(comp), _t(np.array([root]), torch.int32), want_sweeps=True)
+    if variant == "cta-local-spatial":
+        nloc = len(comp)
+        perm, rank = ops.spatial_order(_t(med[comp]), torch.zeros(nloc, dtype=torch.int32, device=DEV))
+        assert np.array_equal(np.sort(perm.cpu().numpy()), np.arange(nloc)) and np.array_equal(rank.cpu().numpy()[perm.cpu().numpy()], np.arange(nloc))
+        row_ptr, col, ww = ops.csr_build(_t(le, torch.int32), _t(lw), nloc, vertex_map=rank)
+        dist, pred, sweeps = ops.sssp(row_ptr, col, ww, nloc, rank[root:root + 1].contiguous(), want_sweeps=True, orig_id=perm)
+    else:
+        row_ptr, col, ww = ops.csr_build(_t(le, torch.int32), _t(lw), len(comp))
+        dist, pred, sweeps = ops.sssp(row_ptr, col, ww, len(comp), _t(np.array([root]), torch.int32), want_sweeps=True)
     assert np.array_equal(dist.cpu().numpy(), rdist)
     assert np.array_equal(pred.cpu().numpy(), rpred)
     is_root = torch.zeros(len(comp), dtype=torch.uint8, device=DEV); is_root[root] = 1
