@@ -293,7 +293,7 @@ int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *w, int64_t 
             const int32_t *sources, int32_t n_sources,
             float delta /* threshold step of the distance-ordered schedule; any value gives the same result; <=0: default */,
             float *dist, int32_t *pred,
-            int32_t *sweeps_host, void *ctl_workspace /* 256 + 16n B, device */, const int32_t *orig_id, void *stream);
+            int32_t *sweeps_host, void *ctl_workspace /* 4608 + 16n B, device */, const int32_t *orig_id, void *stream);
 /* pred_graph + second sssp             smart_tree/skeleton/shortest_path.py:46-55
  * tree_dist[v] = tree_dist[pred[v]] + ||p_v - p_pred(v)||, 0 at roots (pred<0 & reachable
  * flag), FLT_MAX where unreachable[v] != 0.                                              */

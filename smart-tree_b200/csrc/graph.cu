@@ -422,146 +422,415 @@ __global__ void __launch_bounds__(256) k_sssp_nf_big(const int32_t *__restrict__
 
 
 // ------------------------------------------------------------------------------------ SSSP with CTA-local propagation
-// Same relaxation and the same distance-ordered acceptance as k_sssp, but every CTA keeps the distances and the wake-up
-// counters of its own contiguous vertex range in SHARED memory.  With the vertices numbered in spatial (Z) order -- the
-// caller builds the CSR that way and passes the map back to its own numbering as `orig_id` -- a CTA's range is a blob a few
-// hops across: most hops of a shortest-path chain then stay inside one CTA and cost a shared-memory round trip instead of
-// two L2 round trips (poll + relax), only the hops that cross a range boundary go through global memory as before.
-//   * a vertex' distance lives in sdist (owner CTA, authoritative for its warps) AND in dist[] (written through on every
-//     accepted improvement: what remote CTAs read);
-//   * notifications to a neighbour in the same range bump its shared counter, to a neighbour elsewhere its global one;
-//     the gpu-scope fence an accepted improvement needs before a REMOTE neighbour may be woken is only paid by vertices
-//     that have remote neighbours to wake;
-//   * per outer pass one poll of the global counters and up to `nlocal` polls of the shared ones.
-// Any schedule converges to the same fp32 fixed point (see k_sssp).
+// Same relaxation and the same distance-ordered ("near-far") acceptance as k_sssp, organised around WHERE a shortest-path
+// chain spends its time: every hop is a dependent round trip, and through L2 (poll a counter, relax, fence, notify) it
+// costs microseconds.  Here every CTA keeps the distances and wake-up counters of its own contiguous vertex range in SHARED
+// memory.  With the vertices numbered in spatial (Z) order -- the caller builds the CSR that way and passes the map back
+// to its own numbering as `orig_id` -- a range is a stretch of branch some tens of hops long (bench tree, 2048 vertices per
+// CTA: 7 % of the arcs and 39 of the 363 hops of the deepest path leave their range; in the caller's numbering 90 % and
+// 343); a hop inside it costs a shared-memory round trip, only the hops across a range boundary go through L2.
+//   * one LANE per vertex (a group of 32 consecutive vertices is one cross-section of a branch: the wave reaches its
+//     vertices together, so they are relaxed together, every lane walking its own arcs);
+//   * a vertex' distance lives in sdist (owner CTA) and is written through to dist[] (what remote CTAs read);
+//   * arcs to vertices of the own range are evaluated whenever the vertex is woken; arcs to REMOTE vertices only when the
+//     vertex' GLOBAL counter moved -- a remote neighbour that improved bumps exactly that counter (judged against a
+//     distance of ours it has read, which can only be staler = larger than the truth, so no wake-up is ever missed);
+//   * improvements are accepted while they lie below the threshold T of the current EPOCH, larger candidates stay parked
+//     in a register of the owning lane.  Without this order the relaxation is chaotic: every tiny improvement near the
+//     root re-sums the whole subtree behind it (measured on the bench tree: thousands of correction waves, 33 ms);
+//   * the warps of a CTA run free -- no block barrier while anything moves in the CTA (s_nactive counts the warps that
+//     found work in their last poll);
+//   * no grid barrier, and NO gpu-scope fence on the hot path (on sm_100 __threadfence() = MEMBAR.SC + CCTL.IVALL: it
+//     empties the SM's L1, where the arcs of the range live).  Every CTA has a MAILBOX word: notification count << 2 |
+//     epoch parity << 1 | idle bit.  A remote notification = relaxed bumps of the vertices' counters, then ONE
+//     release-add on the owner's mailbox (MEMBAR.ALL.GPU + atom: distance and counters are performed first).  A CTA in
+//     which nothing moves below T publishes its smallest parked candidate (atomicMin), ORs the idle bit into its own
+//     mailbox and compares the count it gets back with the count it has consumed: atomics on one word are totally ordered,
+//     so either the owner sees the notification or the notifier sees the idle bit -- then it clears the bit and takes the
+//     CTA out of the epoch's idle count on its behalf.  The count reaches the number of CTAs only when no CTA is active
+//     and no notification is pending; the CTA whose increment completes it opens the next epoch with T = (smallest parked
+//     candidate) + delta -- or ends the kernel if nothing is parked: the fixed point.
+// Any schedule converges to the same fp32 fixed point (see k_sssp); T and delta only decide how much work it takes.
+struct SsspBlobCtl {
+    unsigned long long epoch_T;  // (epoch << 32) | float bits of T: one word, so a reader never pairs a new epoch with an old T
+    int idle_count[2];           // by epoch parity
+    unsigned gmin[2];            // smallest parked candidate published in the epoch (float bits), by epoch parity
+    int rounds;                  // rounds of CTA 0 (diagnostics)
+    int pad0;
+    unsigned long long stats[4]; // relaxations, accepted improvements, remote notifications, epochs
+    unsigned long long phase[6]; // thread 0 of every CTA, summed (cycles): local polls, global step, barriers, idle spin, whole kernel; [5] = busiest CTA
+    int pad[36];
+    int mbox[1];                 // [gridDim.x] mailboxes
+};
+constexpr int ST_EPOCH_DONE = 0x7FFFFFFF;
+
+__device__ __forceinline__ int atom_add_release(int *p, int v) {
+    int old;
+    asm volatile("atom.release.gpu.global.add.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+
+__global__ void k_sssp_blob_init(SsspBlobCtl *ctl, int nblocks, float T0) {
+    if (threadIdx.x == 0) {
+        ctl->epoch_T = (unsigned long long)__float_as_uint(T0);
+        ctl->idle_count[0] = ctl->idle_count[1] = 0;
+        ctl->gmin[0] = ctl->gmin[1] = 0x7F800000u;
+        ctl->rounds = 0;
+        for (int i = 0; i < 4; ++i) ctl->stats[i] = 0;
+        for (int i = 0; i < 6; ++i) ctl->phase[i] = 0;
+    }
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) ctl->mbox[i] = 0;
+}
+
+// debug (ST_SSSP_BLOB_FLAGS & 4): %globaltimer >> 3 of the last accepted improvement of every vertex (graph numbering)
+__device__ unsigned g_sssp_tfinal[1 << 20];
+__device__ unsigned long long g_sssp_epoch_log[1024][4];    // per epoch: time of the advance, advancing CTA, its rounds, time it woke up in this epoch
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+constexpr int SSSP_OW = 960;       // threads of a k_sssp_blob CTA that own vertices (30 warps); the last two warps publish
+
 template <int G>
-__global__ void __launch_bounds__(1024, 1) k_sssp_local(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
-                                                        const float *__restrict__ w, int n, float *dist, int *dirty, SsspCtl *ctl, float delta,
-                                                        int npass, int adv, int nlocal) {
+__global__ void __launch_bounds__(1024, 1) k_sssp_blob(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col,
+                                                       const float *__restrict__ w, int n, float *dist, int *dirty, SsspBlobCtl *ctl,
+                                                       float delta, int nlocal, int flags) {
+    constexpr int VB = SSSP_OW * G;                      // vertices per CTA
+    constexpr int NW = (VB + 31) / 32;                   // words of the publish bitmap
     extern __shared__ __align__(16) unsigned char sssp_smem[];
-    constexpr int VB = 1024 * G;                         // vertices per CTA
-    volatile float *sdist = reinterpret_cast<volatile float *>(sssp_smem);
+    float *sdist = reinterpret_cast<float *>(sssp_smem);
     int *sflag = reinterpret_cast<int *>(sssp_smem + (size_t)VB * sizeof(float));
-    unsigned phase = 0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned *rbits = reinterpret_cast<unsigned *>(sssp_smem + (size_t)VB * 8);      // bit lv: improved, remote neighbours not yet told
+    __shared__ int s_nactive;                            // owner warps that found work in their last poll
+    __shared__ unsigned s_minpend[2];                    // by round parity: the slot of the next round is reset between this round's barriers
+    __shared__ int s_state;
+    __shared__ int s_mbox;                               // notification count of our mailbox as the publisher warp last saw it
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool owner = tid < SSSP_OW;
     const int v0 = blockIdx.x * VB;
-    for (int i = threadIdx.x; i < VB; i += 1024) {
+    const int NB = (int)gridDim.x;
+    int *const mybox = ctl->mbox + blockIdx.x;
+    for (int i = tid; i < VB; i += 1024) {
         sdist[i] = v0 + i < n ? __ldcg(dist + v0 + i) : ST_INF;
         sflag[i] = 0;
     }
-    __syncthreads();
+    for (int i = tid; i < NW; i += 1024) rbits[i] = 0;
+    if (tid == 0) { s_nactive = 0; s_minpend[0] = s_minpend[1] = 0x7F800000u; s_state = 0; s_mbox = 0; }
     int seenL[G], seenG[G], rb[G], re[G];
     float pend[G];
+    unsigned hasrem = 0;                                 // bit k: vertex k has arcs that leave the range
 #pragma unroll
     for (int k = 0; k < G; ++k) {
-        const int v = v0 + ((k * 32 + warp) << 5) + lane;
+        const int v = v0 + k * SSSP_OW + tid;
+        const bool in = owner && v < n;
         seenL[k] = 0; seenG[k] = 0;
         pend[k] = ST_INF;
-        rb[k] = v < n ? __ldg(row_ptr + v) : 0;
-        re[k] = v < n ? __ldg(row_ptr + v + 1) : 0;
+        rb[k] = in ? __ldg(row_ptr + v) : 0;
+        re[k] = in ? __ldg(row_ptr + v + 1) : 0;
+        for (int a = rb[k]; a < re[k]; ++a)
+            if ((unsigned)(__ldg(col + a) - v0) >= (unsigned)VB) hasrem |= 1u << k;
     }
-    auto rd = [&](int u) -> float {                     // current distance of u: shared if it is ours, L2 otherwise
-        const unsigned lu = (unsigned)(u - v0);
-        return lu < (unsigned)VB ? sdist[lu] : __ldcg(dist + u);
-    };
-    float T = delta;
-    for (unsigned chunk = 0;; ++chunk) {
-        bool consumed = false;
-        for (int pass = 0; pass < npass; ++pass) {
-            unsigned wokeG = 0;                              // bit k: group k has a lane whose GLOBAL counter moved (per lane)
+    __syncthreads();
+    volatile float *vdist = sdist;
+    volatile int *vflag = sflag;
+    volatile int *vnact = &s_nactive;
+    volatile unsigned *vbits = rbits;
+    volatile int *vmbox = &s_mbox;
+    float T = 0.f;
+    int epoch = 0;
+    int epoch_prev = -1;
+    unsigned long long t_epoch_wake = 0;
+    int mb_seen = -1;                                    // notification count of our mailbox that has been consumed (-1: look at the counters once)
+    unsigned n_relax = 0, n_acc = 0, n_remote = 0;
+    long long ph[4] = {0, 0, 0, 0};
+    const long long t_begin = clock64();
+
+    // One relaxation of local vertex lv (arcs [b, e)); gw: its global counter moved, remote arcs are evaluated too.
+    // pd (in/out): the vertex' parked candidate -- a realisable path length, possibly through a remote neighbour, so it
+    // takes part in the minimum even when only the local arcs are walked.
+    auto relax = [&](int lv, int b, int e, bool gw, bool rem, float &pd) -> bool {
+        ++n_relax;
+        const float cur = vdist[lv];
+        float best = fminf(cur, pd);
+        pd = ST_INF;
+        for (int a = b; a < e; a += 4) {
+            int u[4]; float ww[4];
 #pragma unroll
-            for (int k = 0; k < G; ++k) {
-                const int v = v0 + ((k * 32 + warp) << 5) + lane;
-                const int cnt = v < n ? __ldcg(dirty + v) : seenG[k];
-                if (cnt != seenG[k]) wokeG |= 1u << k;
-                seenG[k] = cnt;
+            for (int i = 0; i < 4; ++i) {
+                const bool in = a + i < e;
+                u[i] = in ? __ldg(col + a + i) : -1;
+                ww[i] = in ? __ldg(w + a + i) : 0.f;
             }
-            if (__any_sync(0xffffffffu, wokeG != 0)) __threadfence();      // counter observed -> the remote distance behind it is visible
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (u[i] < 0) continue;
+                const unsigned lu = (unsigned)(u[i] - v0);
+                float du = ST_INF;
+                if (lu < (unsigned)VB) du = vdist[lu];
+                else if (gw) du = __ldcg(dist + u[i]);
+                best = fminf(best, __fadd_rn(du, ww[i]));
+            }
+        }
+        if (!(best < cur)) return false;
+        if (best > T) { pd = best; return false; }       // parked until the threshold reaches it
+        ++n_acc;
+        vdist[lv] = best;
+        __stcg(dist + v0 + lv, best);
+        if ((flags & 4) && v0 + lv < (1 << 20)) g_sssp_tfinal[v0 + lv] = (unsigned)(global_timer() >> 3);
+        __threadfence_block();                           // the new distance is visible in the CTA before any counter of it moves
+        // local neighbours that can still improve through this vertex (d + w < d[u]) are woken right away; the remote ones
+        // are notified by the publisher warps (bit in rbits): the wave inside the range never waits for L2
+        for (int a = b; a < e; a += 4) {
+            int u[4]; float c[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in = a + i < e;
+                u[i] = in ? __ldg(col + a + i) : -1;
+                c[i] = in ? __fadd_rn(best, __ldg(w + a + i)) : ST_INF;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned lu = (unsigned)(u[i] - v0);
+                if (u[i] >= 0 && lu < (unsigned)VB && c[i] < vdist[lu]) atomicAdd(sflag + lu, 1);
+            }
+        }
+        if (rem) atomicOr(rbits + (lv >> 5), 1u << (lv & 31));
+        return true;
+    };
+
+    // Remote notifications of local vertex lv at its CURRENT distance (several improvements since the last call are one
+    // notification): counters of the remote vertices it can still improve (relaxed), then one release-add per owner mailbox.
+    auto publish = [&](int lv) {
+        const int b = __ldg(row_ptr + v0 + lv), e = __ldg(row_ptr + v0 + lv + 1);
+        const float d = vdist[lv];
+        unsigned long long rmask = 0ull;
+        bool rover = false;
+        for (int a = b; a < e; a += 4) {
+            int u[4]; float c[4], du[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool in = a + i < e;
+                u[i] = in ? __ldg(col + a + i) : -1;
+                c[i] = in ? __fadd_rn(d, __ldg(w + a + i)) : ST_INF;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {               // the remote distances of the four arcs are in flight together
+                const unsigned lu = (unsigned)(u[i] - v0);
+                du[i] = (u[i] >= 0 && lu >= (unsigned)VB) ? __ldcg(dist + u[i]) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned lu = (unsigned)(u[i] - v0);
+                if (u[i] >= 0 && lu >= (unsigned)VB && c[i] < du[i]) {
+                    atomicAdd(dirty + u[i], 1);
+                    if (a + i - b < 64) rmask |= 1ull << (a + i - b); else rover = true;
+                }
+            }
+        }
+        if (!(rmask || rover)) return;
+        ++n_remote;
+        int lastX = -1;
+        for (int a = b; a < e; ++a) {
+            const int i = a - b;
+            if (i < 64 && !((rmask >> i) & 1ull)) continue;
+            const int u = __ldg(col + a);
+            if ((unsigned)(u - v0) < (unsigned)VB) continue;
+            const int X = u / VB;
+            if (X == lastX) continue;                    // (a repeated bump of the same mailbox would only cost the owner another look)
+            lastX = X;
+            const int old = atom_add_release(ctl->mbox + X, 4);
+            if (old & 1) {                               // the owner is idle: wake it and take it out of the idle count of its epoch
+                const int old2 = atomicAnd(ctl->mbox + X, ~3);
+                if (old2 & 1) atomicSub(&ctl->idle_count[(old2 >> 1) & 1], 1);
+            }
+        }
+    };
+
+    for (int round = 0;; ++round) {
+        // epoch / threshold (they only change while every CTA is idle)
+        {
+            const unsigned long long et = *(volatile unsigned long long *)&ctl->epoch_T;
+            epoch = (int)(et >> 32);
+            T = __uint_as_float((unsigned)et);
+        }
+        bool did = false;
+        long long t0 = clock64();
+        if (epoch != epoch_prev) { epoch_prev = epoch; t_epoch_wake = global_timer(); }
+        // One polling loop per round, left only when the whole CTA is quiet: no warp has found work for two polls, the
+        // publish bitmap is empty and the mailbox count every warp has acted on is the current one.  Warps that have left
+        // wait at the barrier below -- deaf to their wake-up counters -- so leaving must be rare.
+        if (owner) {
+            bool awake = false;                          // this warp is counted in s_nactive
+            int quiet = 0;
             for (int q = 0; q < nlocal; ++q) {
-                bool any = false;
+                bool woke[G];
+                bool anyw_lane = false;
 #pragma unroll
                 for (int k = 0; k < G; ++k) {
-                    const int lv = ((k * 32 + warp) << 5) + lane;
-                    const int v = v0 + lv;
-                    const int cnt = *(volatile int *)(sflag + lv);
-                    const bool woke = v < n && (cnt != seenL[k] || ((wokeG >> k) & 1u) || pend[k] <= T);
+                    const int lv = k * SSSP_OW + tid;
+                    const int cnt = vflag[lv];
+                    woke[k] = v0 + lv < n && (cnt != seenL[k] || pend[k] <= T);
                     seenL[k] = cnt;
-                    unsigned mask = __ballot_sync(0xffffffffu, woke);
-                    if (!mask) continue;
-                    any = true;
-                    if (woke) pend[k] = ST_INF;
-                    while (mask) {            // woken vertices one after the other, each relaxed by the whole warp
-                        const int l = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int lvv = ((k * 32 + warp) << 5) + l;
-                        const int vv = v0 + lvv;
-                        const int b = __shfl_sync(0xffffffffu, rb[k], l), e = __shfl_sync(0xffffffffu, re[k], l);
-                        const float cur = sdist[lvv];
-                        float best = cur;
-                        int u0 = -1, u1 = -1;
-                        float c0 = ST_INF, c1 = ST_INF, d0 = 0.f, d1 = 0.f, ww0 = 0.f, ww1 = 0.f;
-                        if (b + lane < e) { u0 = __ldg(col + b + lane); ww0 = __ldg(w + b + lane); d0 = rd(u0); c0 = __fadd_rn(d0, ww0); }
-                        if (b + 32 + lane < e) { u1 = __ldg(col + b + 32 + lane); ww1 = __ldg(w + b + 32 + lane); d1 = rd(u1); c1 = __fadd_rn(d1, ww1); }
-                        best = fminf(best, fminf(c0, c1));
-                        for (int a = b + 64 + lane; a < e; a += 32) best = fminf(best, __fadd_rn(rd(__ldg(col + a)), __ldg(w + a)));
-                        for (int o = 16; o; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
-                        if (best < cur) {
-                            if (best <= T) {
-                                consumed = true;
-                                if (lane == 0) { sdist[lvv] = best; __stcg(dist + vv, best); }
-                                __threadfence_block();
-                                __syncwarp();
-                                __threadfence_block();
-                                // u can only improve through vv if d[vv] + w < d[u]
-                                bool remote = false;
-                                auto notify = [&](int u, float ww, float du) {
-                                    if (u < 0 || !(__fadd_rn(best, ww) < du)) return;
-                                    const unsigned lu = (unsigned)(u - v0);
-                                    if (lu < (unsigned)VB) atomicAdd(sflag + lu, 1);
-                                    else remote = true;
-                                };
-                                notify(u0, ww0, d0);
-                                notify(u1, ww1, d1);
-                                for (int a = b + 64 + lane; a < e; a += 32) { const int u = __ldg(col + a); notify(u, __ldg(w + a), rd(u)); }
-                                if (__any_sync(0xffffffffu, remote)) {
-                                    __threadfence();          // the improvement is visible device-wide before a remote owner is woken
-                                    auto notify_remote = [&](int u, float ww, float du) {
-                                        if (u < 0 || !(__fadd_rn(best, ww) < du)) return;
-                                        if ((unsigned)(u - v0) >= (unsigned)VB) atomicAdd(dirty + u, 1);
-                                    };
-                                    notify_remote(u0, ww0, d0);
-                                    notify_remote(u1, ww1, d1);
-                                    for (int a = b + 64 + lane; a < e; a += 32) { const int u = __ldg(col + a); notify_remote(u, __ldg(w + a), __ldcg(dist + u)); }
-                                }
-                            } else if (lane == l) {
-                                pend[k] = best;       // parked until the threshold reaches it (or a neighbour wakes it again)
-                            }
+                    anyw_lane |= woke[k];
+                }
+                if (__any_sync(0xffffffffu, anyw_lane)) {
+                    if (!awake) { awake = true; if (lane == 0) atomicAdd(&s_nactive, 1); }
+#pragma unroll
+                    for (int k = 0; k < G; ++k)
+                        if (woke[k] && relax(k * SSSP_OW + tid, rb[k], re[k], false, (hasrem >> k) & 1u, pend[k])) did = true;
+                    quiet = 0;
+                    continue;
+                }
+                // the mailbox count as the publisher warp last saw it: new remote notifications -> look at our vertices' counters
+                const int mbx = __shfl_sync(0xffffffffu, *vmbox, 0);
+                if (mbx != mb_seen) {
+                    if (!awake) { awake = true; if (lane == 0) atomicAdd(&s_nactive, 1); }
+                    mb_seen = mbx;
+                    int cg[G];
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        const int v = v0 + k * SSSP_OW + tid;
+                        cg[k] = v < n ? __ldcg(dirty + v) : seenG[k];
+                    }
+#pragma unroll
+                    for (int k = 0; k < G; ++k) {
+                        const int lv = k * SSSP_OW + tid;
+                        if (cg[k] != seenG[k]) {
+                            seenG[k] = cg[k];
+                            seenL[k] = vflag[lv];
+                            relax(lv, rb[k], re[k], true, (hasrem >> k) & 1u, pend[k]);
+                            did = true;                  // (a consumed notification counts as work: the round is not quiescent)
                         }
                     }
+                    quiet = 0;
+                    continue;
                 }
-                wokeG = 0;
-                if (!any) break;                    // nothing moved in this warp's groups: back to the global poll
+                if (awake) { awake = false; __syncwarp(); if (lane == 0) atomicSub(&s_nactive, 1); }
+                const int na = __shfl_sync(0xffffffffu, *vnact, 0);
+                quiet = na == 0 ? quiet + 1 : 0;
+                if (quiet >= 2) break;
             }
-        }
-        float pmin = ST_INF;
+            if (awake) { __syncwarp(); if (lane == 0) atomicSub(&s_nactive, 1); }
+            float pmin = ST_INF;
 #pragma unroll
-        for (int k = 0; k < G; ++k) pmin = fminf(pmin, pend[k]);
-        for (int o = 16; o; o >>= 1) pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
-        if (lane == 0 && pmin < ST_INF) atomicMin(&ctl->min_pend[chunk % 3], __float_as_uint(pmin));
-        if (__syncthreads_or(consumed) && threadIdx.x == 0) atomicOr(&ctl->changed[chunk % 3], 1u);
-        if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->changed[(chunk + 1) % 3] = 0; ctl->min_pend[(chunk + 1) % 3] = 0x7F800000u; }
-        grid_barrier(&ctl->barrier, phase);
-        const unsigned anyc = *(volatile unsigned *)&ctl->changed[chunk % 3];
-        const unsigned mp = *(volatile unsigned *)&ctl->min_pend[chunk % 3];
-        if (!anyc) {
-            if (mp == 0x7F800000u) {
-                if (blockIdx.x == 0 && threadIdx.x == 0) ctl->chunks = chunk + 1;
-                break;
+            for (int k = 0; k < G; ++k) pmin = fminf(pmin, pend[k]);
+            for (int o = 16; o; o >>= 1) pmin = fminf(pmin, __shfl_xor_sync(0xffffffffu, pmin, o));
+            if (lane == 0 && pmin < ST_INF) atomicMin(&s_minpend[round & 1], __float_as_uint(pmin));
+        } else {
+            // publisher warps: keep the CTA's copy of the mailbox count current and drain the publish bitmap (lane = one word)
+            const int wi = tid - SSSP_OW;
+            bool awake = false;
+            int quiet = 0;
+            for (int q = 0; q < nlocal; ++q) {
+                if (wi == 0) {
+                    const int mbc = *(volatile int *)mybox >> 2;
+                    if (mbc != *vmbox) { *vmbox = mbc; did = true; }
+                }
+                bool found = false;                      // (only the words this warp drains: the other publisher warp may already have left the round)
+                for (int j = ((tid - SSSP_OW) >> 5) + 2 * lane; j < NW; j += 64) found |= vbits[j] != 0u;
+                if (__any_sync(0xffffffffu, found)) {
+                    if (!awake) { awake = true; if (lane == 0) atomicAdd(&s_nactive, 1); }
+                    // a word = 32 consecutive vertices = the ones that improve together: the warp takes one word at a time,
+                    // lane i publishes vertex i of it
+                    const int pw = (tid - SSSP_OW) >> 5;
+                    for (int j = pw; j < NW; j += (1024 - SSSP_OW) / 32) {
+                        unsigned bits = 0;
+                        if (lane == 0 && vbits[j] != 0u) bits = atomicExch(rbits + j, 0u);
+                        bits = __shfl_sync(0xffffffffu, bits, 0);
+                        if ((bits >> lane) & 1u) publish(j * 32 + lane);
+                    }
+                    did = true;
+                    quiet = 0;
+                    continue;
+                }
+                if (awake) { awake = false; __syncwarp(); if (lane == 0) atomicSub(&s_nactive, 1); }
+                const int na = __shfl_sync(0xffffffffu, *vnact, 0);
+                quiet = na == 0 ? quiet + 1 : 0;
+                if (quiet >= 2) break;
             }
-            T = fmaxf(T, __uint_as_float(mp)) + delta;
-        } else if (adv && mp != 0x7F800000u) {
-            T = fmaxf(T, __uint_as_float(mp) + delta);
+            if (awake) { __syncwarp(); if (lane == 0) atomicSub(&s_nactive, 1); }
         }
+        { const long long t = clock64(); ph[0] += t - t0; t0 = t; }
+        __syncthreads();
+        // a warp that left before the last mailbox update has not looked at its counters for it: not quiescent
+        const int mb_final = *vmbox;
+        if (owner && mb_seen != mb_final) did = true;
+        const int anyw = __syncthreads_or(did);
+        const unsigned mp = s_minpend[round & 1];
+        if (tid == 0) s_minpend[(round + 1) & 1] = 0x7F800000u;
+        __syncthreads();
+        { const long long t = clock64(); ph[2] += t - t0; t0 = t; }
+        if (anyw) continue;
+        // nothing moved below T: publish the smallest parked candidate and go idle (see the kernel comment)
+        if (tid == 0) {
+            const int par = epoch & 1;
+            if (mp != 0x7F800000u) atomicMin(&ctl->gmin[par], mp);
+            const int old = atomicOr(mybox, 1 | (par << 1));
+            if ((old >> 2) != mb_final) {
+                // a notification arrived before the idle bit: back to work.  If a notifier has already cleared the bit it
+                // has also taken us out of the count -- which we never entered
+                const int old2 = atomicAnd(mybox, ~3);
+                if (!(old2 & 1)) atomicAdd(&ctl->idle_count[par], 1);
+                s_state = 0;
+            } else if (atom_add_release(&ctl->idle_count[par], 1) == NB - 1) {
+                // every CTA is idle in this epoch and no notification is pending: next threshold, or the fixed point
+                const unsigned gm = atomicExch(&ctl->gmin[par], 0x7F800000u);
+                if (gm == 0x7F800000u) {
+                    *(volatile unsigned long long *)&ctl->epoch_T = (unsigned long long)ST_EPOCH_DONE << 32;
+                    s_state = 1;
+                } else {
+                    const float Tn = fmaxf(T, __uint_as_float(gm)) + delta;
+                    if ((flags & 4) && epoch < 1024) {
+                        g_sssp_epoch_log[epoch][0] = global_timer();
+                        g_sssp_epoch_log[epoch][1] = blockIdx.x;
+                        g_sssp_epoch_log[epoch][2] = (unsigned long long)round;
+                        g_sssp_epoch_log[epoch][3] = t_epoch_wake;
+                    }
+                    *(volatile unsigned long long *)&ctl->epoch_T = ((unsigned long long)(unsigned)(epoch + 1) << 32) | __float_as_uint(Tn);
+                    const int old2 = atomicAnd(mybox, ~3);
+                    if (old2 & 1) atomicSub(&ctl->idle_count[(old2 >> 1) & 1], 1);
+                    s_state = 0;
+                }
+            } else {
+                for (;;) {
+                    const int mb = *(volatile int *)mybox;
+                    const int ep = (int)(*(volatile unsigned long long *)&ctl->epoch_T >> 32);
+                    if (ep == ST_EPOCH_DONE) { s_state = 1; break; }
+                    if (!(mb & 1)) { s_state = 0; break; }                                        // woken by a notifier
+                    if (ep != epoch) {                                                              // next threshold
+                        const int old2 = atomicAnd(mybox, ~3);
+                        if (old2 & 1) atomicSub(&ctl->idle_count[(old2 >> 1) & 1], 1);
+                        s_state = 0;
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+            }
+            if (blockIdx.x == 0) ctl->rounds = round + 1;
+        }
+        __syncthreads();
+        { const long long t = clock64(); ph[3] += t - t0; t0 = t; }
+        if (s_state == 1) break;
+    }
+    // diagnostics
+    for (int o = 16; o; o >>= 1) {
+        n_relax += __shfl_xor_sync(0xffffffffu, n_relax, o);
+        n_acc += __shfl_xor_sync(0xffffffffu, n_acc, o);
+        n_remote += __shfl_xor_sync(0xffffffffu, n_remote, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&ctl->stats[0], (unsigned long long)n_relax);
+        atomicAdd(&ctl->stats[1], (unsigned long long)n_acc);
+        atomicAdd(&ctl->stats[2], (unsigned long long)n_remote);
+    }
+    if (blockIdx.x == 0 && tid == 0) ctl->stats[3] = (unsigned long long)epoch + 1;
+    if (tid == 0) {
+        const unsigned long long tot = (unsigned long long)(clock64() - t_begin);
+        for (int i = 0; i < 4; ++i) atomicAdd(&ctl->phase[i], (unsigned long long)ph[i]);
+        atomicAdd(&ctl->phase[4], tot);
+        atomicMax(&ctl->phase[5], (unsigned long long)(ph[0] + ph[1] + ph[2]));      // busiest CTA: cycles outside the idle spin
     }
 }
 
@@ -643,17 +912,19 @@ __global__ void k_set_pred_sources_orig(int32_t *pred, const int32_t *__restrict
     if (i < ns) pred[orig[sources[i]]] = -1;
 }
 
+constexpr int ST_SSSP_MAX_CTAS = 960;      // idle flags of k_sssp_blob in the workspace tail (4 KB)
+
 template <int G>
-static int launch_sssp_local(int blocks_needed, int device, void **args, cudaStream_t s, bool &launched) {
-    const size_t smem = (size_t)8 * 1024 * G;
+static int launch_sssp_blob(int blocks_needed, int device, void **args, cudaStream_t s, bool &launched) {
+    const size_t smem = (size_t)8 * SSSP_OW * G + 4 * (size_t)((SSSP_OW * G + 31) / 32);
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute((const void *)k_sssp_local<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    if (!attr) { ST_CHECK_CUDA(cudaFuncSetAttribute((const void *)k_sssp_blob<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     int per_sm = 0, sms = 0;
-    ST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_sssp_local<G>, 1024, smem));
+    ST_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k_sssp_blob<G>, 1024, smem));
     ST_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     launched = false;
     if (per_sm * sms < blocks_needed) return ST_OK;
-    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_local<G>, dim3(blocks_needed), dim3(1024), args, smem, s));
+    ST_CHECK_CUDA(cudaLaunchCooperativeKernel((const void *)k_sssp_blob<G>, dim3(blocks_needed), dim3(1024), args, smem, s));
     launched = true;
     return ST_OK;
 }
@@ -664,7 +935,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     cudaStream_t s = (cudaStream_t)stream;
     if (sweeps_host) *sweeps_host = 0;
     if (n == 0) return ST_OK;
-    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (256 + 16n bytes) required");
+    ST_REQUIRE(ctl_workspace != nullptr, "ctl_workspace (4608 + 16n bytes) required");
     int device = 0;
     ST_CHECK_CUDA(cudaGetDevice(&device));
     SsspCtl *ctl = (SsspCtl *)ctl_workspace;
@@ -700,23 +971,35 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
     // near-far counter variant: poll state in registers when every resident warp can own its vertices there, in global
     // memory otherwise (ctl_workspace holds dirty[n], seen[n], pend[n]); ST_SSSP_FLAGS=1 forces the old flag variant
     const bool small = (int64_t)blocks * 8 * SSSP_G * 32 >= n && !getenv("ST_SSSP_FORCE_BIG");      // (env: tests exercise the large-graph kernel)
-    // CTA-local propagation (k_sssp_local): the smallest range per CTA for which the whole graph is resident
+    // CTA-local propagation (k_sssp_blob): the smallest range per CTA for which the whole graph is resident
     bool local_done = false;
-    if (!getenv("ST_SSSP_NO_LOCAL") && !getenv("ST_SSSP_FORCE_BIG") && !getenv("ST_SSSP_FLAGS")) {
-        int nlocal = 8;
-        if (const char *e = getenv("ST_SSSP_NLOCAL")) { int v = atoi(e); if (v >= 1 && v <= 256) nlocal = v; }
-        void *largs[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&ctl, (void *)&delta,
-                         (void *)&npass, (void *)&adv, (void *)&nlocal};
+    // Opt-in (ST_SSSP_LOCAL=1): measured on the bench tree 13 ms against 4.4 ms of k_sssp -- a hop inside a range costs ~7 us
+    // (the two walks over a vertex' arcs through L1/L2), a hop across a range boundary ~80 us, and every epoch waits for
+    // its slowest range (profiles/README.md, tools/sssp_trace.py).
+    const char *loc_env = getenv("ST_SSSP_LOCAL");
+    if (loc_env && atoi(loc_env) != 0 && !getenv("ST_SSSP_FORCE_BIG") && !getenv("ST_SSSP_FLAGS")) {
+        int nlocal = 1 << 30;                 // cap of the polls per round (a round ends when the CTA is quiet; tests force short rounds)
+        if (const char *e = getenv("ST_SSSP_NLOCAL")) { int v = atoi(e); if (v >= 1) nlocal = v; }
+        float bdelta = delta;                 // threshold step per epoch (any value is exact)
+        if (const char *e = getenv("ST_SSSP_BLOB_DELTA")) { float v = (float)atof(e); if (v > 0.f) bdelta = v; }
+        SsspBlobCtl *bctl = (SsspBlobCtl *)((char *)ctl_workspace + 256 + 16 * (size_t)n);
+        int bflags = 0;
+        if (const char *e = getenv("ST_SSSP_BLOB_FLAGS")) bflags = atoi(e);
+        void *largs[] = {(void *)&row_ptr, (void *)&col, (void *)&w, (void *)&nn, (void *)&dist, (void *)&dirty, (void *)&bctl, (void *)&bdelta,
+                         (void *)&nlocal, (void *)&bflags};
         int gsel = 0;
         if (const char *e = getenv("ST_SSSP_LOCAL_G")) gsel = atoi(e);
         for (int G : {1, 2, 4, 8}) {
             if (local_done || (gsel && G != gsel)) continue;
-            const int need = (int)cdiv(n, 1024 * (int64_t)G);
+            const int need = (int)cdiv(n, SSSP_OW * (int64_t)G);
+            if (need > ST_SSSP_MAX_CTAS) continue;
+            k_sssp_blob_init<<<1, 256, 0, s>>>(bctl, need, bdelta);
+            ST_CHECK_LAUNCH();
             int rc2 = ST_OK;
-            if (G == 1) rc2 = launch_sssp_local<1>(need, device, largs, s, local_done);
-            else if (G == 2) rc2 = launch_sssp_local<2>(need, device, largs, s, local_done);
-            else if (G == 4) rc2 = launch_sssp_local<4>(need, device, largs, s, local_done);
-            else rc2 = launch_sssp_local<8>(need, device, largs, s, local_done);
+            if (G == 1) rc2 = launch_sssp_blob<1>(need, device, largs, s, local_done);
+            else if (G == 2) rc2 = launch_sssp_blob<2>(need, device, largs, s, local_done);
+            else if (G == 4) rc2 = launch_sssp_blob<4>(need, device, largs, s, local_done);
+            else rc2 = launch_sssp_blob<8>(need, device, largs, s, local_done);
             if (rc2) return rc2;
         }
     }
@@ -760,6 +1043,7 @@ extern "C" int st_sssp(const int32_t *row_ptr, const int32_t *col, const float *
         unsigned chunks = 0;
         ST_CHECK_CUDA(cudaMemcpyAsync(&chunks, &ctl->chunks, 4, cudaMemcpyDeviceToHost, s));
         ST_CHECK_CUDA(cudaStreamSynchronize(s));
+        if (local_done) ST_CHECK_CUDA(cudaMemcpy(&chunks, &((SsspBlobCtl *)((char *)ctl_workspace + 256 + 16 * (size_t)n))->rounds, 4, cudaMemcpyDeviceToHost));
         *sweeps_host = (int32_t)chunks;
     }
     return ST_OK;
@@ -1014,6 +1298,26 @@ extern "C" int st_repair_branches(float *nodes, const int32_t *row, const int32_
 }
 
 // debug only: [chunks, evaluations, improvements, wakeups(unused), lane-mode groups] of the last st_sssp on this workspace
+extern "C" int st_debug_sssp_blob_stats(const void *ctl_workspace, int64_t n, unsigned long long *out_host) {
+    const SsspBlobCtl *c = (const SsspBlobCtl *)((const char *)ctl_workspace + 256 + 16 * (size_t)n);
+    ST_CHECK_CUDA(cudaMemcpy(out_host, c->stats, sizeof(unsigned long long) * 4, cudaMemcpyDeviceToHost));
+    int r = 0;
+    ST_CHECK_CUDA(cudaMemcpy(&r, &c->rounds, 4, cudaMemcpyDeviceToHost));
+    out_host[4] = (unsigned long long)r;
+    ST_CHECK_CUDA(cudaMemcpy(out_host + 5, c->phase, sizeof(unsigned long long) * 6, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
+extern "C" int st_debug_sssp_epoch_log(unsigned long long *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_sssp_epoch_log, sizeof(unsigned long long) * 4096));
+    return ST_OK;
+}
+
+extern "C" int st_debug_sssp_tfinal(unsigned *out_host, int64_t n) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_sssp_tfinal, sizeof(unsigned) * (size_t)(n < (1 << 20) ? n : (1 << 20))));
+    return ST_OK;
+}
+
 extern "C" int st_debug_sssp_stats(const void *ctl_workspace, unsigned *out_host) {
     const SsspCtl *c = (const SsspCtl *)ctl_workspace;
     ST_CHECK_CUDA(cudaMemcpy(out_host, &c->chunks, sizeof(unsigned) * 5, cudaMemcpyDeviceToHost));

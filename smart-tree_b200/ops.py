@@ -535,7 +535,7 @@ def sssp(row_ptr, col, w, n, sources, want_sweeps=False, delta=0.0, orig_id=None
     dev = row_ptr.device
     dist = torch.empty(n, dtype=F32, device=dev)
     pred = torch.empty(n, dtype=I32, device=dev)
-    ctl = torch.empty(64 + 4 * n, dtype=I32, device=dev)      # control block + dirty[n] (+ seen[n], pend[n] for large graphs) + internal dist[n]
+    ctl = torch.empty(64 + 4 * n + 1088, dtype=I32, device=dev)      # control block + dirty[n] (+ seen[n], pend[n] for large graphs) + internal dist[n] + idle flags
     sweeps = C.c_int32(0)
     _count("sssp")
     _lib.check(lib.st_sssp(_ptr(row_ptr), _ptr(col), _ptr(w), n, _ptr(sources), sources.shape[0], float(delta), _ptr(dist), _ptr(pred),

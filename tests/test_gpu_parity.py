@@ -551,19 +551,25 @@ def test_connected_components_exact():
     assert sum(len(c) for c in comps) == len(med)
 
 
-@pytest.mark.parametrize("variant", ["cta-local", "cta-local-spatial", "cta-local-G8", "registers", "large-graph", "large-graph-flags"])
+@pytest.mark.parametrize("variant", ["cta-local", "cta-local-spatial", "cta-local-G8", "cta-local-threshold", "cta-local-1-poll", "registers", "large-graph",
+                                     "large-graph-flags"])
 def test_sssp_and_tree_distances_exact(variant, monkeypatch):
     """Every relaxation schedule reaches the same fp32 fixed point and predecessors: CTA-local propagation in shared memory
-    (default) in the caller's numbering or with the graph renumbered in spatial order (st_sssp orig_id), poll state in
-    registers, in global memory for graphs beyond the resident capacity, and the older flag variant."""
+    with barrier-free termination (k_sssp_blob, default) in the caller's numbering or with the graph renumbered in spatial
+    order (st_sssp orig_id), with per-CTA thresholds, poll state in registers (k_sssp), in global memory for graphs beyond
+    the resident capacity, and the older flag variant."""
     if variant in ("large-graph", "large-graph-flags"):
         monkeypatch.setenv("ST_SSSP_FORCE_BIG", "1")
     if variant == "large-graph-flags":
         monkeypatch.setenv("ST_SSSP_FLAGS", "1")
-    if variant == "registers":
-        monkeypatch.setenv("ST_SSSP_NO_LOCAL", "1")
+    if variant.startswith("cta-local"):
+        monkeypatch.setenv("ST_SSSP_LOCAL", "1")
     if variant == "cta-local-G8":
         monkeypatch.setenv("ST_SSSP_LOCAL_G", "8")
+    if variant == "cta-local-threshold":          # per-CTA distance-ordered acceptance (parked candidates)
+        monkeypatch.setenv("ST_SSSP_BLOB_DELTA", "0.05")
+    if variant == "cta-local-1-poll":
+        monkeypatch.setenv("ST_SSSP_NLOCAL", "1")
     ops = _ops()
     xyz, med, rad, e, w = _graph_case()
     comp = S.connected_components(len(med), e, 32)[0]

@@ -1,6 +1,7 @@
-"""Sweep of the SSSP schedule knobs (threshold advance rule, polls per barrier chunk, threshold step) on the bench
-workload: stage times of skel.sssp / skel.tree_dist per setting.  Any setting gives the same distances (tests)."""
-import itertools
+"""Sweep of the SSSP schedule knobs on the bench workload (C2): the CTA-local kernel (k_sssp_blob: vertices per CTA,
+local polls per round, optional per-CTA threshold step) against the register-resident near-far kernel (k_sssp).  Prints the
+median stage time of skel.sssp per setting and whether the distances are identical (they must be: any schedule reaches
+the same fp32 fixed point)."""
 import json
 import os
 import sys
@@ -21,31 +22,41 @@ W = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "s
 pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0.01, 4, 0.4, device=dev),
                 Skeletonizer(16, 0.02, 32, device=dev), repair_skeletons=True, smooth_skeletons=True, smooth_kernel_size=11,
                 prune_skeletons=True, min_skeleton_radius=0.01, min_skeleton_length=0.02, device=dev)
-tr = synth.make_tree(0, 1_000_000)
+tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
-for _ in range(2):
-    pipe.process_cloud(cloud=cloud)
+KNOBS = ("ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
+settings = [{}, {"ST_SSSP_SPATIAL": "1"}, {"ST_SSSP_LOCAL": "1"}, {"ST_SSSP_LOCAL": "1", "ST_SSSP_BLOB_DELTA": "0.25"},
+            {"ST_SSSP_PASSES": "32"}, {"ST_SSSP_PASSES": "128"}, {"ST_SSSP_DELTA": "0.06"}, {"ST_SSSP_DELTA": "0.25"}]
 ref = None
 rows = []
-settings = [dict(adv=0, passes=32, delta=0.5)]
-for adv, passes, delta in itertools.product([1, 0], [64, 128, 256], [0.015, 0.03, 0.06, 0.125]):
-    settings.append(dict(adv=adv, passes=passes, delta=delta))
 for s in settings:
-    os.environ["ST_SSSP_ADVANCE"] = str(s["adv"])
-    os.environ["ST_SSSP_PASSES"] = str(s["passes"])
-    os.environ["ST_SSSP_DELTA"] = str(s["delta"])
+    for k in KNOBS:
+        os.environ.pop(k, None)
+    os.environ.update(s)
+    pipe.skeletonizer = Skeletonizer(16, 0.02, 32, device=dev)      # (reads ST_SSSP_SPATIAL / ST_SSSP_LOCAL)
+    pipe.process_cloud(cloud=cloud)
     _timing.enable(True)
     _timing.RECORDS.clear(); _timing.SAMPLES.clear()
-    for _ in range(4):
+    for _ in range(5):
         pipe.process_cloud(cloud=cloud)
     torch.cuda.synchronize()
-    med = {k: float(np.median(v)) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.tree_dist", "skel.sample_tree")}
+    med = {k: round(float(np.median(v)), 3) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.tree_dist", "skel.regroup_csr")}
     _timing.enable(False)
     d = pipe.skeletonizer.last["dist"].clone()
+    p = pipe.skeletonizer.last["pred"].clone()
     if ref is None:
-        ref = d
-    same = bool(torch.equal(ref, d))
-    rows.append({**s, **med, "same_distances": same})
+        ref = (d, p)
+    import ctypes as C
+    from smart_tree_b200 import _lib, ops
+    st = (C.c_ulonglong * 11)()
+    lib = _lib.load()
+    lib.st_debug_sssp_blob_stats.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+    if "ST_SSSP_LOCAL" in s:
+        lib.st_debug_sssp_blob_stats(C.c_void_p(ops.LAST_SSSP_CTL.data_ptr()), int(d.shape[0]), st)
+    med["relax_accepted_remote_epochs_rounds"] = list(st)[:5]
+    ncta = max(1, -(-int(d.shape[0]) // (960 * int(s.get("ST_SSSP_LOCAL_G", 2)))))
+    med["avg_us_per_cta_local_global_barrier_idle_total"] = [round(x / ncta / 1965.0, 1) for x in list(st)[5:10]]
+    med["busiest_cta_busy_us"] = round(st[10] / 1965.0, 1)
+    rows.append({**s, **med, "same_distances_and_preds": bool(torch.equal(ref[0], d) and torch.equal(ref[1], p))})
     print(json.dumps(rows[-1]), flush=True)
-best = min(rows, key=lambda r: r["skel.sssp"])
-print("BEST", json.dumps(best))
+print("BEST", json.dumps(min(rows, key=lambda r: r["skel.sssp"])))

@@ -79,7 +79,8 @@ bst = (C.c_ulonglong * 16)()
 lib.st_debug_sample_batch_stats.argtypes = [C.c_void_p]
 lib.st_debug_sample_batch_stats(bst)
 bnames = ["rounds", "long_iterations", "batches", "members_offered", "accepted", "skipped", "cut_long_member", "cut_start_touched",
-          "cut_route_or_parent_touched", "claimed_points", "cycles_batches", "cycles_long"]
+          "cut_route_or_parent_touched", "cut_passed_over_entry_unclaimed", "cycles_batches", "cycles_long", "cycles_A_window_scan",
+          "cycles_BC_select_routes", "cycles_D_claim", "cluster_size"]
 batch_stats = {n: int(bst[i]) for i, n in enumerate(bnames)}
 names = ["find", "trace", "claim", "resolve", "finish"]
 cyc = {n: stats[i] for i, n in enumerate(names)}
