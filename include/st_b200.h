@@ -170,6 +170,22 @@ int st_conv_gather_inv(const float *in, int in_ld, const int32_t *up_sorted, con
                        const uint32_t *tile_mask, int64_t n_out, int ntaps, const float *w, int cin, int cout,
                        const float *scale, const float *shift, float *out, int out_ld, int act, void *stream);
 
+/* Brick variant of the sub-manifold 3x3x3 conv for the narrow level (cin 8 or 16, cout 8: level 0 of the UNet), no
+ * gather map.  Rows must be in (batch, Z-order) -- st_morton_perm order -- so that the voxels of an aligned 4x4x4 brick
+ * are contiguous rows; st_brick_plan_build derives, once per level, the brick table, a 1-byte window-cell code per row and
+ * a halo list per brick (occupied cells of the 6x6x6 window outside the brick, found through the level's hash table).
+ * st_conv_brick then stages each brick's window in shared memory and computes the same result as st_conv_gather with
+ * the level's st_subm_map (unbounded grid: no strict_spconv_bounds), including the fused epilogue.
+ * st_brick_plan_info: [0] bricks, [1] halo entries, [2] status -- nonzero if the rows are not strictly increasing in
+ * (batch, Z-order) (the plan is then unusable).      replaces spconv SubMConv3d  smart_tree/model/model_blocks.py:8-38,107-156 */
+size_t st_brick_plan_bytes(int64_t n);
+int st_brick_plan_build(const int32_t *coords, int64_t n, const uint64_t *keys, const int32_t *vals, int64_t capacity,
+                        void *plan, size_t plan_bytes, void *stream);
+int st_brick_plan_info(const void *plan, int64_t n, int32_t *info_host);
+int st_conv_brick(const float *in, int in_ld, const void *plan, int64_t n, const float *w /* [27, cin, 8] */, int cin,
+                  int cout, const float *scale, const float *shift, const float *residual, int res_ld, const float *in2,
+                  int in2_ld, const float *w2, int cin2, float *out, int out_ld, int act, void *stream);
+
 /* Tensor-core variant (tcgen05.mma kind::tf32 with a 3xTF32 split, accumulators in TMEM).  Same
  * contract as st_conv_gather except that `wprep` is the weight tensor pre-arranged by
  * st_conv_tc_prepare (st_conv_tc_weight_floats(ntaps,cin,cout) floats; -1 = unsupported channel

@@ -46,6 +46,11 @@ SIGNATURES = {
                                  _p, C.c_int, _p, C.c_int, _p, C.c_int, C.c_int, _p]),
     "st_stem_conv": (C.c_int, [_p, C.c_int, _p, _i64, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p]),
     "st_conv_gather_inv": (C.c_int, [_p, C.c_int, _p, _p, _p, _i64, C.c_int, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, C.c_int, _p]),
+    "st_brick_plan_bytes": (_sz, [_i64]),
+    "st_brick_plan_build": (C.c_int, [_p, _i64, _p, _p, _i64, _p, _sz, _p]),
+    "st_brick_plan_info": (C.c_int, [_p, _i64, _p]),
+    "st_conv_brick": (C.c_int, [_p, C.c_int, _p, _i64, _p, C.c_int, C.c_int, _p, _p, _p, C.c_int, _p, C.c_int, _p, C.c_int, _p, C.c_int,
+                                C.c_int, _p]),
     "st_conv_tc_weight_floats": (_i64, [C.c_int, C.c_int, C.c_int]),
     "st_conv_tc_prepare": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p]),
     "st_conv_tc_weight_floats_fused": (_i64, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libst_b200.so")
-SOURCES = ["voxel.cu", "blocks.cu", "conv.cu", "conv_tc.cu", "knn.cu", "graph.cu", "sample.cu", "post.cu"]
+SOURCES = ["voxel.cu", "blocks.cu", "conv.cu", "conv_brick.cu", "conv_tc.cu", "knn.cu", "graph.cu", "sample.cu", "post.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "550,177,39,179"] + os.environ.get("ST_NVCC_EXTRA", "").split()
 

@@ -83,16 +83,25 @@ class LevelIndex:
     """Coordinate table and gather maps of one resolution level.  `spatial_shape` (int32 device tensor (z,y,x), optional):
     the shape spconv would bound-check neighbour locations against -- strict_spconv_bounds, see build_levels."""
 
-    def __init__(self, coords, spatial_shape=None):
+    def __init__(self, coords, spatial_shape=None, brick=False):
+        """brick: the rows are in (batch, Z-order) and the level's 3x3x3 convs run on 4x4x4 bricks (ops.brick_plan); the
+        [27, n] gather map is then only built if somebody asks for it (`nbr`)."""
         self.coords = coords
         self.n = coords.shape[0]
         self.spatial_shape = spatial_shape
         self.table = ops.CoordTable(coords)
-        self.nbr = ops.subm_map(coords, self.table, spatial_shape)
+        self.brick = ops.brick_plan(coords, self.table) if (brick and spatial_shape is None and self.n > 0) else None
+        self._nbr = None if self.brick is not None else ops.subm_map(coords, self.table, spatial_shape)
         self.down = None
         self.up = None
         self.child = None
         self._plans = {}
+
+    @property
+    def nbr(self):
+        if self._nbr is None:
+            self._nbr = ops.subm_map(self.coords, self.table, self.spatial_shape)
+        return self._nbr
 
     def up_map(self):
         """The unsorted `up` map (built on demand when the level was indexed with the parity-sorted plan only)."""
@@ -125,12 +134,12 @@ def declared_spatial_shape(coords: torch.Tensor) -> torch.Tensor:
 
 
 def build_levels(coords: torch.Tensor, depth: int, morton: bool = False, inverse_plan: bool = False,
-                 spatial_shape: torch.Tensor = None) -> List[LevelIndex]:
+                 spatial_shape: torch.Tensor = None, brick0: bool = False) -> List[LevelIndex]:
     """Index structures of every level.  With `spatial_shape` (strict_spconv_bounds) the maps reproduce spconv's bound
     checks against the declared shape: neighbour locations >= shape are invisible to the sub-manifold convs and strided
     outputs >= out_shape = (shape - 1) // 2 + 1 are never created; each level passes its out_shape on as the next
     level's shape, as spconv does.  Default (None): unbounded grid."""
-    levels = [LevelIndex(coords, spatial_shape)]
+    levels = [LevelIndex(coords, spatial_shape, brick=brick0 and morton)]
     for _ in range(depth - 1):
         cur = levels[-1]
         out_shape = None
@@ -171,6 +180,10 @@ class SmartTreeEngine:
         self.eps = eps
         self.conv_impl = conv_impl
         self.morton = bool(int(os.environ.get("ST_MORTON", "1")))
+        # level-0 sub-manifold convs (8 / 16 -> 8 channels) on 4x4x4 bricks staged in shared memory instead of a gather map
+        # (conv_brick.cu).  Opt-in (ST_CONV_BRICK=1 or conv_impl="brick"): first measurement 128 us per 8 -> 8 launch against
+        # 72 us of the gather-map kernel -- one warp per brick at 24 warps per SM is latency bound (profiles/README.md)
+        self.brick_convs = bool(int(os.environ.get("ST_CONV_BRICK", "0"))) or conv_impl == "brick"
         self.inverse_sorted = bool(int(os.environ.get("ST_INVERSE_SORTED", "1")))
         dev = self.device
         self.stem = ConvLayer(_conv_w(sd["input_conv.sequence.0.weight"]),
@@ -238,6 +251,11 @@ class SmartTreeEngine:
         tile-plan path (source rows staged in shared memory)."""
         taps, cin, cout = layer.w.shape
         impl, plan = "fma", None
+        if (which == "nbr" and lv is not None and getattr(lv, "brick", None) is not None and self.conv_impl in ("auto", "brick")
+                and ops.conv_brick_supported(taps, cin, cout)):
+            return ops.conv_brick(x, lv.brick, layer.w, n_out, layer.scale, layer.shift, residual=residual, in2=in2, w2=w2, out=out, relu=relu)
+        if taps > 1 and nbr is None and which == "nbr" and lv is not None:
+            nbr = lv.nbr
         if taps > 1:
             if self.conv_impl == "tp" and lv is not None and ops.conv_tp_supported(taps, cin, cout):
                 if which == "up" and nbr is None:
@@ -265,10 +283,11 @@ class SmartTreeEngine:
 
     def _resblock_run(self, x, rb: ResBlockPlan, lv, out):
         n = x.shape[0]
-        t = self._conv(x, rb.c1, lv.nbr, n, relu=True, lv=lv, which="nbr")
+        nbr = None if getattr(lv, "brick", None) is not None and self.conv_impl in ("auto", "brick") else lv.nbr      # (lazy on a brick level)
+        t = self._conv(x, rb.c1, nbr, n, relu=True, lv=lv, which="nbr")
         if rb.ident_w is None:
-            return self._conv(t, rb.c2, lv.nbr, n, relu=True, out=out, residual=x, lv=lv, which="nbr")
-        return self._conv(t, rb.c2, lv.nbr, n, relu=True, out=out, in2=x, w2=rb.ident_w, lv=lv, which="nbr")
+            return self._conv(t, rb.c2, nbr, n, relu=True, out=out, residual=x, lv=lv, which="nbr")
+        return self._conv(t, rb.c2, nbr, n, relu=True, out=out, in2=x, w2=rb.ident_w, lv=lv, which="nbr")
 
     def _ublock(self, x, li, levels, trace, pre="UNet."):
         lp, lv = self.levels[li], levels[li]
@@ -297,12 +316,14 @@ class SmartTreeEngine:
         (batch, Z-order): level 0 through a permutation of the caller's rows (undone by the heads
         kernel), deeper levels by construction."""
         coords = coords.contiguous().int()
-        inv = self.inverse_sorted and self.conv_impl in ("auto", "tc", "fma")      # (the tile-plan path wants the unsorted up map)
+        inv = self.inverse_sorted and self.conv_impl in ("auto", "tc", "fma", "brick")      # (the tile-plan path wants the unsorted up map)
         shape = declared_spatial_shape(coords) if self.strict_spconv_bounds else None
         if not self.morton:
             return build_levels(coords, self.depth, inverse_plan=inv, spatial_shape=shape)
         perm = ops.morton_perm(coords)
-        levels = build_levels(ops.gather_rows(coords, perm), self.depth, morton=True, inverse_plan=inv, spatial_shape=shape)      # int32 index: no widening pass
+        brick0 = self.conv_impl in ("auto", "brick") and self.planes[0] == 8 and self.brick_convs
+        levels = build_levels(ops.gather_rows(coords, perm), self.depth, morton=True, inverse_plan=inv, spatial_shape=shape,      # int32 index: no widening pass
+                              brick0=brick0)
         levels[0].perm = perm
         return levels
 

@@ -425,6 +425,57 @@ def conv_gather(inp, nbr_map, weight, n_out, scale=None, shift=None, residual=No
     return out
 
 
+def brick_plan(coords, table: CoordTable):
+    """Plan of the brick conv for one level (st_brick_plan_build): coords [n,4] i32 in (batch, Z-order)."""
+    lib = _lib.load()
+    _req(coords, I32, "coords")
+    n = coords.shape[0]
+    plan = torch.empty(lib.st_brick_plan_bytes(n), dtype=U8, device=coords.device)
+    _count("subm_map")
+    _lib.check(lib.st_brick_plan_build(_ptr(coords), n, _ptr(table.keys), _ptr(table.vals), table.capacity, _ptr(plan), plan.numel(), _stream()),
+               "st_brick_plan_build")
+    return plan
+
+
+def brick_plan_info(plan, n):
+    """(bricks, halo entries, status): status != 0 -> the rows were not strictly increasing in (batch, Z-order)."""
+    info = (C.c_int32 * 3)()
+    _lib.check(_lib.load().st_brick_plan_info(_ptr(plan), n, info), "st_brick_plan_info")
+    return int(info[0]), int(info[1]), int(info[2])
+
+
+def conv_brick_supported(ntaps, cin, cout):
+    return ntaps == 27 and cin in (8, 16) and cout == 8
+
+
+def conv_brick(inp, plan, weight, n_out, scale=None, shift=None, residual=None, in2=None, w2=None, out=None, relu=False):
+    """Sub-manifold 3x3x3 conv on 4x4x4 bricks (st_conv_brick): same result as conv_gather with the level's subm_map."""
+    lib = _lib.load()
+    _req_rows(inp, "inp"); _req(weight, F32, "weight"); _req(plan, U8, "plan")
+    ntaps, cin, cout = weight.shape
+    assert conv_brick_supported(ntaps, cin, cout) and inp.shape == (n_out, cin)
+    if out is None:
+        out = torch.empty((n_out, cout), dtype=F32, device=inp.device)
+    _req_rows(out, "out")
+    if residual is not None:
+        _req_rows(residual, "residual")
+    if in2 is not None:
+        _req_rows(in2, "in2"); _req(w2, F32, "w2")
+    _count("conv")
+    prof = _conv_profile
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _lib.check(lib.st_conv_brick(_ptr(inp), _ld(inp), _ptr(plan), n_out, _ptr(weight), cin, cout, _ptr(scale), _ptr(shift), _ptr(residual),
+                                 _ld(residual), _ptr(in2), _ld(in2), _ptr(w2), (in2.shape[1] if in2 is not None else 0), _ptr(out), _ld(out),
+                                 1 if relu else 0, _stream()), "st_conv_brick")
+    if prof is not None:
+        ev1.record()
+        extra = (cout if residual is not None else 0) + (in2.shape[1] if in2 is not None else 0)
+        prof.append((cin, cout, ntaps, n_out, extra, ev0, ev1, "brick"))
+    return out
+
+
 def heads_fused(feat, params, want_logits=True, out_index=None):
     lib = _lib.load()
     _req_rows(feat, "feat"); _req(params, F32, "params")

@@ -203,6 +203,59 @@ def test_conv_tile_plan_z_order(cin, cout, n, extent):
     assert torch.equal(out, tc)
 
 
+@pytest.mark.parametrize("cin,variant", [(8, "plain"), (8, "residual"), (8, "identity"), (16, "plain"), (16, "slices")])
+@pytest.mark.parametrize("n,extent", [(40000, 48), (300, 40), (129, 6), (6000, 13), (1, 3)])
+def test_conv_brick_matches_oracle_and_map_kernel(cin, variant, n, extent):
+    """Brick conv of the narrow level (st_conv_brick: 4x4x4 bricks of Z-ordered rows staged in shared memory, no gather map)
+    == the fp64 oracle conv and the gather-map FMA kernel, with every fused epilogue of the level-0 ResBlocks: plain,
+    residual add, identity 1x1 conv, reading / writing column slices of the concat buffer.  Clouds: sparse (few
+    neighbours), dense (13^3 grid nearly full: bricks of up to 64 voxels, 152-entry halos), a single voxel, two batches."""
+    ops = _ops()
+    rng = np.random.default_rng(n + cin + len(variant))
+    c = _random_coords(rng, n, extent)
+    cd = _t(c, torch.int32)
+    perm = ops.morton_perm(cd).cpu().numpy()
+    c = c[perm]
+    n = len(c)
+    cd = _t(c, torch.int32)
+    table = ops.CoordTable(cd)
+    plan = ops.brick_plan(cd, table)
+    bricks, halo, status = ops.brick_plan_info(plan, n)
+    assert status == 0 and 1 <= bricks <= n and halo <= 7 * n
+    nbr = U.subm_map(c)
+    assert np.array_equal(ops.subm_map(cd, table).cpu().numpy(), nbr)
+    w = (rng.standard_normal((8, 3, 3, 3, cin)) / np.sqrt(27 * cin)).astype(np.float32)
+    wt = torch.from_numpy(w).reshape(8, 27, cin).permute(1, 2, 0).contiguous().to(DEV)
+    scale = rng.uniform(0.5, 2, 8).astype(np.float32)
+    shift = rng.standard_normal(8).astype(np.float32)
+    cat = rng.standard_normal((n, 32)).astype(np.float32)
+    catd = _t(cat)
+    x = cat[:, 16:16 + cin] if variant == "slices" else cat[:, :cin].copy()
+    xd = catd[:, 16:16 + cin] if variant == "slices" else _t(x)
+    kw, ref_extra = {}, 0.0
+    if variant == "residual":
+        res = rng.standard_normal((n, 8)).astype(np.float32)
+        kw["residual"] = _t(res)
+        ref_extra = res.astype(np.float64)
+    if variant == "identity":
+        w2 = (rng.standard_normal((16, 8)) / 4).astype(np.float32)
+        kw.update(in2=catd[:, :16], w2=_t(w2))
+        ref_extra = cat[:, :16].astype(np.float64) @ w2
+    ref = np.maximum(U.gather_conv(x.astype(np.float64), w, nbr, n) * scale + shift + ref_extra, 0)
+    outbuf = torch.full((n, 16), -7.0, device=DEV)
+    out = outbuf[:, 8:] if variant == "slices" else None
+    got = ops.conv_brick(xd, plan, wt, n, _t(scale), _t(shift), out=out, relu=True, **kw)
+    np.testing.assert_allclose(got.cpu().numpy(), ref, rtol=1e-4, atol=2e-6 * max(np.abs(ref).max(), 1.0))
+    if variant == "slices":
+        assert torch.all(outbuf[:, :8] == -7.0)
+    via_map = ops.conv_gather(xd, _t(nbr, torch.int32), wt, n, _t(scale), _t(shift), relu=True, impl="fma", **kw)
+    np.testing.assert_allclose(got.cpu().numpy(), via_map.cpu().numpy(), rtol=1e-5, atol=1e-5)
+    # the plan notices rows that are not in (batch, Z-order)
+    if n > 100:
+        bad = ops.brick_plan(cd.flip(0).contiguous(), table)
+        assert ops.brick_plan_info(bad, n)[2] != 0
+
+
 @pytest.mark.parametrize("cin,cout,cin2", [(16, 16, 32), (32, 32, 64), (16, 8, 16), (64, 32, 48)])
 def test_conv_tc_identity_as_k_stages(cin, cout, cin2):
     """ResBlock tail conv with the identity 1x1 conv appended to the tensor-core K loop (weights / BN scale):
@@ -415,7 +468,7 @@ def _rel_close(got, ref, tol=1e-3, unit_rows=False):
     return err
 
 
-@pytest.mark.parametrize("impl", ["fma", "tc", "tp", "auto"])
+@pytest.mark.parametrize("impl", ["fma", "tc", "tp", "auto", "brick"])
 @pytest.mark.parametrize("weights", ["noble-elevator-58", "peach-forest-65", "random"])
 def test_unet_forward_matches_oracle(weights, impl):
     from smart_tree_b200.engine import SmartTreeEngine

@@ -58,6 +58,37 @@ for cin, cout, li in cases:
         byt = 4 * (lv.n * cout + levels[li + 1].n * cin)
         print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s")
         continue
+    if impl == "brick":
+        if not ops.conv_brick_supported(27, cin, cout):
+            continue
+        x = torch.randn(lv.n, cin, device=dev)
+        w = torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5
+        out = torch.empty(lv.n, cout, device=dev)
+        ts = []
+        for _ in range(5):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); plan = ops.brick_plan(lv.coords, lv.table); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        nb, nh, st = ops.brick_plan_info(plan, lv.n)
+        print(f"  brick plan: {nb} bricks ({lv.n / nb:.1f} voxels each), {nh} halo entries ({nh / lv.n:.2f} per voxel), status {st}, build {float(np.median(ts)):.1f} us")
+        ref = ops.conv_gather(x, lv.nbr, w, lv.n, relu=True, impl="fma")
+        got = ops.conv_brick(x, plan, w, lv.n, relu=True)
+        print(f"  max |brick - map kernel| = {float((ref - got).abs().max()):.3e}")
+        for _ in range(3):
+            ops.conv_brick(x, plan, w, lv.n, out=out, relu=True)
+        ts = []
+        for _ in range(10):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); ops.conv_brick(x, plan, w, lv.n, out=out, relu=True); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e3)
+        us = float(np.median(ts))
+        byt = 4 * lv.n * (cin + cout)
+        print(f"{impl} {cin:3d}->{cout:3d} L{li} n={lv.n:7d}  {us:8.1f} us  {byt / us / 1e3:7.1f} GB/s  ({byt / us / 1e3 / 6525.2 * 100:5.2f}% of measured HBM peak)")
+        continue
     x = torch.randn(lv.n, cin, device=dev)
     w = torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5
     wtc = ops.conv_tc_prepare(w) if impl in ("tc", "tp") else None
