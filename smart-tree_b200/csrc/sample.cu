@@ -863,7 +863,8 @@ constexpr int MB = 16;         // members per round
 constexpr int MP = 128;        // route slots per member (two per thread of the member's 64)
 constexpr int MPS = 7;         // log2(MP)
 constexpr int WIN = 512;       // live entries examined per round
-constexpr int SCAN_STEPS = 4;  // scan steps of 8192 list positions per round at most (the list is compacted as the loop goes)
+constexpr int SCAN_PPT = 16;   // list positions per thread and scan step (the loads of a step are in flight together: a step costs two L2 round trips + a block scan whatever its width)
+constexpr int SCAN_STEPS = 2;  // scan steps of 1024 * SCAN_PPT list positions per round at most (the list is compacted as the loop goes)
 
 struct RoundSmem {
     float4 path[MB * MP];      // xyz + radius of member g's route vertex h at [g * MP + h]  (the long-route path reuses it as [1024])
@@ -886,7 +887,7 @@ struct RoundSmem {
 __device__ __forceinline__ int stamp_who(int sv, int epoch) { return (sv >> 4) == epoch ? 15 - (sv & 15) : 16; }
 
 __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
-                                                           int32_t *clist_all, int32_t *ccnt_all) {
+                                                           int32_t *clist_all, int32_t *ccnt_all, int win, int scan_steps) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem &S = *reinterpret_cast<RoundSmem *>(smem_raw);
     const unsigned CL = cluster_size(), cr = cluster_rank();
@@ -905,40 +906,40 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     long long t_mark = clock64();
     while (true) {
         ++dbg[0];
-        // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 8192 positions at a time
-        //         (eight consecutive positions per thread: two 16-byte loads of the list, one block scan per step)
+        // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 1024 * SCAN_PPT positions at a
+        //         time (consecutive positions per thread: 16-byte loads of the list, one block scan per step)
         long long t_ph = clock64();
         int nlive = 0, scan_end = cursor;
-        for (int step = 0; step < SCAN_STEPS && nlive <= WIN && scan_end < nc; ++step) {
-            int vtx[8];
+        for (int step = 0; step < scan_steps && nlive <= win && scan_end < nc; ++step) {
+            int vtx[SCAN_PPT];
             unsigned lmask = 0;
-            const int p0 = scan_end + tid * 8;
+            const int p0 = scan_end + tid * SCAN_PPT;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) vtx[k] = p0 + k < nc ? __ldcg(a.order + base + p0 + k) : -1;
+            for (int k = 0; k < SCAN_PPT; ++k) vtx[k] = p0 + k < nc ? __ldcg(a.order + base + p0 + k) : -1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < SCAN_PPT; ++k)
                 if (vtx[k] >= 0 && __ldcg(a.distw + vtx[k]) > 0.f) lmask |= 1u << k;
             int total;
             int rank = block_excl_scan_1024(__popc(lmask), S.scan, total);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
+            for (int k = 0; k < SCAN_PPT; ++k) {
                 if (lmask & (1u << k)) {
-                    if (nlive + rank <= WIN) { S.win_pos[nlive + rank] = p0 + k; if (nlive + rank < WIN) S.win_v[nlive + rank] = vtx[k]; }
+                    if (nlive + rank <= win) { S.win_pos[nlive + rank] = p0 + k; if (nlive + rank < win) S.win_v[nlive + rank] = vtx[k]; }
                     ++rank;
                 }
             }
             nlive += total;
             __syncthreads();
-            scan_end = min(scan_end + 8192, nc);
+            scan_end = min(scan_end + 1024 * SCAN_PPT, nc);
         }
         if (nlive == 0) {
             if (scan_end >= nc) break;
             cursor = scan_end;
             continue;
         }
-        int nwin = min(nlive, WIN);
+        int nwin = min(nlive, win);
         // position where the window ends: the first live entry beyond it, or the end of the scanned range
-        int win_end = nlive > WIN ? S.win_pos[WIN] : scan_end;
+        int win_end = nlive > win ? S.win_pos[win] : scan_end;
         if (tid < nwin) {
             const int v = S.win_v[tid];
             S.win_pt[tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
@@ -1497,7 +1498,11 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     if (mode == 2) {
         ST_REQUIRE(n < (1ll << 28), "components of at most 2^28 vertices");
         cfg.dynamicSmemBytes = sizeof(RoundSmem);
-        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo));
+        // live entries examined per round / scan steps of 8192 list positions per round: any value gives the same result
+        int win = WIN, scan_steps = SCAN_STEPS;
+        if (const char *e = getenv("ST_SAMPLE_WIN")) { int v = atoi(e); if (v >= 1 && v <= WIN) win = v; }
+        if (const char *e = getenv("ST_SAMPLE_SCAN_STEPS")) { int v = atoi(e); if (v >= 1 && v <= 64) scan_steps = v; }
+        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo, win, scan_steps));
     } else if (mode == 1) {
         ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_b, a, jump_c, nt, stamp, tlist_all, binfo));
     } else {
