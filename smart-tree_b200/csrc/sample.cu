@@ -59,7 +59,22 @@ struct SampleArgs {
     int32_t *path_out, *branch_len, *branch_parent, *comp_nb, *comp_np;
     int32_t *touched;      // [n] segment-local list of points claimed in the current iteration
     int32_t *touch_cnt;    // [2 * n_comp] append counters, alternating by iteration parity
+    int32_t *pos;          // k_sample_tree_c only (else null): position of every vertex in `order`, for the tombstones below
 };
+
+// A vertex leaves the candidate list.  k_sample_tree_c scans the list for live entries every round; without help it has to
+// look up distw of every entry it passes (random L2 loads: 8192 per step and CTA, the whole cost of its phase A), and most of
+// them are dead.  So a kill also overwrites the vertex' list entry with -1 -- but only entries at or beyond `stable_from`:
+// the entries of the current window are being compacted in place by another CTA at the same time (their liveness is
+// re-checked through distw by the next scan, as before).
+__device__ __forceinline__ void kill_vertex(const SampleArgs &a, int v, int stable_from) {
+    a.distw[v] = -1.f;
+    a.alloc[v] = 1;
+    if (a.pos) {
+        const int p = __ldcg(a.pos + v);
+        if (p >= stable_from) a.order[p] = -1;
+    }
+}
 
 // One (path vertex, grid row) task per warp: the rows within r of the vertex are numbered
 // 0 .. RW*RW-1 around the vertex's own cell, so a short path still spreads over every warp of the cluster.
@@ -138,8 +153,7 @@ __device__ __forceinline__ void claim_drain(const SampleArgs &a, const float4 *s
     for (int j2 = jlo; j2 <= jhi; ++j2) own = own && !(claim_key(q, s_path[j2], (unsigned)(len - 1 - j2)) < key);
     if (own && sqrtf(d2) < p.w) {
         const int gi = __float_as_int(q.w);
-        a.distw[gi] = -1.f;
-        a.alloc[gi] = 1;
+        kill_vertex(a, gi, 0);          // (no compaction is going on in the iterations that claim through this function)
         if (bid >= 0) a.branch_id[gi] = bid;
     }
 }
@@ -863,8 +877,8 @@ constexpr int MB = 16;         // members per round
 constexpr int MP = 128;        // route slots per member (two per thread of the member's 64)
 constexpr int MPS = 7;         // log2(MP)
 constexpr int WIN = 512;       // live entries examined per round
-constexpr int SCAN_PPT = 16;   // list positions per thread and scan step (the loads of a step are in flight together: a step costs two L2 round trips + a block scan whatever its width)
-constexpr int SCAN_STEPS = 2;  // scan steps of 1024 * SCAN_PPT list positions per round at most (the list is compacted as the loop goes)
+constexpr int SCAN_PPT = 8;    // list positions per thread and scan step (the loads of a step are in flight together: a step costs two L2 round trips + a block scan whatever its width)
+constexpr int SCAN_STEPS = 4;  // scan steps of 1024 * SCAN_PPT list positions per round at most (the list is compacted as the loop goes)
 
 struct RoundSmem {
     float4 path[MB * MP];      // xyz + radius of member g's route vertex h at [g * MP + h]  (the long-route path reuses it as [1024])
@@ -907,26 +921,45 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     while (true) {
         ++dbg[0];
         // ---- A. window: the next live entries of the (distance desc, index asc) list, scanned 1024 * SCAN_PPT positions at a
-        //         time (consecutive positions per thread: 16-byte loads of the list, one block scan per step)
+        //         time
         long long t_ph = clock64();
         int nlive = 0, scan_end = cursor;
         for (int step = 0; step < scan_steps && nlive <= win && scan_end < nc; ++step) {
+            // a warp takes 32 * SCAN_PPT consecutive positions, lane-contiguous (one line per load instruction); the rank of a
+            // live entry = live entries of the warps before + of the warp's earlier load rounds + of the lower lanes
+            const int wbase = scan_end + warp * (32 * SCAN_PPT);
             int vtx[SCAN_PPT];
-            unsigned lmask = 0;
-            const int p0 = scan_end + tid * SCAN_PPT;
-#pragma unroll
-            for (int k = 0; k < SCAN_PPT; ++k) vtx[k] = p0 + k < nc ? __ldcg(a.order + base + p0 + k) : -1;
-#pragma unroll
-            for (int k = 0; k < SCAN_PPT; ++k)
-                if (vtx[k] >= 0 && __ldcg(a.distw + vtx[k]) > 0.f) lmask |= 1u << k;
-            int total;
-            int rank = block_excl_scan_1024(__popc(lmask), S.scan, total);
+            unsigned masks[SCAN_PPT];
 #pragma unroll
             for (int k = 0; k < SCAN_PPT; ++k) {
-                if (lmask & (1u << k)) {
-                    if (nlive + rank <= win) { S.win_pos[nlive + rank] = p0 + k; if (nlive + rank < win) S.win_v[nlive + rank] = vtx[k]; }
-                    ++rank;
+                const int p = wbase + k * 32 + lane;
+                vtx[k] = p < nc ? __ldcg(a.order + base + p) : -1;
+            }
+            int wtotal = 0;
+#pragma unroll
+            for (int k = 0; k < SCAN_PPT; ++k) {
+                const bool live = vtx[k] >= 0 && __ldcg(a.distw + vtx[k]) > 0.f;      // (-1 = tombstone: no look-up)
+                masks[k] = __ballot_sync(0xffffffffu, live);
+                wtotal += __popc(masks[k]);
+            }
+            if (lane == 0) S.scan[warp] = wtotal;
+            __syncthreads();
+            const int x = S.scan[lane];
+            int incl = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            int rank = nlive + __shfl_sync(0xffffffffu, incl - x, warp);
+#pragma unroll
+            for (int k = 0; k < SCAN_PPT; ++k) {
+                if ((masks[k] >> lane) & 1u) {
+                    const int r = rank + __popc(masks[k] & ((1u << lane) - 1u));
+                    if (r <= win) { S.win_pos[r] = wbase + k * 32 + lane; if (r < win) S.win_v[r] = vtx[k]; }
                 }
+                rank += __popc(masks[k]);
             }
             nlive += total;
             __syncthreads();
@@ -1091,8 +1124,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     const float d2 = __uint_as_float((unsigned)(bkey >> 32));
                     const float vr = jj < PATH_SMEM ? S.path[jj].w : a.radii[base + path[jj]];
                     if (sqrtf(d2) < vr) {
-                        a.distw[gi] = -1.f;
-                        a.alloc[gi] = 1;
+                        kill_vertex(a, gi, 0);
                         if (emit) a.branch_id[gi] = bid;
                     }
                     __stcg(a.best + gi, BEST_NONE);
@@ -1100,8 +1132,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             }
             for (int jj = gtid; jj < len; jj += nthr) {
                 const int v = base + path[jj];
-                a.distw[v] = -1.f;
-                a.alloc[v] = 1;
+                kill_vertex(a, v, 0);
                 if (emit) a.branch_id[v] = bid;
             }
             cluster_sync_all();
@@ -1339,8 +1370,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                 const int word = __ldcg(clist + k);
                 const int m = (word >> 28) & 15, v = base + (word & 0x0FFFFFFF);
                 if (S.status[m] == ST_ACCEPT) {
-                    a.distw[v] = -1.f;
-                    a.alloc[v] = 1;
+                    kill_vertex(a, v, base + win_end);
                     if (S.len[m] >= 2) atomicMax(a.branch_id + v, S.bid[m]);
                 }
             }
@@ -1353,8 +1383,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     if (hh < len) {
                         const int lv = S.pv[g * MP + hh];
                         const int v = base + lv;
-                        a.distw[v] = -1.f;
-                        a.alloc[v] = 1;
+                        kill_vertex(a, v, base + win_end);
                         if (emit) {
                             atomicMax(a.branch_id + v, S.bid[g]);
                             a.path_out[base + S.pcur[g] + (len - 1 - hh)] = lv;      // root side first
@@ -1375,7 +1404,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         // win_end (they only move right, in order), so that the next round's scan starts on a dense run of live entries
         // instead of re-reading the dead ones.  Nobody reads the list before the barrier below (win_v is the round's copy).
         const int keep = nwin - stop_entry;
-        if (cr == 0 && tid < keep) a.order[base + win_end - keep + tid] = S.win_v[stop_entry + tid];
+        if (cr == 0 && tid < keep) {
+            a.order[base + win_end - keep + tid] = S.win_v[stop_entry + tid];
+            if (a.pos) a.pos[S.win_v[stop_entry + tid]] = base + win_end - keep + tid;
+        }
         cursor = win_end - keep;
         ++epoch;
         cluster_sync_all();                                  // 2: commits visible before the next round reads the state
@@ -1383,6 +1415,15 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
     if (tid == 0 && cr == 0 && c == 0) { dbg[15] = CL; for (int i = 0; i < 16; ++i) g_stb_stats[i] = dbg[i]; }
     cluster_sync_all();
+}
+
+// positions of the vertices in the sorted list; entries that are dead from the start (path.py:71-72) become tombstones
+__global__ void k_st_positions(int32_t *__restrict__ order, const float *__restrict__ distw, int n, int32_t *__restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int v = order[i];
+    pos[v] = i;
+    if (!(distw[v] > 0.f)) order[i] = -1;
 }
 
 static size_t sort_bytes(int64_t n) {
@@ -1395,7 +1436,7 @@ static size_t sort_bytes(int64_t n) {
 extern "C" size_t st_sample_tree_workspace_bytes(int64_t n, int32_t n_comp) {
     return grid_ws_bytes(n) + align_up(sort_bytes(n)) + 2 * align_up(n * 8) + 2 * align_up(n * 4) + align_up(n * 4) + align_up(n) +
            align_up(n * 4) + align_up(n * 8) + align_up((size_t)JUMP_LEVELS * n * 4) + 2 * align_up(n * 4) + align_up((2 * (size_t)n_comp + 2) * 4) +
-           align_up(n * 4) + align_up((size_t)16 * n * 4) + align_up((size_t)n_comp * 64 * 4) + 8192;      // batches: stamps, touched lists, verdicts
+           align_up(n * 4) + align_up((size_t)16 * n * 4) + align_up((size_t)n_comp * 64 * 4) + align_up(n * 4) + 8192;      // batches: stamps, touched lists, verdicts, list positions
 }
 
 extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const int32_t *pred, const float *tree_dist,
@@ -1421,6 +1462,7 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     int32_t *stamp = cv.take<int32_t>(n);
     int32_t *tlist_all = cv.take<int32_t>((size_t)16 * n);
     int32_t *binfo = cv.take<int32_t>((size_t)n_comp * 64);
+    int32_t *pos = cv.take<int32_t>(n);
     size_t sb = sort_bytes(n);
     void *sort_ws = cv.take<char>(sb);
     if (!cv.ok()) { set_error("st_sample_tree: workspace too small"); return ST_ERR_WORKSPACE; }
@@ -1451,7 +1493,7 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
         ST_CHECK_LAUNCH();
     }
     SampleArgs a{medial_pts, radii, pred, comp_off, gb.g, gb.cell_start, gb.sorted, order, distw, alloc, branch_id, best,
-                 path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path, touched, touch_cnt};
+                 path_vertices, branch_len, branch_parent, comp_n_branches, comp_n_path, touched, touch_cnt, nullptr};
     ST_CHECK_CUDA(cudaMemsetAsync(touch_cnt, 0, (2 * (size_t)n_comp + 2) * sizeof(int32_t), s));
     // largest cluster the device can co-schedule: more CTAs per component = more lanes on the scans
     static int cluster_cached = 0;
@@ -1497,9 +1539,14 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
     const int32_t *jump_c = jump;
     if (mode == 2) {
         ST_REQUIRE(n < (1ll << 28), "components of at most 2^28 vertices");
+        if (!getenv("ST_SAMPLE_NO_TOMBSTONES")) {
+            k_st_positions<<<(unsigned)cdiv(n, 256), 256, 0, s>>>(order, distw, (int)n, pos);
+            ST_CHECK_LAUNCH();
+            a.pos = pos;
+        }
         cfg.dynamicSmemBytes = sizeof(RoundSmem);
         // live entries examined per round / scan steps of 8192 list positions per round: any value gives the same result
-        int win = WIN, scan_steps = SCAN_STEPS;
+        int win = 128, scan_steps = SCAN_STEPS;      // tools/sample_sweep.py: 128 live entries per round were best on the bench tree (4.7 ms; 512: 6.0 ms)
         if (const char *e = getenv("ST_SAMPLE_WIN")) { int v = atoi(e); if (v >= 1 && v <= WIN) win = v; }
         if (const char *e = getenv("ST_SAMPLE_SCAN_STEPS")) { int v = atoi(e); if (v >= 1 && v <= 64) scan_steps = v; }
         ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo, win, scan_steps));

@@ -661,11 +661,13 @@ def _assert_same_skeletons(got, ref):
             assert np.array_equal(gb.radii.numpy().reshape(-1), rb.radii)
 
 
-@pytest.mark.parametrize("schedule", ["batched", "batched-cluster-4", "batched-cluster-1", "members", "sequential", "hopwise-tree-dist"])
+@pytest.mark.parametrize("schedule", ["batched", "batched-cluster-4", "batched-cluster-1", "batched-window-32", "batched-no-tombstones", "members", "sequential",
+                                      "hopwise-tree-dist"])
 @pytest.mark.parametrize("seed,n,vs", [(0, 50000, 0.02), (3, 30000, 0.02)])
 def test_skeletonizer_topology_bit_identical(seed, n, vs, schedule, monkeypatch):
     """Every schedule of the skeleton kernels gives the oracle's result bit for bit: sample_tree in speculative rounds
-    spread over a cluster of 16 / 4 / 1 CTAs (default), with one speculative member per CTA, or strictly sequential;
+    spread over a cluster of 16 / 4 / 1 CTAs (default; with list tombstones or without, with small windows), with one
+    speculative member per CTA, or strictly sequential;
     tree distances by chain walking (default) or hop by hop."""
     from smart_tree_b200.data_types.cloud import Cloud
     from smart_tree_b200.skeleton.skeletonize import Skeletonizer
@@ -677,6 +679,11 @@ def test_skeletonizer_topology_bit_identical(seed, n, vs, schedule, monkeypatch)
         monkeypatch.setenv("ST_SAMPLE_CLUSTER", schedule.rsplit("-", 1)[1])
     if schedule == "members":
         monkeypatch.setenv("ST_SAMPLE_MODE", "members")
+    if schedule == "batched-window-32":           # few live entries per round, one scan step
+        monkeypatch.setenv("ST_SAMPLE_WIN", "32")
+        monkeypatch.setenv("ST_SAMPLE_SCAN_STEPS", "1")
+    if schedule == "batched-no-tombstones":
+        monkeypatch.setenv("ST_SAMPLE_NO_TOMBSTONES", "1")
     xyz, mv = _medial_case(seed, n, vs)
     sk = Skeletonizer(K=16, min_connection_length=0.02, minimum_graph_vertices=32, device=torch.device(DEV))
     got = sk.forward(Cloud(xyz=_t(xyz), medial_vector=_t(mv)))
