@@ -339,7 +339,9 @@ def run_b200(args):
     packed = sk2.skeletons
     d2h = int(packed.payload.nbytes + 16 + 4 * len(packed.cnb_h)) if getattr(packed, "payload", None) is not None else 0
     if g2 is not None:
-        d2h += int(g2.buf.numel() * 4)
+        d2h += int(g2.host_bytes)
+    if g is not None:
+        g.to_host()               # (outside the timed region: the resident arm's gathered buffer is checked for overflow once)
 
     # ---- kernels launched by one step, measured (CUPTI); the lookup table of ops.py only as a fallback
     launches_src = "torch.profiler (CUPTI), one step outside the timed region"
@@ -475,14 +477,18 @@ def run_b200(args):
 
 
 def main():
-    # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry the JSON line only
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout must carry the JSON line only, and native libraries write to it (NCCL prints its version banner there at
+    # NCCL_DEBUG=VERSION/WARN): file descriptor 1 points at stderr for the whole run, the JSON line goes to the saved one
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     args = parse()
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

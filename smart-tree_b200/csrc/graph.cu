@@ -24,6 +24,15 @@ __global__ void k_cc_init(int32_t *parent, int n) {
     if (i < n) parent[i] = i;
 }
 
+// Optional first pass (ST_CC_PRELINK=1): every vertex points at its smallest neighbour with a smaller id -- one atomicMin per
+// edge, no root search; pointers only go to smaller ids, so the result is a forest the hooking pass can start from.
+__global__ void k_cc_prelink(const int32_t *__restrict__ edges, int64_t ne, int32_t *parent) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= ne) return;
+    const int u = edges[2 * e], v = edges[2 * e + 1];
+    if (u != v) atomicMin(parent + max(u, v), min(u, v));
+}
+
 __global__ void k_cc_hook(const int32_t *__restrict__ edges, int64_t ne, int32_t *parent) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= ne) return;
@@ -45,7 +54,9 @@ __global__ void k_cc_flatten(int32_t *parent, int n, int32_t *size) {
     int r = i;
     while (true) { int p = parent[r]; if (p == r) break; r = p; }
     parent[i] = r;      // racing writers all write a value on the path to the same root
-    atomicAdd(size + r, 1);
+    // one atomic per distinct root and warp (a tree cloud is ONE component: 245 k increments of the same word otherwise)
+    const unsigned peers = __match_any_sync(__activemask(), r);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(size + r, __popc(peers));
 }
 
 __global__ void k_cc_sizes(const int32_t *__restrict__ label, int n, int32_t *size) {
@@ -70,6 +81,10 @@ extern "C" int st_connected_components(const int32_t *edges, int64_t n_edges, in
     k_cc_init<<<g, 256, 0, s>>>(label, (int)n);
     ST_CHECK_LAUNCH();
     if (n_edges) {
+        if (getenv("ST_CC_PRELINK")) {
+            k_cc_prelink<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, label);
+            ST_CHECK_LAUNCH();
+        }
         k_cc_hook<<<(unsigned)cdiv(n_edges, 256), 256, 0, s>>>(edges, n_edges, label);
         ST_CHECK_LAUNCH();
     }

@@ -131,16 +131,32 @@ class GatheredPacked:
     """Every rank's packed skeleton buffer after ONE all-gather (device-resident int32 [world, cap]); host copy and the
     reference's object model only on demand."""
 
-    def __init__(self, buf, world):
+    def __init__(self, buf, world, cap=None, redo=None):
         self.buf, self.world = buf, world
+        self.cap = int(buf.shape[1]) if cap is None else int(cap)
+        self._redo = redo
         self._host = None
+        self.host_bytes = 0
 
     def to_host(self):
-        """One device->host copy of the gathered buffer -> list of (unit, PackedSkeletons) per rank."""
+        """Read the `world` length words, then ONE device->host copy of the used prefixes (not of the capacity-padded
+        buffer) -> list of (unit, PackedSkeletons) per rank.  Collective if a rank's result overflowed (gather_packed)."""
         if self._host is None:
             from .data_types.packed import PackedSkeletons
-            h = self.buf.cpu().numpy()
-            self._host = [PackedSkeletons.from_wire(h[r]) for r in range(self.world)]
+            lens = [int(v) for v in self.buf[:, 0].cpu().tolist()]
+            if max(lens) > self.cap:
+                if self._redo is None:
+                    raise RuntimeError("gathered skeleton buffer overflowed and cannot be re-exchanged")
+                self.buf = self._redo(max(lens))
+                self.cap = max(lens)
+            flat = torch.cat([self.buf[r, :max(lens[r], 8)] for r in range(self.world)]).cpu().numpy()
+            self.host_bytes = int(flat.nbytes + 4 * self.world)
+            out, o = [], 0
+            for r in range(self.world):
+                m = max(lens[r], 8)
+                out.append(PackedSkeletons.from_wire(flat[o:o + m]))
+                o += m
+            self._host = out
         return self._host
 
     @property
@@ -162,9 +178,11 @@ class GatheredPacked:
 def gather_packed(local: DisjointTreeSkeleton, unit: int, capacity: int = 1 << 20, device=None) -> GatheredPacked:
     """All-gather of the packed result of one skeletoniser call per rank (the path's only exchange).
     The device buffer st_finish_skeletons wrote is shipped as it is -- no Python re-packing of branches: ONE all-gather
-    of `capacity` int32 words per rank (the used prefix carries its own length) and one read-back of the `world` length
-    words (all ranks must agree on whether anything overflowed).  If a rank's result does not fit, the collective is
-    repeated once with the largest size (rare: the default capacity holds ~200 k nodes)."""
+    of `capacity` int32 words per rank (the used prefix carries its own length), no host synchronisation: the collective
+    overlaps whatever the caller does next.  The lengths are only read when the result is brought to the host
+    (GatheredPacked.to_host: the `world` length words, then the used prefixes in one copy); if a rank's result did not fit,
+    to_host repeats the collective once with the largest size -- every rank sees the same lengths, so every rank takes the
+    same branch, but every rank has to call it (rare: the default capacity holds ~200 k nodes)."""
     from .data_types.packed import PackedSkeletons
     packed = local.skeletons
     if not isinstance(packed, PackedSkeletons):
@@ -195,11 +213,7 @@ def gather_packed(local: DisjointTreeSkeleton, unit: int, capacity: int = 1 << 2
         return recv
 
     cap = max(int(capacity), 16)
-    recv = exchange(cap)
-    biggest = int(recv[:, 0].max().item())
-    if biggest > cap:
-        recv = exchange(biggest)
-    return GatheredPacked(recv, world)
+    return GatheredPacked(exchange(cap), world, cap, exchange)
 
 
 # ---------------------------------------------------------------------------------------------- labelled voxels (plots)

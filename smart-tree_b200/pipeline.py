@@ -74,14 +74,22 @@ class Pipeline:
         DisjointTreeSkeleton (skeleton ids = global component indices); gather them with dist.gather_skeletons.
         `exchange(parts) -> list of all ranks' parts` replaces the collective (tests run the ranks in one process)."""
         from . import dist as stdist
+        t = {}
+        sync = (lambda: torch.cuda.synchronize(self.device)) if self.device.type == "cuda" else (lambda: None)
+        t0 = time.perf_counter()
         cloud = self.preprocessing(cloud.to_device(self.device))
+        sync(); t["preprocess"] = time.perf_counter() - t0; t0 = time.perf_counter()
         lc = self.model_inference.forward(cloud, shard=(rank, world)).to_device(self.device)
+        sync(); t["inference_own_blocks"] = time.perf_counter() - t0; t0 = time.perf_counter()
         part = stdist.labelled_part(lc, self.model_inference.last_voxel_block)
         parts = exchange(part) if exchange is not None else stdist.gather_labelled(part, device=self.device)
         lc = stdist.merge_labelled(parts, self.device)
+        sync(); t["gather_labelled_voxels"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.labelled_cloud = lc
         branch_cloud = lc.filter_by_class(self.branch_classes)
         skeleton = self.skeletonizer.forward(branch_cloud, post=self._fused_post(), shard=(rank, world))
+        sync(); t["skeleton_redundant_graph_plus_own_components"] = time.perf_counter() - t0
+        self.timings = t
         done = getattr(skeleton, "post_applied", None) or {}
         if not done:
             # object-level post-processing: only the globally first skeleton is pruned (quirk C-18)

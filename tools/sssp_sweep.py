@@ -24,9 +24,12 @@ pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0
                 prune_skeletons=True, min_skeleton_radius=0.01, min_skeleton_length=0.02, device=dev)
 tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
-KNOBS = ("ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
-settings = [{}, {"ST_SSSP_SPATIAL": "1"}, {"ST_SSSP_LOCAL": "1"}, {"ST_SSSP_LOCAL": "1", "ST_SSSP_BLOB_DELTA": "0.25"},
-            {"ST_SSSP_PASSES": "32"}, {"ST_SSSP_PASSES": "128"}, {"ST_SSSP_DELTA": "0.06"}, {"ST_SSSP_DELTA": "0.25"}]
+KNOBS = ("ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
+settings = [{}]
+for d in ("0.045", "0.06", "0.09", "0.125", "0.18"):
+    for ps in ("16", "24", "32", "48", "64"):
+        settings.append({"ST_SSSP_DELTA": d, "ST_SSSP_PASSES": ps})
+settings.append({"ST_CC_PRELINK": "1"})
 ref = None
 rows = []
 for s in settings:
@@ -40,7 +43,7 @@ for s in settings:
     for _ in range(5):
         pipe.process_cloud(cloud=cloud)
     torch.cuda.synchronize()
-    med = {k: round(float(np.median(v)), 3) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.tree_dist", "skel.regroup_csr")}
+    med = {k: round(float(np.median(v)), 3) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.components")}
     _timing.enable(False)
     d = pipe.skeletonizer.last["dist"].clone()
     p = pipe.skeletonizer.last["pred"].clone()
