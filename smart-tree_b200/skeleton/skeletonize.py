@@ -130,9 +130,10 @@ class Skeletonizer:
                 src = torch.full((ncomp,), m, dtype=torch.int64, device=dev).scatter_reduce(0, comp_of, cand, "amin")
         # skeletonize.py:73-78
         with section("skel.sssp"):
-            # threshold step of the distance-ordered SSSP schedule (any value is exact; tools/sssp_sweep.py: with the threshold
-            # advancing at every barrier, 0.125 m and 64 polls per barrier were best on the 6 m bench tree: 4.4 -> 3.1 ms)
-            delta = float(os.environ.get("ST_SSSP_DELTA", 6.25 * self.min_connection_length))
+            # threshold step of the distance-ordered SSSP schedule (any value is exact; tools/sssp_sweep.py on the 6 m bench
+            # tree: the best settings lie on a line of ~360 polls per metre of threshold step -- 0.06 m / 16 polls 3.0 ms,
+            # 0.125 / 48 2.8, 0.18 / 64 2.6 -- fewer barriers win as long as the step stays a few edge lengths)
+            delta = float(os.environ.get("ST_SSSP_DELTA", 9.0 * self.min_connection_length))
             if sperm is not None:
                 dist, pred = ops.sssp(row_ptr, col, w, m, srank[src].contiguous(), delta=delta, orig_id=sperm)
             else:
