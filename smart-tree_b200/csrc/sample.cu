@@ -266,7 +266,10 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
         int beg = 0, end = 0, jj = 0;
         if (t < nflat) {
             jj = (int)(t / R2);
-            row_range(a, s_path[jj], (int)(t % R2), R, rr, beg, end);
+            // SHORT modes decide ownership by an explicit nearest-vertex test (claim_drain), so a vertex only has to offer the
+            // points it could claim itself, i.e. those within ITS radius (a claimed point lies within the radius of its nearest
+            // vertex); the atomicMin variant needs every vertex within the route's largest radius to register
+            row_range(a, s_path[jj], (int)(t % R2), R, SHORT ? s_path[jj].w * 1.0001f + 1e-7f : rr, beg, end);
         }
         int total;
         const int ex = block_excl_scan_1024(end > beg ? end - beg : 0, s_warp, total);
@@ -295,7 +298,8 @@ __device__ __forceinline__ void claim_flat(const SampleArgs &a, int base, int nc
             if (gi >= base && gi < base + nc) {
                 const float4 p = s_path[j];
                 const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
-                if (d2 < r2) {
+                const float rj = p.w * 1.0001f + 1e-7f;
+                if (SHORT ? d2 <= rj * rj : d2 < r2) {
                     key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
                     cand = true;
 #pragma unroll
@@ -1248,8 +1252,8 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     const int local = (int)(t - S.toff[m]);
                     const int jj = local / R2;
                     slot = m * MP + jj;
-                    const float r = __int_as_float(S.rbits[m]);
-                    row_range(a, S.path[slot], local % R2, R, r * 1.0001f + 1e-7f, beg, end);
+                    // rows within the vertex' OWN radius (see claim_flat): the grid of rows is laid out for the route's largest
+                    row_range(a, S.path[slot], local % R2, R, S.path[slot].w * 1.0001f + 1e-7f, beg, end);
                 }
                 int total;
                 const int ex = block_excl_scan_1024(end > beg ? end - beg : 0, S.scan, total);
@@ -1276,11 +1280,10 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     bool cand = false;
                     if (gi >= base && gi < base + nc) {
                         const int m = sl >> MPS, j = sl & (MP - 1), len = S.len[m];
-                        const float r = __int_as_float(S.rbits[m]);
-                        const float r2 = __fmul_rn(r, r);
                         const float4 p = S.path[sl];
                         const float d2 = dist2_exact(q.x, q.y, q.z, p.x, p.y, p.z);
-                        if (d2 < r2) {
+                        const float rj = p.w * 1.0001f + 1e-7f;
+                        if (d2 <= rj * rj) {
                             const unsigned long long key = ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)(len - 1 - j);
                             cand = true;
 #pragma unroll

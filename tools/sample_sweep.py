@@ -26,10 +26,11 @@ cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb)
 lib = _lib.load()
 lib.st_debug_sample_batch_stats.argtypes = [C.c_void_p]
 ref = None
-for win in (512, 256, 128, 64, 32):
-    for steps in (4, 1):
+for win, steps, cl in ((128, 4, 16), (128, 4, 8), (128, 4, 4), (128, 4, 2), (96, 4, 16), (192, 4, 16), (64, 4, 8), (256, 4, 8)):
+    if True:
         os.environ["ST_SAMPLE_WIN"] = str(win)
         os.environ["ST_SAMPLE_SCAN_STEPS"] = str(steps)
+        os.environ["ST_SAMPLE_CLUSTER"] = str(cl)
         sk = pipe.process_cloud(cloud=cloud)
         _timing.enable(True)
         _timing.RECORDS.clear(); _timing.SAMPLES.clear()
@@ -42,7 +43,7 @@ for win in (512, 256, 128, 64, 32):
         lib.st_debug_sample_batch_stats(bst)
         dg = skeleton_digest(sk.skeletons)["topology"]
         ref = ref or dg
-        print(json.dumps({"win": win, "scan_steps": steps, "sample_tree_ms": round(ms, 3), "rounds": int(bst[0]), "batches": int(bst[2]),
+        print(json.dumps({"win": win, "scan_steps": steps, "cluster": cl, "sample_tree_ms": round(ms, 3), "rounds": int(bst[0]), "batches": int(bst[2]),
                           "offered": int(bst[3]), "accepted": int(bst[4]), "cut_gap": int(bst[9]), "kcycles_A": int(bst[12]) // 1000,
                           "kcycles_BC": int(bst[13]) // 1000, "kcycles_D": int(bst[14]) // 1000, "kcycles_batches": int(bst[10]) // 1000,
                           "same_topology": dg == ref}), flush=True)
