@@ -98,7 +98,11 @@ class Skeletonizer:
             rank_of_root[roots] = torch.arange(ncomp, device=dev)
             vrank = rank_of_root[label.long()]
             sel = torch.nonzero(vrank >= 0).flatten()
-            order = sel[torch.argsort(vrank[sel], stable=True)]               # new id -> old vertex id
+            if ncomp == 1:
+                order = sel                                                   # one component: ascending ids as they are
+            else:                                                             # (16-bit keys: two radix passes instead of eight)
+                vs = vrank[sel]
+                order = sel[torch.argsort(vs.to(torch.int16) if ncomp < 32768 else vs, stable=True)]      # new id -> old vertex id
             m = int(order.shape[0])
             new_id = torch.full((n,), -1, dtype=torch.int32, device=dev)
             new_id[order] = torch.arange(m, dtype=torch.int32, device=dev)
