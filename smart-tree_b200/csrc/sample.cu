@@ -126,10 +126,12 @@ __device__ __forceinline__ unsigned long long claim_key(float4 q, float4 o, unsi
 // `lohi` (optional): per path vertex j the index interval [lo, hi] (lo | hi << 16) that contains every path vertex within
 // 2 r of it.  A vertex that beats j for a point within r of j is itself within r of the point, hence within 2 r of j: the
 // scan over [lo, hi] decides exactly what the scan over the whole path decides, ~20x cheaper on a 300-vertex route.
+// Window of path positions that can hold a vertex nearer to a point than vertex j does: a candidate point of j lies within
+// j's own radius r_j (claim_flat), a nearer vertex therefore within 2 r_j of j.
 __device__ __forceinline__ void path_windows(const float4 *s_path, int len, float r, int *lohi, int t0, int nt) {
-    const float lim = 2.f * r * 1.001f + 1e-6f, lim2 = lim * lim;
     for (int j = t0; j < len; j += nt) {
         const float4 p = s_path[j];
+        const float lim = 2.f * p.w * 1.001f + 1e-6f, lim2 = lim * lim;
         int lo = j, hi = j;
         for (int j2 = 0; j2 < len; ++j2) {
             const float4 q = s_path[j2];
@@ -573,6 +575,7 @@ constexpr int BATCH_PATH = 64;
 // accepted, skipped, batches cut by a long member, cut because the start vertex was touched, cut because the route / parent
 // vertex was touched, claimed points of accepted members, cycles in batches, cycles in long iterations, ...]
 __device__ unsigned long long g_stb_stats[16];
+__device__ unsigned long long g_stc_phase[8];     // k_sample_tree_c, CTA 0 of component 0, cycles: B select, C routes, C fill + windows, barrier 1, E verdict inputs, verdict, F commit, barrier 2
 constexpr int ST_ACCEPT = 1, ST_SKIP = 2, ST_CUT = 0;
 
 __global__ void __launch_bounds__(1024, 1) k_sample_tree_b(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
@@ -905,7 +908,7 @@ struct RoundSmem {
 __device__ __forceinline__ int stamp_who(int sv, int epoch) { return (sv >> 4) == epoch ? 15 - (sv & 15) : 16; }
 
 __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const int32_t *__restrict__ jump, int n_total, int32_t *stamp,
-                                                           int32_t *clist_all, int32_t *ccnt_all, int win, int scan_steps) {
+                                                           int32_t *clist_all, int32_t *ccnt_all, int win, int scan_steps, float sep) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RoundSmem &S = *reinterpret_cast<RoundSmem *>(smem_raw);
     const unsigned CL = cluster_size(), cr = cluster_rank();
@@ -921,6 +924,13 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
     unsigned long long dbg[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) dbg[i] = 0;
+    unsigned long long ph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_f = 0;
+#ifdef ST_SAMPLE_TRACE      // per-phase cycle counters of the rounds (tools/sample_sweep.py; build with ST_NVCC_EXTRA=-DST_SAMPLE_TRACE)
+#define ST_PH(i) do { if (tid == 0) { const long long t_ = clock64(); ph[i] += (unsigned long long)(t_ - t_f); t_f = t_; } } while (0)
+#else
+#define ST_PH(i) do { (void)t_f; } while (0)
+#endif
     long long t_mark = clock64();
     while (true) {
         ++dbg[0];
@@ -982,7 +992,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             S.win_pt[tid] = make_float4(a.pts[3 * (size_t)v], a.pts[3 * (size_t)v + 1], a.pts[3 * (size_t)v + 2], a.radii[v]);
         }
         __syncthreads();
-        if (tid == 0) { const long long t = clock64(); dbg[12] += (unsigned long long)(t - t_ph); t_ph = t; }
+        if (tid == 0) { const long long t = clock64(); dbg[12] += (unsigned long long)(t - t_ph); t_ph = t; t_f = t; }
         // ---- B. members: greedy in list order, an entry is taken iff it is far from every member taken so far (warp 0)
         if (warp == 0) {
             int nsel = 0;
@@ -995,7 +1005,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     far = true;
                     for (int m = 0; m < nsel; ++m) {
                         const float4 q = S.selpt[m];
-                        const float rho = 2.f * fmaxf(p.w, q.w);
+                        const float rho = sep * fmaxf(p.w, q.w);
                         if (dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < rho * rho) far = false;
                     }
                 }
@@ -1012,7 +1022,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
                     // lanes after l that were still candidates re-test against the new member; lanes after l come after it in the list
                     if (lane > l) {
                         my_gap = nsel;
-                        const float rho = 2.f * fmaxf(p.w, q.w);
+                        const float rho = sep * fmaxf(p.w, q.w);
                         if (far && dist2_exact(p.x, p.y, p.z, q.x, q.y, q.z) < rho * rho) far = false;
                     }
                     todo &= __ballot_sync(0xffffffffu, far);
@@ -1025,6 +1035,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             if (lane == 0) S.nsel = nsel;
         }
         __syncthreads();
+        ST_PH(0);
         int nsel = S.nsel;
         if (nsel == MB && S.sel[MB - 1] + 1 < nwin) {           // the round ends right after its last member
             nwin = S.sel[MB - 1] + 1;
@@ -1051,6 +1062,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             }
         }
         __syncthreads();
+        ST_PH(1);
         if (S.first[0] == 1024) {
             // =========================== long route: one iteration of k_sample_tree on candidate 0, whole cluster
             const int f = S.win_v[0] - base;
@@ -1207,6 +1219,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         }
         __syncthreads();
         if (tid == 0) { const long long t = clock64(); dbg[13] += (unsigned long long)(t - t_ph); t_ph = t; }
+        ST_PH(2);
         // ---- D. claim, all members at once, tasks interleaved over the CTAs of the cluster
         int32_t *const cnt_cur = ccnt + (epoch & 1);
         {
@@ -1308,8 +1321,9 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             __syncwarp();
             drain(0, qn);
         }
-        if (tid == 0) { const long long t = clock64(); dbg[14] += (unsigned long long)(t - t_ph); t_ph = t; }
+        if (tid == 0) { const long long t = clock64(); dbg[14] += (unsigned long long)(t - t_ph); t_ph = t; t_f = t; }
         cluster_sync_all();                                  // 1: every claim and stamp of the round is in place
+        ST_PH(3);
         // ---- E. verdict inputs, every CTA for itself: who touched the members' vertices and the passed-over entries
         if (g < nsel) {
             const int len = S.len[g];
@@ -1332,6 +1346,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             else atomicMin(&S.gapbad[after], tid);           // nobody before it claimed it: the sequential loop would pick it
         }
         __syncthreads();
+        ST_PH(4);
         if (tid == 0) {
             int b = bid, p = pcur, stop_entry = nwin;
             unsigned acc = 0;
@@ -1366,6 +1381,7 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
             dbg[5] += nwin;
         }
         __syncthreads();
+        ST_PH(5);
         // ---- F. commit, whole cluster
         {
             const int ntouch = __ldcg(cnt_cur);
@@ -1413,10 +1429,13 @@ __global__ void __launch_bounds__(1024, 1) k_sample_tree_c(SampleArgs a, const i
         }
         cursor = win_end - keep;
         ++epoch;
+        ST_PH(6);
         cluster_sync_all();                                  // 2: commits visible before the next round reads the state
+        ST_PH(7);
     }
     if (tid == 0 && cr == 0) { a.comp_nb[c] = bid; a.comp_np[c] = pcur; }
-    if (tid == 0 && cr == 0 && c == 0) { dbg[15] = CL; for (int i = 0; i < 16; ++i) g_stb_stats[i] = dbg[i]; }
+    if (tid == 0 && cr == 0 && c == 0) { dbg[15] = CL; for (int i = 0; i < 16; ++i) g_stb_stats[i] = dbg[i]; for (int i = 0; i < 8; ++i) g_stc_phase[i] = ph[i]; }
+#undef ST_PH
     cluster_sync_all();
 }
 
@@ -1552,7 +1571,10 @@ extern "C" int st_sample_tree(const float *medial_pts, const float *radii, const
         int win = 128, scan_steps = SCAN_STEPS;      // tools/sample_sweep.py: 128 live entries per round were best on the bench tree (4.7 ms; 512: 6.0 ms)
         if (const char *e = getenv("ST_SAMPLE_WIN")) { int v = atoi(e); if (v >= 1 && v <= WIN) win = v; }
         if (const char *e = getenv("ST_SAMPLE_SCAN_STEPS")) { int v = atoi(e); if (v >= 1 && v <= 64) scan_steps = v; }
-        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo, win, scan_steps));
+        // members of a round are at least sep * max(radius) apart (a heuristic: it only decides how much of the round survives)
+        float sep = 1.f;      // tools/sample_sweep.py: 2.0 -> 158 rounds / 99 cut by a passed-over entry, 1.0 -> 112 / 19
+        if (const char *e = getenv("ST_SAMPLE_SEP")) { float v = (float)atof(e); if (v >= 0.f) sep = v; }
+        ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_c, a, jump_c, nt, stamp, tlist_all, binfo, win, scan_steps, sep));
     } else if (mode == 1) {
         ST_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k_sample_tree_b, a, jump_c, nt, stamp, tlist_all, binfo));
     } else {
@@ -1569,6 +1591,10 @@ extern "C" int st_debug_sample_iters(int *out_host) {
 }
 extern "C" int st_debug_sample_batch_stats(unsigned long long *out_host) {
     ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stb_stats, sizeof(unsigned long long) * 16));
+    return ST_OK;
+}
+extern "C" int st_debug_sample_round_phases(unsigned long long *out_host) {
+    ST_CHECK_CUDA(cudaMemcpyFromSymbol(out_host, g_stc_phase, sizeof(unsigned long long) * 8));
     return ST_OK;
 }
 extern "C" int st_debug_sample_stats(unsigned long long *out_host) {

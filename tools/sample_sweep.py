@@ -26,8 +26,9 @@ cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb)
 lib = _lib.load()
 lib.st_debug_sample_batch_stats.argtypes = [C.c_void_p]
 ref = None
-for win, steps, cl in ((128, 4, 16), (128, 4, 8), (128, 4, 4), (128, 4, 2), (96, 4, 16), (192, 4, 16), (64, 4, 8), (256, 4, 8)):
+for win, steps, cl, sep in ((128, 4, 16, 1.0), (128, 4, 16, 0.8), (128, 4, 16, 0.9), (128, 4, 16, 1.1), (192, 4, 16, 1.0), (96, 4, 16, 1.0)):
     if True:
+        os.environ["ST_SAMPLE_SEP"] = str(sep)
         os.environ["ST_SAMPLE_WIN"] = str(win)
         os.environ["ST_SAMPLE_SCAN_STEPS"] = str(steps)
         os.environ["ST_SAMPLE_CLUSTER"] = str(cl)
@@ -41,9 +42,14 @@ for win, steps, cl in ((128, 4, 16), (128, 4, 8), (128, 4, 4), (128, 4, 2), (96,
         _timing.enable(False)
         bst = (C.c_ulonglong * 16)()
         lib.st_debug_sample_batch_stats(bst)
+        phs = (C.c_ulonglong * 8)()
+        lib.st_debug_sample_round_phases.argtypes = [C.c_void_p]
+        lib.st_debug_sample_round_phases(phs)
+        print(json.dumps(dict(zip(["kc_B_select", "kc_C_routes", "kc_C_fill_windows", "kc_barrier1", "kc_E_inputs", "kc_verdict", "kc_F_commit", "kc_barrier2"],
+                                  [int(v) // 1000 for v in phs]))))
         dg = skeleton_digest(sk.skeletons)["topology"]
         ref = ref or dg
-        print(json.dumps({"win": win, "scan_steps": steps, "cluster": cl, "sample_tree_ms": round(ms, 3), "rounds": int(bst[0]), "batches": int(bst[2]),
+        print(json.dumps({"win": win, "sep": sep, "cluster": cl, "sample_tree_ms": round(ms, 3), "rounds": int(bst[0]), "batches": int(bst[2]),
                           "offered": int(bst[3]), "accepted": int(bst[4]), "cut_gap": int(bst[9]), "kcycles_A": int(bst[12]) // 1000,
                           "kcycles_BC": int(bst[13]) // 1000, "kcycles_D": int(bst[14]) // 1000, "kcycles_batches": int(bst[10]) // 1000,
                           "same_topology": dg == ref}), flush=True)
