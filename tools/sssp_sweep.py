@@ -24,12 +24,8 @@ pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0
                 prune_skeletons=True, min_skeleton_radius=0.01, min_skeleton_length=0.02, device=dev)
 tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
-KNOBS = ("ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
-settings = [{}]
-for d in ("0.045", "0.06", "0.09", "0.125", "0.18"):
-    for ps in ("16", "24", "32", "48", "64"):
-        settings.append({"ST_SSSP_DELTA": d, "ST_SSSP_PASSES": ps})
-settings.append({"ST_CC_PRELINK": "1"})
+KNOBS = ("ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
+settings = [{}, {"ST_CC_NO_SAMPLE": "1"}, {}]
 ref = None
 rows = []
 for s in settings:
