@@ -94,21 +94,24 @@ class Skeletonizer:
         with section("skel.regroup_csr"):
             dev = medial.device
             # rank of each vertex's component (-1 = dropped), then vertices grouped by rank, ascending id inside
-            rank_of_root = torch.full((n,), -1, dtype=torch.int64, device=dev)
-            rank_of_root[roots] = torch.arange(ncomp, device=dev)
-            vrank = rank_of_root[label.long()]
-            sel = torch.nonzero(vrank >= 0).flatten()
-            if ncomp == 1:
-                order = sel                                                   # one component: ascending ids as they are
-            else:                                                             # (16-bit keys: two radix passes instead of eight)
-                vs = vrank[sel]
+            if ncomp == 1:                                                    # a single tree: one component, ids as they are
+                order = torch.nonzero(label == roots[0]).flatten()
+                m = int(order.shape[0])
+                comp_off = torch.tensor([0, m], dtype=torch.int64, device=dev)
+                comp_of = torch.zeros(m, dtype=torch.int64, device=dev)
+            else:
+                rank_of_root = torch.full((n,), -1, dtype=torch.int64, device=dev)
+                rank_of_root[roots] = torch.arange(ncomp, device=dev)
+                vrank = rank_of_root[label.long()]
+                sel = torch.nonzero(vrank >= 0).flatten()
+                vs = vrank[sel]                                               # (16-bit keys: two radix passes instead of eight)
                 order = sel[torch.argsort(vs.to(torch.int16) if ncomp < 32768 else vs, stable=True)]      # new id -> old vertex id
-            m = int(order.shape[0])
+                m = int(order.shape[0])
+                comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
+                comp_off[1:] = torch.cumsum(sizes, 0)
+                comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
             new_id = torch.full((n,), -1, dtype=torch.int32, device=dev)
             new_id[order] = torch.arange(m, dtype=torch.int32, device=dev)
-            comp_off = torch.zeros(ncomp + 1, dtype=torch.int64, device=dev)
-            comp_off[1:] = torch.cumsum(sizes, 0)
-            comp_of = torch.repeat_interleave(torch.arange(ncomp, device=dev), sizes)
             sub_xyz = cloud.xyz[order]
             sub_medial = medial[order].contiguous()
             sub_radius = radius[order].contiguous()
@@ -125,7 +128,9 @@ class Skeletonizer:
             row_ptr, col, w = ops.csr_build(graph.edges, graph.edge_weights, m, vertex_map=vmap)
             # root of each component = first argmin of surface y (cloud.py:205-206)
             y = sub_xyz[:, 1].contiguous()
-            if ncomp <= 64:       # components are contiguous segments: a plain argmin per segment
+            if ncomp == 1:
+                src = torch.argmin(y).reshape(1)
+            elif ncomp <= 64:     # components are contiguous segments: a plain argmin per segment
                 off_l = comp_off.tolist()
                 src = torch.stack([torch.argmin(y[off_l[c]:off_l[c + 1]]) + off_l[c] for c in range(ncomp)])
             else:
