@@ -232,20 +232,12 @@ __global__ void __launch_bounds__(256) k_sssp(const int32_t *__restrict__ row_pt
     for (unsigned chunk = 0;; ++chunk) {
         bool consumed = false;
         for (int pass = 0; pass < npass; ++pass) {
-            // the counters of the warp's four groups in one round trip (the relaxations below have side effects the compiler
-            // will not move a load across: read one by one, an idle poll cost four dependent L2 latencies)
-            int cnts[SSSP_G];
-#pragma unroll
-            for (int k = 0; k < SSSP_G; ++k) {
-                const int v = ((w0 + k * nwarps) << 5) + lane;
-                cnts[k] = v < n ? __ldcg(dirty + v) : seen[k];
-            }
 #pragma unroll
             for (int k = 0; k < SSSP_G; ++k) {
                 const int g = w0 + k * nwarps;
                 if (g >= ngroups) continue;
                 const int v = (g << 5) + lane;
-                const int cnt = cnts[k];
+                const int cnt = v < n ? __ldcg(dirty + v) : seen[k];
                 const bool woke = cnt != seen[k] || pend[k] <= T;
                 seen[k] = cnt;
                 unsigned mask = __ballot_sync(0xffffffffu, woke);
