@@ -604,8 +604,8 @@ def test_connected_components_exact():
     assert sum(len(c) for c in comps) == len(med)
 
 
-@pytest.mark.parametrize("variant", ["cta-local", "cta-local-spatial", "cta-local-G8", "cta-local-threshold", "cta-local-1-poll", "registers", "large-graph",
-                                     "large-graph-flags"])
+@pytest.mark.parametrize("variant", ["cta-local", "cta-local-spatial", "cta-local-G8", "cta-local-threshold", "cta-local-1-poll", "registers",
+                                     "registers-one-vertex-at-a-time", "large-graph", "large-graph-flags"])
 def test_sssp_and_tree_distances_exact(variant, monkeypatch):
     """Every relaxation schedule reaches the same fp32 fixed point and predecessors: CTA-local propagation in shared memory
     with barrier-free termination (k_sssp_blob, default) in the caller's numbering or with the graph renumbered in spatial
@@ -617,6 +617,8 @@ def test_sssp_and_tree_distances_exact(variant, monkeypatch):
         monkeypatch.setenv("ST_SSSP_FLAGS", "1")
     if variant.startswith("cta-local"):
         monkeypatch.setenv("ST_SSSP_LOCAL", "1")
+    if variant == "registers-one-vertex-at-a-time":
+        monkeypatch.setenv("ST_SSSP_PAIRS", "0")
     if variant == "cta-local-G8":
         monkeypatch.setenv("ST_SSSP_LOCAL_G", "8")
     if variant == "cta-local-threshold":          # per-CTA distance-ordered acceptance (parked candidates)

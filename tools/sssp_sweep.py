@@ -24,8 +24,9 @@ pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0
                 prune_skeletons=True, min_skeleton_radius=0.01, min_skeleton_length=0.02, device=dev)
 tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
-KNOBS = ("ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
-settings = [{}, {"ST_CC_NO_SAMPLE": "1"}, {}]
+KNOBS = ("ST_SSSP_PAIRS", "ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
+settings = [{}, {"ST_SSSP_PAIRS": "1"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_PASSES": "48"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_PASSES": "96"},
+            {"ST_SSSP_PAIRS": "1", "ST_SSSP_DELTA": "0.125"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_DELTA": "0.25"}, {}]
 ref = None
 rows = []
 for s in settings:
