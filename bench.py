@@ -324,7 +324,11 @@ def run_b200(args):
     for _ in range(args.warmup):
         step(True)
     import gc
+    # a full collection now, and what survives it (the interpreter's ~10^6 module-level objects) out of the collector's sight:
+    # a generation-2 pass over them costs 50-100 ms, and at N ranks in lockstep every rank's pause is everybody's pause
+    # (seen as 53-102 ms steps in an 8-GPU run, profiles/README.md)
     gc.collect()
+    gc.freeze()
     clocks.mark()
     dev_ms, wall_ms, sk, g, steps_res = timed(True, args.steps)
     stage_t = dict(pipe.timings)
