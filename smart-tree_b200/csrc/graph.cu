@@ -79,7 +79,8 @@ extern "C" int st_connected_components(const int32_t *edges, int64_t n_edges, in
         // Sampled first (every 8th edge), compressed, then all edges with the same-parent shortcut (the idea of Afforest,
         // Sutton et al. 2018): a tree cloud is one giant component, after the sample nearly every vertex already points at
         // its root.  Bench graph (245 k vertices, 3.9 M edges): 512 us for one plain pass -> see profiles/README.md.
-        const int sample = getenv("ST_CC_NO_SAMPLE") ? 0 : 8;
+        int sample = getenv("ST_CC_NO_SAMPLE") ? 0 : 8;
+        if (const char *e = getenv("ST_CC_SAMPLE")) { int v = atoi(e); if (v >= 2 && v <= 1024) sample = v; }
         if (sample && n_edges >= 4096) {
             k_cc_hook<<<(unsigned)cdiv(cdiv(n_edges, sample), 256), 256, 0, s>>>(edges, n_edges, label, sample, 0);
             ST_CHECK_LAUNCH();

@@ -192,8 +192,9 @@ __global__ void __launch_bounds__(1024) k_finish(FinishArgs a) {
             const int t1 = prow + bmeta[4 * pb + 1];
             float best = FLT_MAX * 2.f, bx = 0, by = 0, bz = 0;     // +inf
             int bidx = INT_MAX;
+#pragma unroll 4      // (the loads of four segments in flight: the polyline was written by this kernel and comes from L2)
             for (int m = t0 + lane; m < t1; m += 32) {
-                const float4 A = *(const float4 *)(nd + 4 * (size_t)m), B = *(const float4 *)(nd + 4 * (size_t)m + 4);
+                const float4 A = __ldcg((const float4 *)(nd + 4 * (size_t)m)), B = __ldcg((const float4 *)(nd + 4 * (size_t)m + 4));
                 float abx = B.x - A.x, aby = B.y - A.y, abz = B.z - A.z;
                 float apx = px - A.x, apy = py - A.y, apz = pz - A.z;
                 float t = fminf(fmaxf((apx * abx + apy * aby + apz * abz) / (abx * abx + aby * aby + abz * abz), 0.f), 1.f);

@@ -24,9 +24,8 @@ pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0
                 prune_skeletons=True, min_skeleton_radius=0.01, min_skeleton_length=0.02, device=dev)
 tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
-KNOBS = ("ST_SSSP_PAIRS", "ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
-settings = [{}, {"ST_SSSP_PAIRS": "1"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_PASSES": "48"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_PASSES": "96"},
-            {"ST_SSSP_PAIRS": "1", "ST_SSSP_DELTA": "0.125"}, {"ST_SSSP_PAIRS": "1", "ST_SSSP_DELTA": "0.25"}, {}]
+KNOBS = ("ST_CC_SAMPLE", "ST_SSSP_PAIRS", "ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
+settings = [{}, {"ST_CC_SAMPLE": "4"}, {"ST_CC_SAMPLE": "16"}, {"ST_CC_SAMPLE": "32"}, {"ST_CC_SAMPLE": "64"}, {}]
 ref = None
 rows = []
 for s in settings:
@@ -40,7 +39,7 @@ for s in settings:
     for _ in range(5):
         pipe.process_cloud(cloud=cloud)
     torch.cuda.synchronize()
-    med = {k: round(float(np.median(v)), 3) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.components")}
+    med = {k: round(float(np.median(v)), 3) for k, v in _timing.SAMPLES.items() if k in ("skel.sssp", "skel.components", "skel.emit")}
     _timing.enable(False)
     d = pipe.skeletonizer.last["dist"].clone()
     p = pipe.skeletonizer.last["pred"].clone()
