@@ -7,7 +7,10 @@
 One "step" = one pass of the hot path over one batch of synthetic input per rank:
   tree configs (c2, c3, c4): Pipeline.process_cloud on one synthetic tree cloud per rank (CentreCloud -> block tiling ->
       voxelise -> sparse UNet -> class filter -> skeletonise -> prune / repair / smooth), then (N > 1) ONE NCCL
-      all-gather of the packed skeletons.  Rank r gets the tree with seed seed0 + r: weak scaling, distinct trees.
+      all-gather of the packed skeletons.  Weak scaling.  c2 / c4 (BASELINE configs[1] / [3]: ONE named tree): every rank
+      processes a replica of that tree -- per-GPU work is fixed, as weak scaling means.  c3 (configs[2]: a batch of distinct
+      trees): rank r gets the tree with seed seed0 + r; the seeds differ by up to 1.8x in voxels (seed 0: 495 k, seed 1:
+      819 k at 1 M points), so the step of c3 ends with its largest tree.  --distinct-trees forces distinct seeds for any config.
   plot config (c5): Pipeline.process_plot_sharded on one forest plot held by every rank -- blocks dealt round-robin,
       all-gather of the labelled voxels, components dealt round-robin, all-gather of the packed skeletons.  Strong scaling.
 Default = c2 = BASELINE.json configs[1] (noble-elevator-58, 1 M-point tree, 1 cm voxels), the configuration the metric is
@@ -34,11 +37,11 @@ UNIT = "points/s"
 # BASELINE.json configs[1..4] (SURVEY section 8d "Synthetic inputs")
 CONFIGS = {
     "c2": dict(label="BASELINE.json configs[1]", weights="noble-elevator-58", points=1_000_000, voxel=0.01, block=4.0, buffer=0.4,
-               seed0=0, kind="tree"),
+               seed0=0, kind="tree", distinct=False),
     "c3": dict(label="BASELINE.json configs[2]", weights="noble-elevator-58", points=500_000, voxel=0.01, block=4.0, buffer=0.4,
-               seed0=0, kind="tree"),
+               seed0=0, kind="tree", distinct=True),
     "c4": dict(label="BASELINE.json configs[3]", weights="peach-forest-65", points=4_000_000, voxel=0.005, block=4.0, buffer=0.4,
-               seed0=1, kind="tree"),
+               seed0=1, kind="tree", distinct=False),
     "c5": dict(label="BASELINE.json configs[4]", weights="noble-elevator-58", points=500_000, voxel=0.01, block=0.64, buffer=0.4,
                seed0=0, kind="plot", trees=40),
 }
@@ -57,6 +60,8 @@ def parse():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--points", type=int, default=None, help="points per tree (default: the config's)")
     ap.add_argument("--voxel", type=float, default=None)
+    ap.add_argument("--seed0", type=int, default=None, help="seed of the tree (default: the config's)")
+    ap.add_argument("--distinct-trees", action="store_true", help="rank r processes the tree with seed seed0 + r (default for c3)")
     ap.add_argument("--plot-trees", type=int, default=None, help="c5: trees in the plot (default 40 = 20 M points)")
     ap.add_argument("--cpu-sample-points", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -69,6 +74,10 @@ def parse():
         cfg["points"] = args.points
     if args.voxel is not None:
         cfg["voxel"] = args.voxel
+    if args.seed0 is not None:
+        cfg["seed0"] = args.seed0
+    if args.distinct_trees:
+        cfg["distinct"] = True
     if args.plot_trees is not None and cfg["kind"] == "plot":
         cfg["trees"] = args.plot_trees
     args.cfg = cfg
@@ -87,8 +96,12 @@ def workload_config(args, world, points_override=None):
     else:
         what = (f"{c['weights']} UNet inference + skeleton, one {pts}-point synthetic tube tree per GPU, {c['voxel']} m voxels "
                 f"({c['label']})")
-        par = f"tree-sharded x{world} (rank r: seed {c['seed0']}+r), one NCCL all-gather of packed skeletons"
-        seeds = f"{c['seed0']}..{c['seed0'] + world - 1}"
+        if c.get("distinct"):
+            par = f"tree-sharded x{world} (rank r: seed {c['seed0']}+r), one NCCL all-gather of packed skeletons"
+            seeds = f"{c['seed0']}..{c['seed0'] + world - 1}"
+        else:
+            par = f"tree-sharded x{world} (every rank: a replica of the seed-{c['seed0']} tree), one NCCL all-gather of packed skeletons"
+            seeds = f"{c['seed0']} on every rank"
         total = pts * world
     return {"workload": what, "config": args.config, "points_per_tree": pts, "total_points": total, "voxel_size": c["voxel"],
             "block_size": c["block"], "buffer_size": c["buffer"], "K": 16, "weights": c["weights"], "tree_seeds": seeds,
@@ -267,8 +280,8 @@ def run_b200(args):
     if plot:      # every rank holds the whole plot (strong scaling)
         tr = synth.make_forest(range(cfg["seed0"], cfg["seed0"] + cfg["trees"]), cfg["points"], pitch=5.0, cols=8)
         total_points = int(tr.xyz.shape[0])
-    else:         # weak scaling: one tree per rank, seeds seed0 .. seed0 + world - 1
-        tr = synth.make_tree(cfg["seed0"] + rank, cfg["points"])
+    else:         # weak scaling: one tree per rank -- replicas of the named tree, or seeds seed0 .. seed0 + world - 1 (c3)
+        tr = synth.make_tree(cfg["seed0"] + (rank if cfg.get("distinct") else 0), cfg["points"])
         total_points = cfg["points"] * world
     h_xyz = torch.from_numpy(tr.xyz).pin_memory()
     h_rgb = torch.from_numpy(tr.rgb).pin_memory()

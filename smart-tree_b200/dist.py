@@ -131,24 +131,33 @@ class GatheredPacked:
     """Every rank's packed skeleton buffer after ONE all-gather (device-resident int32 [world, cap]); host copy and the
     reference's object model only on demand."""
 
-    def __init__(self, buf, world, cap=None, redo=None):
+    def __init__(self, buf, world, cap=None, redo=None, works=None):
         self.buf, self.world = buf, world
         self.cap = int(buf.shape[1]) if cap is None else int(cap)
         self._redo = redo
+        self._works = works if works is not None else []
         self._host = None
         self.host_bytes = 0
+
+    def wait(self):
+        """Join the (asynchronous) collective: afterwards `buf` may be read on the current stream."""
+        while self._works:
+            self._works.pop(0).wait()
+        return self
 
     def to_host(self):
         """Read the `world` length words, then ONE device->host copy of the used prefixes (not of the capacity-padded
         buffer) -> list of (unit, PackedSkeletons) per rank.  Collective if a rank's result overflowed (gather_packed)."""
         if self._host is None:
             from .data_types.packed import PackedSkeletons
+            self.wait()
             lens = [int(v) for v in self.buf[:, 0].cpu().tolist()]
             if max(lens) > self.cap:
                 if self._redo is None:
                     raise RuntimeError("gathered skeleton buffer overflowed and cannot be re-exchanged")
                 self.buf = self._redo(max(lens))
                 self.cap = max(lens)
+                self.wait()
             flat = torch.cat([self.buf[r, :max(lens[r], 8)] for r in range(self.world)]).cpu().numpy()
             self.host_bytes = int(flat.nbytes + 4 * self.world)
             out, o = [], 0
@@ -207,13 +216,16 @@ def gather_packed(local: DisjointTreeSkeleton, unit: int, capacity: int = 1 << 2
             return send.unsqueeze(0)
         recv = torch.empty((world, cap), dtype=torch.int32, device=dev)
         if dist.get_backend() == "nccl":
+            # (async_op=True, the compute stream not waiting for the collective, was measured and bought nothing: the pipeline's
+            # stage timers synchronise the device, and NCCL's kernel shares the SMs with the resident-grid SSSP launch)
             dist.all_gather_into_tensor(recv, send)
         else:
             dist.all_gather(list(recv.unbind(0)), send)
         return recv
 
+    works = []
     cap = max(int(capacity), 16)
-    return GatheredPacked(exchange(cap), world, cap, exchange)
+    return GatheredPacked(exchange(cap), world, cap, exchange, works)
 
 
 # ---------------------------------------------------------------------------------------------- labelled voxels (plots)
