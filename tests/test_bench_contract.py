@@ -34,3 +34,29 @@ def test_b200_arm_fails_loudly_without_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
                        timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_workload_config_names_replicas_and_distinct_trees():
+    """c2 / c4 name one tree: at N ranks every rank runs a replica (fixed per-GPU work); c3 is a batch of distinct trees."""
+    sys.path.insert(0, ROOT)
+    import importlib
+    bench = importlib.import_module("bench")
+    old = sys.argv
+    try:
+        sys.argv = ["bench.py", "--gpus", "8"]
+        a = bench.parse()
+        c = bench.workload_config(a, 8)
+        assert c["config"] == "c2" and c["tree_seeds"] == "0 on every rank" and c["total_points"] == 8_000_000 and "replica" in c["parallelism"]
+        sys.argv = ["bench.py", "--gpus", "8", "--config", "c3"]
+        a = bench.parse()
+        c = bench.workload_config(a, 8)
+        assert c["tree_seeds"] == "0..7" and c["points_per_tree"] == 500_000 and c["total_points"] == 4_000_000
+        sys.argv = ["bench.py", "--gpus", "2", "--distinct-trees", "--seed0", "3"]
+        a = bench.parse()
+        assert bench.workload_config(a, 2)["tree_seeds"] == "3..4"
+        sys.argv = ["bench.py", "--config", "c5"]
+        a = bench.parse()
+        c = bench.workload_config(a, 8)
+        assert c["total_points"] == 20_000_000 and c["block_size"] == 0.64
+    finally:
+        sys.argv = old
