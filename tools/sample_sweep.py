@@ -26,7 +26,8 @@ cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb)
 lib = _lib.load()
 lib.st_debug_sample_batch_stats.argtypes = [C.c_void_p]
 ref = None
-for win, steps, cl, sep in ((128, 4, 16, 1.0), (128, 4, 16, 0.8), (128, 4, 16, 0.9), (128, 4, 16, 1.1), (192, 4, 16, 1.0), (96, 4, 16, 1.0)):
+for win, steps, cl, sep in ((128, 4, 16, 1.0), (128, 4, 16, 2.0), (128, 4, 16, 1.5), (128, 4, 16, 0.8), (64, 4, 16, 1.0), (256, 4, 16, 1.0), (512, 4, 16, 1.0),
+                           (128, 4, 8, 1.0), (128, 4, 4, 1.0)):
     if True:
         os.environ["ST_SAMPLE_SEP"] = str(sep)
         os.environ["ST_SAMPLE_WIN"] = str(win)

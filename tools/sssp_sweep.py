@@ -25,7 +25,12 @@ pipe = Pipeline(AugmentationPipeline([CentreCloud()]), ModelInference(None, W, 0
 tr = synth.make_tree(0, int(os.environ.get("POINTS", 1_000_000)))
 cloud = Cloud(xyz=torch.from_numpy(tr.xyz).to(dev), rgb=torch.from_numpy(tr.rgb).to(dev))
 KNOBS = ("ST_CC_SAMPLE", "ST_SSSP_PAIRS", "ST_CC_NO_SAMPLE", "ST_CC_PRELINK", "ST_SSSP_BLOB_FLAGS", "ST_SSSP_LOCAL", "ST_SSSP_PASSES", "ST_SSSP_DELTA", "ST_SSSP_NO_LOCAL", "ST_SSSP_LOCAL_G", "ST_SSSP_NLOCAL", "ST_SSSP_BLOB_DELTA", "ST_SSSP_SPATIAL")
-settings = [{}, {"ST_CC_SAMPLE": "4"}, {"ST_CC_SAMPLE": "16"}, {"ST_CC_SAMPLE": "32"}, {"ST_CC_SAMPLE": "64"}, {}]
+# default: the 2-D sweep of threshold step x polls per barrier behind profiles/sssp_schedule_sweep_r2.txt, then the variants
+settings = [{}]
+for d in ("0.06", "0.09", "0.125", "0.18", "0.25"):
+    for ps in ("16", "32", "48", "64", "96"):
+        settings.append({"ST_SSSP_DELTA": d, "ST_SSSP_PASSES": ps})
+settings += [{"ST_SSSP_PAIRS": "0"}, {"ST_SSSP_SPATIAL": "1"}, {"ST_SSSP_LOCAL": "1"}, {"ST_CC_NO_SAMPLE": "1"}, {"ST_CC_SAMPLE": "16"}]
 ref = None
 rows = []
 for s in settings:
