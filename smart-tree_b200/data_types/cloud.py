@@ -59,8 +59,9 @@ class Cloud:
         classes = torch.as_tensor(classes, device=self.class_l.device)
         return self.filter(torch.isin(self.class_l, classes).view(-1))
 
-    def to_device(self, device) -> "Cloud":
-        return self._map(lambda t: t.to(device))
+    def to_device(self, device, non_blocking: bool = False) -> "Cloud":
+        """non_blocking: asynchronous host->device copies (effective for pinned host tensors: load_cloud(pin_memory=True))."""
+        return self._map(lambda t: t.to(device, non_blocking=non_blocking))
 
     def cpu(self) -> "Cloud":
         return self.to_device(torch.device("cpu"))

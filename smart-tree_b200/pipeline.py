@@ -41,12 +41,12 @@ class Pipeline:
         self.labelled_cloud = None
 
     def process_cloud(self, path: Path = None, cloud: Cloud = None) -> DisjointTreeSkeleton:
-        cloud = load_cloud(Path(path)) if path is not None else cloud
+        cloud = load_cloud(Path(path), pin_memory=self.device.type == "cuda") if path is not None else cloud      # pinned: the copy below is asynchronous
         t = {}
         sync = (lambda: torch.cuda.synchronize(self.device)) if self.device.type == "cuda" else (lambda: None)
         t0 = time.perf_counter()
         with section("pipe.preprocess"):
-            cloud = cloud.to_device(self.device)
+            cloud = cloud.to_device(self.device, non_blocking=True)
             cloud = self.preprocessing(cloud)
         sync(); t["preprocess"] = time.perf_counter() - t0; t0 = time.perf_counter()
         lc: Cloud = self.model_inference.forward(cloud).to_device(self.device)      # pipeline.py:63

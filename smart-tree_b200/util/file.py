@@ -51,14 +51,22 @@ def _read_ply(path):
     return xyz, rgb
 
 
-def load_cloud(path: Path) -> Cloud:
+def load_cloud(path: Path, pin_memory: bool = False) -> Cloud:
+    """pin_memory: page-lock the host tensors (when a CUDA runtime is present) so that `cloud.to_device(dev,
+    non_blocking=True)` is an asynchronous copy -- what the pipeline's loader wants."""
     path = Path(path)
     if path.suffix == ".npz":
-        return Cloud.from_numpy(**np.load(path))
-    if path.suffix == ".ply":
+        cloud = Cloud.from_numpy(**np.load(path))
+    elif path.suffix == ".ply":
         xyz, rgb = _read_ply(path)
-        return Cloud.from_numpy(xyz=xyz, rgb=rgb)
-    raise ValueError(f"unsupported cloud format {path.suffix} (supported: .npz, .ply)")
+        cloud = Cloud.from_numpy(xyz=xyz, rgb=rgb)
+    else:
+        raise ValueError(f"unsupported cloud format {path.suffix} (supported: .npz, .ply)")
+    if pin_memory:
+        import torch
+        if torch.cuda.is_available():
+            cloud = cloud.pin_memory()
+    return cloud
 
 
 def skeleton_arrays(skeleton: TreeSkeleton) -> dict:

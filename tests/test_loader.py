@@ -84,3 +84,20 @@ def test_skeleton_npz_schema_round_trip(tmp_path):
         assert got.parent_id == ref.parent_id and torch.equal(got.xyz, ref.xyz) and torch.equal(got.radii, ref.radii)
     empty = skeleton_arrays(TreeSkeleton(0, {}))
     assert empty["skeleton_xyz"].shape == (0, 3) and empty["branch_id"].shape == (0,)
+
+
+def test_load_cloud_pin_memory_flag_is_harmless_without_cuda(tmp_path):
+    """load_cloud(pin_memory=True) returns the same cloud (pinned only where a CUDA runtime exists); to_device accepts non_blocking."""
+    import numpy as np
+    import torch
+    from smart_tree_b200.util.file import load_cloud
+    rng = np.random.default_rng(0)
+    xyz = rng.standard_normal((100, 3)).astype(np.float32)
+    rgb = rng.uniform(0, 1, (100, 3)).astype(np.float32)
+    p = tmp_path / "c.npz"
+    np.savez(p, xyz=xyz, rgb=rgb)
+    a, b = load_cloud(p), load_cloud(p, pin_memory=True)
+    assert torch.equal(a.xyz, b.xyz) and torch.equal(a.rgb, b.rgb)
+    assert b.xyz.is_pinned() == torch.cuda.is_available()
+    c = b.to_device(torch.device("cpu"), non_blocking=True)
+    assert torch.equal(c.xyz, a.xyz)
